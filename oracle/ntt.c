@@ -1,0 +1,221 @@
+/*
+ * oracle/ntt.c -- TEST INFRASTRUCTURE ONLY (CPU oracle).  See ntt.h for the
+ * definition being restated and the reference lines it follows.
+ */
+#include "ntt.h"
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef unsigned __int128 u128;
+
+/* ------------------------------------------------------------ fields -- */
+
+#define GL_P 0xffffffff00000001ULL
+
+static inline uint64_t gl_add(uint64_t a, uint64_t b)
+{
+    uint64_t s = a + b;
+    if (s < a || s >= GL_P)
+        s -= GL_P;
+    return s;
+}
+static inline uint64_t gl_sub(uint64_t a, uint64_t b) { return a >= b ? a - b : a + (GL_P - b); }
+static inline uint64_t gl_mul(uint64_t a, uint64_t b)
+{
+    /* 2^64 = 2^32 - 1, 2^96 = -1 (mod p) */
+    u128 x = (u128)a * b;
+    uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
+    uint64_t hh = hi >> 32, hl = hi & 0xffffffffULL;
+    uint64_t t = gl_sub(lo >= GL_P ? lo - GL_P : lo, hh);
+    return gl_add(t, hl * 0xffffffffULL);
+}
+uint64_t oracle_gl64_mul(uint64_t a, uint64_t b) { return gl_mul(a % GL_P, b % GL_P); }
+
+#define BB_P 0x78000001U
+static inline uint32_t bb_add(uint32_t a, uint32_t b)
+{
+    uint32_t s = a + b;
+    return s >= BB_P ? s - BB_P : s;
+}
+static inline uint32_t bb_sub(uint32_t a, uint32_t b) { return a >= b ? a - b : a + (BB_P - b); }
+static inline uint32_t bb_mul(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b % BB_P); }
+
+static uint64_t gl_pow(uint64_t b, uint64_t e)
+{
+    uint64_t r = 1;
+    for (; e; e >>= 1, b = gl_mul(b, b))
+        if (e & 1)
+            r = gl_mul(r, b);
+    return r;
+}
+static uint32_t bb_pow(uint32_t b, uint64_t e)
+{
+    uint32_t r = 1;
+    for (; e; e >>= 1, b = bb_mul(b, b))
+        if (e & 1)
+            r = bb_mul(r, b);
+    return r;
+}
+
+uint64_t oracle_gl64_root(unsigned lg_n, int inverse)
+{
+    uint64_t w = gl_pow(7, (GL_P - 1) >> 32);          /* primitive 2^32-th root */
+    for (unsigned i = 32; i > lg_n; i--)
+        w = gl_mul(w, w);
+    return inverse ? gl_pow(w, GL_P - 2) : w;
+}
+uint32_t oracle_bb31_root(unsigned lg_n, int inverse)
+{
+    uint32_t w = 137;                                  /* primitive 2^27-th root */
+    for (unsigned i = 27; i > lg_n; i--)
+        w = bb_mul(w, w);
+    return inverse ? bb_pow(w, BB_P - 2) : w;
+}
+
+static inline size_t bitrev(size_t i, unsigned lg)
+{
+    size_t r = 0;
+    for (unsigned b = 0; b < lg; b++)
+        r |= ((i >> b) & 1) << (lg - 1 - b);
+    return r;
+}
+
+/* ------------------------------------------------- generic by macro -- */
+
+#define NTT_IMPL(NAME, T, ADD, SUB, MUL, POW, ROOT, GEN, PM2, MAXLG, REDUCE)                   \
+    typedef struct {                                                                           \
+        T *a;                                                                                  \
+        const T *tw;                                                                           \
+        size_t n, half, lo, hi;                                                                \
+    } NAME##_job;                                                                              \
+    static void *NAME##_stage(void *arg)                                                       \
+    {                                                                                          \
+        NAME##_job *j = arg;                                                                   \
+        size_t half = j->half, step = j->n / (2 * half);                                       \
+        for (size_t b = j->lo; b < j->hi; b++) {                                               \
+            size_t blk = b / half, k = b % half, i0 = blk * 2 * half + k;                      \
+            T u = j->a[i0], v = MUL(j->a[i0 + half], j->tw[k * step]);                         \
+            j->a[i0] = ADD(u, v);                                                              \
+            j->a[i0 + half] = SUB(u, v);                                                       \
+        }                                                                                      \
+        return NULL;                                                                           \
+    }                                                                                          \
+    /* natural in, natural out, X[k] = sum x[j] w^(jk) */                                      \
+    static void NAME##_fast(T *a, unsigned lg, T w, int nthreads)                              \
+    {                                                                                          \
+        size_t n = (size_t)1 << lg;                                                            \
+        for (size_t i = 0; i < n; i++) {                                                       \
+            size_t r = bitrev(i, lg);                                                          \
+            if (r > i) {                                                                       \
+                T t = a[i];                                                                    \
+                a[i] = a[r];                                                                   \
+                a[r] = t;                                                                      \
+            }                                                                                  \
+        }                                                                                      \
+        T *tw = malloc(sizeof(T) * (n / 2 ? n / 2 : 1));                                       \
+        tw[0] = 1;                                                                             \
+        for (size_t i = 1; i < n / 2; i++)                                                     \
+            tw[i] = MUL(tw[i - 1], w);                                                         \
+        if (nthreads < 1)                                                                      \
+            nthreads = 1;                                                                      \
+        if (n < 4096)                                                                          \
+            nthreads = 1;                                                                      \
+        pthread_t th[64];                                                                      \
+        NAME##_job jobs[64];                                                                   \
+        if (nthreads > 64)                                                                     \
+            nthreads = 64;                                                                     \
+        for (size_t half = 1; half < n; half <<= 1) {                                          \
+            size_t total = n / 2, per = (total + nthreads - 1) / nthreads;                     \
+            for (int t = 0; t < nthreads; t++) {                                               \
+                size_t lo = t * per, hi = lo + per > total ? total : lo + per;                 \
+                if (lo > total)                                                                \
+                    lo = total;                                                                \
+                jobs[t] = (NAME##_job){a, tw, n, half, lo, hi};                                \
+                if (nthreads == 1)                                                             \
+                    NAME##_stage(&jobs[t]);                                                    \
+                else                                                                           \
+                    pthread_create(&th[t], NULL, NAME##_stage, &jobs[t]);                      \
+            }                                                                                  \
+            if (nthreads > 1)                                                                  \
+                for (int t = 0; t < nthreads; t++)                                             \
+                    pthread_join(th[t], NULL);                                                 \
+        }                                                                                      \
+        free(tw);                                                                              \
+    }                                                                                          \
+    static void NAME##_dft(T *a, unsigned lg, T w)                                             \
+    {                                                                                          \
+        size_t n = (size_t)1 << lg;                                                            \
+        T *out = malloc(sizeof(T) * n), *pw = malloc(sizeof(T) * n);                           \
+        pw[0] = 1;                                                                             \
+        for (size_t i = 1; i < n; i++)                                                         \
+            pw[i] = MUL(pw[i - 1], w);                                                         \
+        for (size_t k = 0; k < n; k++) {                                                       \
+            T acc = 0;                                                                         \
+            for (size_t j = 0; j < n; j++)                                                     \
+                acc = ADD(acc, MUL(a[j], pw[(j * k) & (n - 1)]));                              \
+            out[k] = acc;                                                                      \
+        }                                                                                      \
+        memcpy(a, out, sizeof(T) * n);                                                         \
+        free(out);                                                                             \
+        free(pw);                                                                              \
+    }                                                                                          \
+    int NAME(T *a, unsigned lg, int order, int direction, int type, int algo, int nthreads)    \
+    {                                                                                          \
+        if (lg == 0)                                                                           \
+            return 0;                                                                          \
+        if (lg > MAXLG)                                                                        \
+            return -1;                                                                         \
+        size_t n = (size_t)1 << lg;                                                            \
+        for (size_t i = 0; i < n; i++)                                                         \
+            a[i] = REDUCE(a[i]);                                                               \
+        int in_rev = order == ORACLE_RN || order == ORACLE_RR;                                 \
+        int out_rev = order == ORACLE_NR || order == ORACLE_RR;                                \
+        if (in_rev)                                                                            \
+            for (size_t i = 0; i < n; i++) {                                                   \
+                size_t r = bitrev(i, lg);                                                      \
+                if (r > i) {                                                                   \
+                    T t = a[i];                                                                \
+                    a[i] = a[r];                                                               \
+                    a[r] = t;                                                                  \
+                }                                                                              \
+            }                                                                                  \
+        if (!direction && type) {                                                              \
+            T g = GEN, pw = 1;                                                                 \
+            for (size_t i = 0; i < n; i++, pw = MUL(pw, g))                                    \
+                a[i] = MUL(a[i], pw);                                                          \
+        }                                                                                      \
+        T w = ROOT(lg, direction);                                                             \
+        if (algo == 1)                                                                         \
+            NAME##_dft(a, lg, w);                                                              \
+        else                                                                                   \
+            NAME##_fast(a, lg, w, nthreads);                                                   \
+        if (direction) {                                                                       \
+            T ninv = POW(POW(2, PM2), lg);             /* 2^-lg */                              \
+            for (size_t i = 0; i < n; i++)                                                     \
+                a[i] = MUL(a[i], ninv);                                                        \
+            if (type) {                                                                        \
+                T gi = POW(GEN, PM2), pw = 1;                                                  \
+                for (size_t i = 0; i < n; i++, pw = MUL(pw, gi))                               \
+                    a[i] = MUL(a[i], pw);                                                      \
+            }                                                                                  \
+        }                                                                                      \
+        if (out_rev)                                                                           \
+            for (size_t i = 0; i < n; i++) {                                                   \
+                size_t r = bitrev(i, lg);                                                      \
+                if (r > i) {                                                                   \
+                    T t = a[i];                                                                \
+                    a[i] = a[r];                                                               \
+                    a[r] = t;                                                                  \
+                }                                                                              \
+            }                                                                                  \
+        return 0;                                                                              \
+    }
+
+#define GL_REDUCE(x) ((x) >= GL_P ? (x) - GL_P : (x))
+#define BB_REDUCE(x) ((x) % BB_P)
+
+NTT_IMPL(oracle_ntt_gl64, uint64_t, gl_add, gl_sub, gl_mul, gl_pow, oracle_gl64_root, 7,
+         GL_P - 2, 32, GL_REDUCE)
+NTT_IMPL(oracle_ntt_bb31, uint32_t, bb_add, bb_sub, bb_mul, bb_pow, oracle_bb31_root, 3,
+         BB_P - 2, 27, BB_REDUCE)

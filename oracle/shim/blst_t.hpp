@@ -1,0 +1,228 @@
+/*
+ * oracle/shim/blst_t.hpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Stand-in for blst's src/blst_t.hpp (crate blst ~0.3.11, not vendored under
+ * /root/reference).  It provides exactly the host-field interface the
+ * reference's own headers consume (ff/bls12-381.hpp:91-139, ec/*.hpp,
+ * msm/pippenger.hpp, msm/pippenger.cuh host side) so that those headers
+ * compile UNMODIFIED from where they lie; see oracle/Makefile.
+ * Arithmetic: portable word-serial Montgomery multiplication on 64-bit limbs
+ * (no blst assembly), so CPU timings taken through this shim are "sppark's
+ * algorithm on portable arithmetic".
+ */
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+
+typedef uint64_t limb_t;
+typedef limb_t vec256[4];
+typedef limb_t vec384[6];
+#define TO_LIMB_T(x) x
+
+namespace shim_detail {
+typedef unsigned __int128 u128;
+
+template<size_t N> static inline bool geq(const limb_t* a, const limb_t* m)
+{
+    for (size_t i = N; i--;)
+        if (a[i] != m[i])
+            return a[i] > m[i];
+    return true;
+}
+template<size_t N> static inline void sub_n(limb_t* a, const limb_t* m)
+{
+    limb_t br = 0;
+    for (size_t i = 0; i < N; i++) {
+        u128 t = (u128)a[i] - m[i] - br;
+        a[i] = (limb_t)t;
+        br = (limb_t)(t >> 64) & 1;
+    }
+}
+template<size_t N> static inline void add_n(limb_t* a, const limb_t* m)
+{
+    limb_t c = 0;
+    for (size_t i = 0; i < N; i++) {
+        u128 t = (u128)a[i] + m[i] + c;
+        a[i] = (limb_t)t;
+        c = (limb_t)(t >> 64);
+    }
+}
+}  // namespace shim_detail
+
+template<size_t NBITS, size_t N, const limb_t* MOD, limb_t M0, const limb_t* RR,
+         const limb_t* ONE>
+class shim_field_t {
+    limb_t v[N];
+    typedef shim_detail::u128 u128;
+
+public:
+    static const size_t nbits = NBITS;
+    static constexpr size_t bit_length() { return NBITS; }
+    static const unsigned degree = 1;
+    using mem_t = shim_field_t;
+    typedef unsigned char pow_t[(NBITS + 7) / 8];
+
+    shim_field_t() {}
+    shim_field_t(const limb_t* p) { memcpy(v, p, sizeof(v)); }
+
+    limb_t& operator[](size_t i) { return v[i]; }
+    const limb_t& operator[](size_t i) const { return v[i]; }
+
+    static shim_field_t one(bool or_zero = false)
+    {
+        shim_field_t r;
+        for (size_t i = 0; i < N; i++)
+            r.v[i] = or_zero ? 0 : ONE[i];
+        return r;
+    }
+    bool is_zero() const
+    {
+        limb_t a = 0;
+        for (size_t i = 0; i < N; i++)
+            a |= v[i];
+        return a == 0;
+    }
+    void zero() { memset(v, 0, sizeof(v)); }
+
+    shim_field_t& operator+=(const shim_field_t& b)
+    {
+        limb_t c = 0;
+        for (size_t i = 0; i < N; i++) {
+            u128 t = (u128)v[i] + b.v[i] + c;
+            v[i] = (limb_t)t;
+            c = (limb_t)(t >> 64);
+        }
+        if (c || shim_detail::geq<N>(v, MOD))
+            shim_detail::sub_n<N>(v, MOD);
+        return *this;
+    }
+    friend shim_field_t operator+(shim_field_t a, const shim_field_t& b) { return a += b; }
+
+    shim_field_t& operator-=(const shim_field_t& b)
+    {
+        limb_t br = 0;
+        for (size_t i = 0; i < N; i++) {
+            u128 t = (u128)v[i] - b.v[i] - br;
+            v[i] = (limb_t)t;
+            br = (limb_t)(t >> 64) & 1;
+        }
+        if (br)
+            shim_detail::add_n<N>(v, MOD);
+        return *this;
+    }
+    friend shim_field_t operator-(shim_field_t a, const shim_field_t& b) { return a -= b; }
+
+    shim_field_t& operator<<=(unsigned l)
+    {
+        while (l--)
+            *this += *this;
+        return *this;
+    }
+    friend shim_field_t operator<<(shim_field_t a, unsigned l) { return a <<= l; }
+
+    shim_field_t& cneg(bool flag)
+    {
+        if (flag && !is_zero()) {
+            shim_field_t z;
+            z.zero();
+            *this = z - *this;
+        }
+        return *this;
+    }
+
+    friend shim_field_t operator*(const shim_field_t& a, const shim_field_t& b)
+    {
+        limb_t t[N + 2];
+        memset(t, 0, sizeof(t));
+        for (size_t i = 0; i < N; i++) {
+            limb_t c = 0;
+            for (size_t j = 0; j < N; j++) {
+                u128 x = (u128)a.v[j] * b.v[i] + t[j] + c;
+                t[j] = (limb_t)x;
+                c = (limb_t)(x >> 64);
+            }
+            u128 x = (u128)t[N] + c;
+            t[N] = (limb_t)x;
+            t[N + 1] = (limb_t)(x >> 64);
+            limb_t m = t[0] * M0;
+            x = (u128)m * MOD[0] + t[0];
+            c = (limb_t)(x >> 64);
+            for (size_t j = 1; j < N; j++) {
+                x = (u128)m * MOD[j] + t[j] + c;
+                t[j - 1] = (limb_t)x;
+                c = (limb_t)(x >> 64);
+            }
+            x = (u128)t[N] + c;
+            t[N - 1] = (limb_t)x;
+            t[N] = t[N + 1] + (limb_t)(x >> 64);
+        }
+        shim_field_t r;
+        memcpy(r.v, t, sizeof(r.v));
+        if (t[N] || shim_detail::geq<N>(r.v, MOD))
+            shim_detail::sub_n<N>(r.v, MOD);
+        return r;
+    }
+    shim_field_t& operator*=(const shim_field_t& b) { return *this = *this * b; }
+    shim_field_t& sqr() { return *this = *this * *this; }
+    shim_field_t& operator^=(int p)
+    {
+        if (p == 2)
+            return sqr();
+        shim_field_t b = *this;
+        for (int i = 1; i < p; i++)
+            *this *= b;
+        return *this;
+    }
+    friend shim_field_t operator^(shim_field_t a, int p) { return a ^= p; }
+
+    void to() { *this = *this * shim_field_t(RR); }
+    void from()
+    {
+        shim_field_t o;
+        o.zero();
+        o.v[0] = 1;
+        *this = *this * o;
+    }
+    void to_scalar(pow_t& s) const
+    {
+        shim_field_t t = *this;
+        t.from();
+        memcpy(s, t.v, sizeof(pow_t));
+    }
+    friend bool operator==(const shim_field_t& a, const shim_field_t& b)
+    {
+        return memcmp(a.v, b.v, sizeof(a.v)) == 0;
+    }
+    friend bool operator!=(const shim_field_t& a, const shim_field_t& b) { return !(a == b); }
+    friend shim_field_t czero(const shim_field_t& a, int set_z)
+    {
+        shim_field_t r = a;
+        if (set_z)
+            r.zero();
+        return r;
+    }
+    static shim_field_t csel(const shim_field_t& a, const shim_field_t& b, int sel_a)
+    {
+        return sel_a ? a : b;
+    }
+    shim_field_t reciprocal() const
+    {
+        limb_t e[N];
+        memcpy(e, MOD, sizeof(e));
+        e[0] -= 2;
+        shim_field_t r = one(), b = *this;
+        for (size_t i = 0; i < N * 64; i++) {
+            if ((e[i / 64] >> (i % 64)) & 1)
+                r *= b;
+            b.sqr();
+        }
+        return r;
+    }
+    friend shim_field_t operator/(int, const shim_field_t& a) { return a.reciprocal(); }
+};
+
+template<size_t NBITS, const limb_t* MOD, limb_t M0, const limb_t* RR, const limb_t* ONE>
+using blst_256_t = shim_field_t<NBITS, 4, MOD, M0, RR, ONE>;
+template<size_t NBITS, const limb_t* MOD, limb_t M0, const limb_t* RR, const limb_t* ONE>
+using blst_384_t = shim_field_t<NBITS, 6, MOD, M0, RR, ONE>;
