@@ -1,0 +1,109 @@
+/*
+ * sppark_b200.h -- C ABI of libsppark_b200.so, the B200-native MSM / NTT library.
+ *
+ * The first block is the DROP-IN surface: the exact symbols, signatures and error
+ * convention that supranational/sppark's PoC crates bind through FFI, so that a caller of
+ * the reference links against this library unchanged.  Each declaration cites the
+ * reference interface it replaces (paths relative to the sppark tree).
+ *
+ * The second block (sppark_b200_*) is this library's extended surface: the same operations
+ * on DEVICE pointers and an explicit CUDA stream (the reference reaches these through C++
+ * only: NTT::Base_dev_ptr ntt/ntt.cuh:344-350, msm_t::invoke with device pointers
+ * msm/pippenger.cuh:582-601), other fields/curves, and introspection for tests.
+ *
+ * Conventions (util/rusterror.h:18-36, util/exception.cuh:12-21, rust/src/lib.rs:9-22):
+ *   - every entry point returns RustError BY VALUE; code == 0 is success, otherwise
+ *     -(cudaError_t) or a negative errno-style code; message is NULL or a malloc()ed C
+ *     string owned by the caller (free() / drop_error_message()).
+ *   - no C++ exception ever crosses this boundary.
+ *   - all pointers are caller-owned; host pointers unless the name says _dev.
+ *   - there is NO CPU fallback: without a usable CUDA device every call fails with
+ *     code -cudaErrorNoDevice (-100).
+ */
+#ifndef SPPARK_B200_H
+#define SPPARK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    int   code;
+    char *message;
+} RustError;                                   /* util/rusterror.h:18-36 */
+
+/* --- memory layouts (ABI) ---------------------------------------------------------
+ * fp  (BLS12-381 base field): 12 x uint32 little-endian limbs = 48 B, Montgomery form,
+ *     R = 2^384   (ff/mont_t.cuh:36, ff/bls12-381.hpp:14-30)
+ * fr  (scalars): 8 x uint32 LE limbs = 32 B, plain (non-Montgomery) integers < r
+ * affine      {X, Y}                96 B, infinity = all-zero     (ec/affine_t.hpp:19-72)
+ * affine_inf  {X, Y, bool inf}     host stride ffi_affine_sz (104 for arkworks G1Affine),
+ *                                   inf = bit 0 of the byte at +96 (ec/affine_t.hpp:74-122)
+ * jacobian    {X, Y, Z}            144 B, infinity = Z == 0       (ec/jacobian_t.hpp:16-58)
+ * xyzz        {X, Y, ZZZ, ZZ}      192 B (internal buckets)       (ec/xyzz_t.hpp:16-17)
+ * gl64        uint64 canonical (< p), not Montgomery              (ff/gl64_t.cuh:39-60)
+ * bb31        uint32 Montgomery residue, R = 2^32                 (ff/mont32_t.cuh:20-41)
+ */
+
+enum { SPPARK_NTT_NN = 0, SPPARK_NTT_NR = 1, SPPARK_NTT_RN = 2, SPPARK_NTT_RR = 3 };
+                                               /* NTT::InputOutputOrder, ntt/ntt.cuh:33 */
+enum { SPPARK_NTT_FORWARD = 0, SPPARK_NTT_INVERSE = 1 };   /* NTT::Direction, ntt/ntt.cuh:34 */
+enum { SPPARK_NTT_STANDARD = 0, SPPARK_NTT_COSET = 1 };    /* NTT::Type,      ntt/ntt.cuh:35 */
+
+/* ================================ drop-in surface ================================= */
+
+/* poc/msm-cuda/cuda/pippenger.cu:20-25 ; Rust decl poc/msm-cuda/src/lib.rs:24-29.
+ * BLS12-381 G1: out = sum scalars[i] * points[i]. */
+RustError mult_pippenger(void *out_jacobian, const void *points_affine, size_t npoints,
+                         const void *scalars);
+
+/* poc/msm-cuda/cuda/pippenger_inf.cu:28-34 ; Rust decl poc/msm-cuda/src/lib.rs:52-58.
+ * Same, points carry an explicit infinity flag and a host stride. */
+RustError mult_pippenger_inf(void *out_jacobian, const void *points_affine_inf, size_t npoints,
+                             const void *scalars, size_t ffi_affine_sz);
+
+/* poc/ntt-cuda/cuda/ntt_api.cu:25-36 (FEATURE_GOLDILOCKS build, the one
+ * poc/ntt-cuda/go/goldilocks.go:24-40 loads); in place on HOST memory; lg == 0 is a no-op. */
+RustError compute_ntt(size_t device_id, void *inout, uint32_t lg_domain_size,
+                      int ntt_order, int ntt_direction, int ntt_type);
+
+/* util/all_gpus.cpp:65-86 */
+int  cuda_available(void);                     /* bool in the reference */
+void drop_error_message(char *msg);
+
+/* ================================ extended surface ================================ */
+
+enum { SPPARK_FIELD_GL64 = 0, SPPARK_FIELD_BB31 = 1 };
+enum { SPPARK_CURVE_BLS12_381_G1 = 0, SPPARK_CURVE_PALLAS = 1, SPPARK_CURVE_VESTA = 2 };
+
+/* compute_ntt for any single-word field (the reference builds one .so per FEATURE_*) */
+RustError sppark_b200_ntt(int field, size_t device_id, void *inout, uint32_t lg_domain_size,
+                          int ntt_order, int ntt_direction, int ntt_type);
+/* NTT::Base_dev_ptr (ntt/ntt.cuh:344-350): d_inout is device memory, work is enqueued on
+ * `stream` (a cudaStream_t; NULL = legacy default stream) and NOT synchronised. */
+RustError sppark_b200_ntt_dev(int field, void *d_inout, uint32_t lg_domain_size,
+                              int ntt_order, int ntt_direction, int ntt_type, void *stream);
+
+/* MSM on any supported curve with host pointers (mult_pippenger's signature + curve id;
+ * the reference has no PoC boundary for Pasta). */
+RustError sppark_b200_msm(int curve, void *out_jacobian, const void *points_affine,
+                          size_t npoints, const void *scalars, size_t ffi_affine_sz);
+/* msm_t::invoke with device-resident points and scalars (msm/pippenger.cuh:582-601):
+ * d_points: packed affine {X,Y}; d_scalars: 32-B LE; result written to HOST out_jacobian
+ * after synchronising `stream`. */
+RustError sppark_b200_msm_dev(int curve, void *out_jacobian, const void *d_points,
+                              size_t npoints, const void *d_scalars, void *stream);
+
+/* introspection */
+int         sppark_b200_sm_count(int device_id);
+const char *sppark_b200_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t    sppark_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

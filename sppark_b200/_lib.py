@@ -1,0 +1,69 @@
+"""ctypes loader of libsppark_b200.so.  There is no CPU fallback: if the CUDA library is
+missing or the machine has no B200-class device, calls fail loudly."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsppark_b200.so")
+
+
+class RustError(C.Structure):
+    """sppark::Error / RustError (rust/src/lib.rs:9-13, util/rusterror.h:18-36)."""
+    _fields_ = [("code", C.c_int), ("message", C.c_void_p)]
+
+
+class SpparkError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"sppark_b200 error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+_SIGS = {
+    "mult_pippenger": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
+    "mult_pippenger_inf": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t],
+    "compute_ntt": [C.c_size_t, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int],
+    "sppark_b200_ntt": [C.c_int, C.c_size_t, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int],
+    "sppark_b200_ntt_dev": [C.c_int, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p],
+    "sppark_b200_msm": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t],
+    "sppark_b200_msm_dev": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p],
+}
+
+# every symbol include/sppark_b200.h declares (tests check the .so exports all of them)
+EXPORTS = list(_SIGS) + ["cuda_available", "drop_error_message", "sppark_b200_sm_count",
+                         "sppark_b200_version", "sppark_b200_launch_count"]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} not built: run `python -m sppark_b200.build` "
+                              "(there is no CPU fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, args in _SIGS.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = RustError
+        l.cuda_available.restype = C.c_int
+        l.drop_error_message.argtypes = [C.c_void_p]
+        l.sppark_b200_sm_count.argtypes = [C.c_int]
+        l.sppark_b200_version.restype = C.c_char_p
+        l.sppark_b200_launch_count.restype = C.c_uint64
+        _lib = l
+    return _lib
+
+
+def check(err):
+    """Turn a by-value RustError into an exception, freeing the message like Rust's
+    `impl From<Error> for String` does (rust/src/lib.rs:15-22)."""
+    if err.code != 0:
+        msg = C.cast(err.message, C.c_char_p).value.decode() if err.message else ""
+        if err.message:
+            lib().drop_error_message(err.message)
+        raise SpparkError(err.code, msg)
+
+
+def launch_count():
+    return int(lib().sppark_b200_launch_count())

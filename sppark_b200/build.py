@@ -1,0 +1,54 @@
+"""In-tree build of libsppark_b200.so (nvcc, sm_100a only).
+
+`python -m sppark_b200.build` or `__graft_entry__.build()`.  The .so is git-ignored but travels
+to the GPU box with the gpurun snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libsppark_b200.so")
+
+SOURCES = ["api.cu", "util/gpu.cu", "ntt/ntt.cu", "msm/msm.cu"]
+NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "--threads", "4"]
+
+
+def _sources():
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def _newest_input():
+    newest = 0.0
+    for root, _, files in os.walk(CSRC):
+        for f in files:
+            newest = max(newest, os.path.getmtime(os.path.join(root, f)))
+    inc = os.path.join(os.path.dirname(HERE), "include", "sppark_b200.h")
+    return max(newest, os.path.getmtime(inc))
+
+
+def build(force=False, verbose=False):
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_input():
+        return LIB
+    objs = []
+    procs = []
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    for src in _sources():
+        obj = os.path.join(objdir, os.path.basename(src).replace(".cu", ".o"))
+        cmd = ["nvcc", *NVCC_FLAGS, "-c", "-o", obj, src]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((subprocess.Popen(cmd), cmd))
+        objs.append(obj)
+    for p, cmd in procs:
+        if p.wait() != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    subprocess.check_call(["nvcc", "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,72 @@
+// NTT instantiations and their C-ABI entry points (include/sppark_b200.h).
+#include "../ff/gl64.cuh"
+#include "../ff/bb31.cuh"
+#include "ntt.cuh"
+
+namespace ntt {
+// lg_tile: log2(elements) of one CTA's shared-memory tile: 128 KiB of data for either field
+template<> struct FieldId<gl64> { static constexpr uint32_t id = 1, lg_tile = 14; };
+template<> struct FieldId<bb31> { static constexpr uint32_t id = 2, lg_tile = 14; };
+template class NTT<gl64>;
+template class NTT<bb31>;
+}  // namespace ntt
+
+template<class F>
+static RustError ntt_host(size_t device_id, void* inout, uint32_t lg, int order, int direction, int type)
+{
+    typedef ntt::NTT<F> N;
+    if (order < 0 || order > 3 || direction < 0 || direction > 1 || type < 0 || type > 1)
+        return rust_err(-(int)cudaErrorInvalidValue, "compute_ntt: bad order/direction/type");
+    try {
+        const gpu_t& gpu = select_gpu((int)device_id);
+        return N::Base(gpu, (typename F::T*)inout, lg, (typename N::InputOutputOrder)order,
+                       (typename N::Direction)direction, (typename N::Type)type);
+    } catch (const cuda_error& e) {
+        return rust_err(e.code(), e.what());
+    } catch (const std::exception& e) {
+        return rust_err(-1, e.what());
+    }
+}
+
+template<class F>
+static RustError ntt_dev(void* d_inout, uint32_t lg, int order, int direction, int type, void* stream)
+{
+    typedef ntt::NTT<F> N;
+    if (order < 0 || order > 3 || direction < 0 || direction > 1 || type < 0 || type > 1)
+        return rust_err(-(int)cudaErrorInvalidValue, "ntt_dev: bad order/direction/type");
+    try {
+        const gpu_t& gpu = gpu_of_current_device();
+        N::Base_dev_ptr(gpu, (cudaStream_t)stream, (typename F::T*)d_inout, lg,
+                        (typename N::InputOutputOrder)order, (typename N::Direction)direction,
+                        (typename N::Type)type);
+        return rust_ok();
+    } catch (const cuda_error& e) {
+        return rust_err(e.code(), e.what());
+    } catch (const std::exception& e) {
+        return rust_err(-1, e.what());
+    }
+}
+
+extern "C" RustError compute_ntt(size_t device_id, void* inout, uint32_t lg_domain_size,
+                                 int ntt_order, int ntt_direction, int ntt_type)
+{   return ntt_host<gl64>(device_id, inout, lg_domain_size, ntt_order, ntt_direction, ntt_type);   }
+
+extern "C" RustError sppark_b200_ntt(int field, size_t device_id, void* inout, uint32_t lg,
+                                     int order, int direction, int type)
+{
+    switch (field) {
+    case SPPARK_FIELD_GL64: return ntt_host<gl64>(device_id, inout, lg, order, direction, type);
+    case SPPARK_FIELD_BB31: return ntt_host<bb31>(device_id, inout, lg, order, direction, type);
+    default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_ntt: unknown field");
+    }
+}
+
+extern "C" RustError sppark_b200_ntt_dev(int field, void* d_inout, uint32_t lg, int order,
+                                         int direction, int type, void* stream)
+{
+    switch (field) {
+    case SPPARK_FIELD_GL64: return ntt_dev<gl64>(d_inout, lg, order, direction, type, stream);
+    case SPPARK_FIELD_BB31: return ntt_dev<bb31>(d_inout, lg, order, direction, type, stream);
+    default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_ntt_dev: unknown field");
+    }
+}

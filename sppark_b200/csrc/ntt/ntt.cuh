@@ -1,0 +1,222 @@
+// class NTT<F>: the reference's `class NTT` (ntt/ntt.cuh:31-366) for single-word fields,
+// rebuilt on the pass kernel of ntt_core.cuh.  Same public entry points and semantics:
+//   NTT::Base(gpu, host_inout, lg, order, direction, type)        ntt/ntt.cuh:216-244
+//   NTT::Base_dev_ptr(stream, d_inout, lg, order, direction, type) ntt/ntt.cuh:344-350
+// order/direction/type are the reference enums (ntt/ntt.cuh:33-35).
+#pragma once
+#include "../util/gpu.cuh"
+#include "ntt_plan.hpp"
+
+namespace ntt {
+
+template<class F>
+__global__ void __launch_bounds__(1024)
+pass_kernel(const Pass d, const Tables<F> tb, const typename F::T* in, typename F::T* out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typename F::T* smem = reinterpret_cast<typename F::T*>(smem_raw);
+    const uint32_t tid = threadIdx.x, nthreads = blockDim.x, t = blockIdx.x;
+
+    phase_twiddles<F>(d, tb, smem, tid, nthreads);
+    phase_load<F>(d, tb, in, smem, t, tid, nthreads);
+    __syncthreads();
+    const uint32_t nsteps = step_count(d.lg_r);
+    for (uint32_t s = 0; s < nsteps; s++) {
+        phase_step_dyn<F>(d, smem, s * LG_EPT, step_log_e(d.lg_r, s), tid);
+        __syncthreads();
+    }
+    phase_store<F>(d, tb, out, smem, t, tid, nthreads);
+}
+
+// ---- one-time table generation (role of NTTParameters, ntt/parameters.cuh:147-337) ----
+template<class F>
+__global__ void gen_tables_kernel(typename F::T* dense, typename F::T* tlo, typename F::T* thi,
+                                  uint32_t n_hi, uint32_t lg_n, bool inverse)
+{
+    typedef typename F::T T;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    T w_max = F::root_of_unity_max();
+    if (inverse) w_max = F::inv(w_max);
+    // w_(2^lg) = w_max^(2^(MAX_LG - lg))
+    if (i < (1u << LG_DENSE)) {
+        if (i == 0) {
+            dense[0] = F::one();
+        } else {
+            uint32_t lg_h = 31 - __clz(i), idx = i - (1u << lg_h);     // i = h + idx
+            T w = F::pow(w_max, 1ull << (F::MAX_LG - (lg_h + 1)));
+            dense[i] = F::pow(w, idx);
+        }
+    }
+    T wn = F::pow(w_max, 1ull << (F::MAX_LG - lg_n));
+    if (i < (1u << LG_TLO)) tlo[i] = F::pow(wn, i);
+    if (i < n_hi) thi[i] = F::pow(wn, (uint64_t)i << LG_TLO);
+}
+
+// coset: x[i] *= g^nat(i)   (reference: LDE_distribute_powers, ntt/kernels.cu:131-153)
+template<class F>
+__global__ void gen_coset_kernel(typename F::T* g0, typename F::T* g1, typename F::T* g2, bool inverse)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    typename F::T g = F::group_gen();
+    if (inverse) g = F::inv(g);
+    if (i < 4096) { g0[i] = F::pow(g, i); g1[i] = F::pow(g, (uint64_t)i << 12); }
+    if (i < 256) g2[i] = F::pow(g, (uint64_t)i << 24);
+}
+
+template<class F>
+__global__ void coset_kernel(typename F::T* data, uint32_t lg_n, bool bitrev,
+                             const typename F::T* g0, const typename F::T* g1,
+                             const typename F::T* g2)
+{
+    typedef typename F::T T;
+    const size_t n = (size_t)1 << lg_n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t e = bitrev ? brev32((uint32_t)i, lg_n) : (uint32_t)i;
+        T x = F::mul(F::load(data[i]), g0[e & 4095]);
+        if (e >> 12) x = F::mul(x, g1[(e >> 12) & 4095]);
+        if (e >> 24) x = F::mul(x, g2[e >> 24]);
+        data[i] = F::canon(x);
+    }
+}
+
+template<class F> struct FieldId;     // specialised in ntt.cu: cache key + shared-memory tile
+
+template<class F>
+class NTT {
+    typedef typename F::T T;
+public:
+    enum class InputOutputOrder { NN, NR, RN, RR };
+    enum class Direction { forward, inverse };
+    enum class Type { standard, coset };
+
+private:
+    struct DevTables { Tables<F> view; };
+
+    static uint64_t key(uint32_t kind, uint32_t lg_n, bool inverse)
+    {   return ((uint64_t)FieldId<F>::id << 48) | ((uint64_t)kind << 40) | ((uint64_t)lg_n << 8) | inverse;   }
+
+    // twiddles live for the life of the process, per device (as NTTParameters::all does)
+    static const Tables<F>& tables(const gpu_t& gpu, uint32_t lg_n, bool inverse, cudaStream_t stream)
+    {
+        std::lock_guard<std::mutex> lock(const_cast<gpu_t&>(gpu).cache_mtx);
+        auto& cache = const_cast<gpu_t&>(gpu).cache;
+        auto it = cache.find(key(0, lg_n, inverse));
+        if (it != cache.end()) return *reinterpret_cast<Tables<F>*>(it->second);
+
+        const uint32_t n_hi = lg_n > LG_TLO ? 1u << (lg_n - LG_TLO) : 1;
+        const size_t total = (1u << LG_DENSE) + (1u << LG_TLO) + n_hi;
+        T* blob;
+        CUDA_OK(cudaMalloc(&blob, total * sizeof(T)));
+        T *dense = blob, *tlo = blob + (1u << LG_DENSE), *thi = tlo + (1u << LG_TLO);
+        uint32_t nthr = n_hi > 4096 ? n_hi : 4096;
+        gen_tables_kernel<F><<<(nthr + 255) / 256, 256, 0, stream>>>(dense, tlo, thi, n_hi, lg_n, inverse);
+        COUNT_LAUNCH();
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaStreamSynchronize(stream));      // one-time: other streams may use it next
+        T half = F::inv(F::add(F::one(), F::one())), ninv = F::one();
+        for (uint32_t i = 0; i < lg_n; i++) ninv = F::mul(ninv, half);
+        auto* tb = new Tables<F>{dense, tlo, thi, ninv};
+        cache[key(0, lg_n, inverse)] = tb;
+        return *tb;
+    }
+
+    struct CosetTables { T *g0, *g1, *g2; };
+    static const CosetTables& coset_tables(const gpu_t& gpu, bool inverse, cudaStream_t stream)
+    {
+        std::lock_guard<std::mutex> lock(const_cast<gpu_t&>(gpu).cache_mtx);
+        auto& cache = const_cast<gpu_t&>(gpu).cache;
+        auto it = cache.find(key(1, 0, inverse));
+        if (it != cache.end()) return *reinterpret_cast<CosetTables*>(it->second);
+        T* blob;
+        CUDA_OK(cudaMalloc(&blob, (4096 + 4096 + 256) * sizeof(T)));
+        auto* ct = new CosetTables{blob, blob + 4096, blob + 8192};
+        gen_coset_kernel<F><<<16, 256, 0, stream>>>(ct->g0, ct->g1, ct->g2, inverse);
+        COUNT_LAUNCH();
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaStreamSynchronize(stream));
+        cache[key(1, 0, inverse)] = ct;
+        return *ct;
+    }
+
+    static void coset_scale(const gpu_t& gpu, T* d_inout, uint32_t lg_n, bool bitrev, bool inverse,
+                            cudaStream_t stream)
+    {
+        const CosetTables& ct = coset_tables(gpu, inverse, stream);
+        size_t n = (size_t)1 << lg_n;
+        uint32_t blocks = (uint32_t)((n + 255) / 256);
+        uint32_t cap = (uint32_t)gpu.sm_count() * 16;
+        coset_kernel<F><<<blocks < cap ? blocks : cap, 256, 0, stream>>>(d_inout, lg_n, bitrev, ct.g0, ct.g1, ct.g2);
+        COUNT_LAUNCH();
+        CUDA_OK(cudaGetLastError());
+    }
+
+public:
+    // device-resident transform, enqueued on `stream`, no synchronisation
+    static void NTT_internal(const gpu_t& gpu, T* d_inout, uint32_t lg_n, InputOutputOrder order,
+                             Direction direction, Type type, cudaStream_t stream)
+    {
+        if (lg_n == 0) return;
+        if (lg_n > (uint32_t)F::MAX_LG || lg_n > 30)
+            throw cuda_error(-(int)cudaErrorInvalidValue, "NTT: lg_domain_size out of range");
+        const bool inverse = direction == Direction::inverse;
+        const bool in_rev = order == InputOutputOrder::RN || order == InputOutputOrder::RR;
+        const bool out_rev = order == InputOutputOrder::NR || order == InputOutputOrder::RR;
+
+        if (!inverse && type == Type::coset)
+            coset_scale(gpu, d_inout, lg_n, in_rev, false, stream);
+
+        const Tables<F>& tb = tables(gpu, lg_n, inverse, stream);
+        Plan plan = make_plan(lg_n, (int)order, inverse, FieldId<F>::lg_tile);
+
+        T* scratch = nullptr;
+        if (plan.needs_scratch)
+            CUDA_OK(cudaMallocAsync((void**)&scratch, sizeof(T) << lg_n, stream));
+        T* buf[2] = {d_inout, scratch};
+
+        static bool attr_done[64];
+        if (!attr_done[gpu.cid() & 63]) {
+            CUDA_OK(cudaFuncSetAttribute(pass_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)gpu.props().sharedMemPerBlockOptin));
+            attr_done[gpu.cid() & 63] = true;
+        }
+        for (const Pass& d : plan.passes) {
+            uint32_t ntiles = 1u << (lg_n - d.lg_r - d.lg_w);
+            size_t smem = smem_elems(d) * sizeof(T);
+            pass_kernel<F><<<ntiles, tile_threads(d), smem, stream>>>(d, tb, buf[d.src], buf[d.dst]);
+            COUNT_LAUNCH();
+            CUDA_OK(cudaGetLastError());
+        }
+        if (scratch) CUDA_OK(cudaFreeAsync(scratch, stream));
+
+        if (inverse && type == Type::coset)
+            coset_scale(gpu, d_inout, lg_n, out_rev, true, stream);
+    }
+
+    static void Base_dev_ptr(const gpu_t& gpu, cudaStream_t stream, T* d_inout, uint32_t lg_n,
+                             InputOutputOrder order, Direction direction, Type type)
+    {   NTT_internal(gpu, d_inout, lg_n, order, direction, type, stream);   }
+
+    // host-pointer entry: alloc + HtoD + transform + DtoH + sync, errors -> RustError
+    static RustError Base(const gpu_t& gpu, T* inout, uint32_t lg_n, InputOutputOrder order,
+                          Direction direction, Type type)
+    {
+        if (lg_n == 0) return rust_ok();
+        try {
+            gpu.select();
+            const stream_t& s = gpu[0];
+            size_t n = (size_t)1 << lg_n;
+            dev_ptr_t<T> d_inout(n, s);
+            s.HtoD(d_inout, inout, n * sizeof(T));
+            NTT_internal(gpu, d_inout, lg_n, order, direction, type, s);
+            s.DtoH(inout, d_inout, n * sizeof(T));
+            s.sync();
+        } catch (const cuda_error& e) {
+            try { gpu.sync(); } catch (...) {}
+            return rust_err(e.code(), e.what());
+        }
+        return rust_ok();
+    }
+};
+
+}  // namespace ntt

@@ -1,0 +1,225 @@
+// NTT pass machinery for single-word fields (gl64, bb31).
+//
+// An N = 2^n point NTT is executed as P <= 3 "passes".  A pass is one kernel launch in
+// which every CTA owns a tile of W independent columns x 2^R rows, pulls it from HBM into
+// shared memory, runs a complete 2^R-point sub-NTT on each column there (radix-2 DIT
+// butterflies, 16 elements per thread in registers between shared-memory exchanges),
+// applies the inter-pass twiddle w_N^(row*col) and writes the tile back.  Every element
+// is therefore read and written exactly once per pass: algorithmic traffic per pass is
+// 2*N*sizeof(T) and a 2^24 transform needs two passes (the reference needs three
+// <=10-stage steps plus a bit-reversal pass for the same NN transform,
+// ntt/ntt.cuh:100-127,174-178).
+//
+// The four orders of the reference API (ntt/ntt.cuh:33,174-194) are four ways of
+// assigning index digits to passes; they share this kernel and differ only in the
+// host-built descriptor (ntt_plan.hpp):
+//   NR  in place, top digit first,    digit left bit-reversed,  twiddle at store
+//   RN  in place, bottom digit first, digit arrives bit-reversed, twiddle at load
+//   NN  ping-pong through a scratch buffer, strided gather -> transposed scatter
+//   RR  mirror image of NN
+//
+// Everything here is HD (host+device) so tests/emu/ntt_emu.cpp can run the same code
+// phase by phase on the CPU; the shipped path is ntt.cu (CUDA only).
+#pragma once
+#include "../util/hd.cuh"
+
+namespace ntt {
+
+constexpr uint32_t LG_DENSE = 12;        // largest sub-NTT: 2^12 rows
+constexpr uint32_t EPT = 16;             // elements per thread per register step
+constexpr uint32_t LG_EPT = 4;
+constexpr uint32_t LG_TLO = 12;          // low half of the two-level w_N^e table
+
+enum TwMode : uint32_t { TW_NONE = 0, TW_LOAD = 1, TW_STORE = 2 };
+
+struct Pass {
+    uint32_t lg_r;                       // rows   = 2^lg_r  (sub-NTT length)
+    uint32_t lg_w;                       // columns = 2^lg_w (independent sub-NTTs per tile)
+    // element address = th*(t >> lg_tlo) + tl*(t & mask) + (row << lg_sa) + (col << lg_sc)
+    uint32_t in_lg_tlo, in_lg_sa, in_lg_sc;
+    uint64_t in_tl, in_th;
+    uint32_t out_lg_tlo, out_lg_sa, out_lg_sc;
+    uint64_t out_tl, out_th;
+    uint32_t in_rev;                     // rows arrive in bit-reversed order
+    uint32_t out_rev;                    // rows leave in bit-reversed order
+    uint32_t tw_mode, tw_rsh, tw_bits, tw_brev, tw_lsh;
+    uint32_t scale;                      // multiply by n^-1 at store (last pass of an inverse)
+    uint32_t src, dst;                   // 0 = caller's buffer, 1 = scratch
+};
+
+template<class F> struct Tables {
+    const typename F::T* dense;          // dense[h + i] = w_(2h)^i, h = 1,2,4..2^(LG_DENSE-1)
+    const typename F::T* tlo;            // tlo[i] = w_N^i,            i < 2^LG_TLO
+    const typename F::T* thi;            // thi[i] = w_N^(i << LG_TLO)
+    typename F::T ninv;                  // 2^-n
+};
+
+HD uint32_t pad(uint32_t i) { return i + (i >> 4); }
+HD uint32_t col_stride(uint32_t lg_r) { return pad(1u << lg_r) + 1; }
+HD uint32_t tile_threads(const Pass& d)
+{
+    return (d.lg_r >= LG_EPT ? (1u << (d.lg_r - LG_EPT)) : 1u) << d.lg_w;
+}
+HD uint32_t smem_elems(const Pass& d) { return (col_stride(d.lg_r) << d.lg_w) + (1u << d.lg_r); }
+
+HD uint64_t tile_base(uint32_t t, uint32_t lg_tlo, uint64_t tl, uint64_t th)
+{
+    uint32_t lo = lg_tlo >= 32 ? t : (t & ((1u << lg_tlo) - 1));
+    uint32_t hi = lg_tlo >= 32 ? 0 : (t >> lg_tlo);
+    return tl * lo + th * hi;
+}
+
+template<class F> HD typename F::T twiddle(const Tables<F>& tb, uint32_t e)
+{
+    typename F::T lo = tb.tlo[e & ((1u << LG_TLO) - 1)];
+    uint32_t h = e >> LG_TLO;
+    return h ? F::mul(lo, tb.thi[h]) : lo;
+}
+
+HD uint32_t tw_column_value(const Pass& d, uint64_t pos0)
+{
+    uint32_t v = (uint32_t)(pos0 >> d.tw_rsh) & (d.tw_bits >= 32 ? ~0u : ((1u << d.tw_bits) - 1));
+    return d.tw_brev ? brev32(v, d.tw_bits) : v;
+}
+
+// ---- phase 0: per-CTA copy of the sub-NTT twiddles into shared memory -------------
+template<class F>
+HD void phase_twiddles(const Pass& d, const Tables<F>& tb, typename F::T* smem,
+                       uint32_t tid, uint32_t nthreads)
+{
+    typename F::T* tw = smem + (col_stride(d.lg_r) << d.lg_w);
+    for (uint32_t i = tid; i < (1u << d.lg_r); i += nthreads)
+        tw[i] = tb.dense[i];
+}
+
+// ---- phase 1: HBM -> shared memory -------------------------------------------------
+template<class F>
+HD void phase_load(const Pass& d, const Tables<F>& tb, const typename F::T* in,
+                   typename F::T* smem, uint32_t t, uint32_t tid, uint32_t nthreads)
+{
+    typedef typename F::T T;
+    const uint32_t R = d.lg_r, n_el = (1u << R) << d.lg_w, cs = col_stride(R);
+    const uint64_t base = tile_base(t, d.in_lg_tlo, d.in_tl, d.in_th);
+    const bool row_fast = d.in_lg_sa == 0;      // consecutive threads walk rows, else columns
+    T v[EPT];
+#pragma unroll
+    for (uint32_t l = 0; l < EPT; l++) {
+        uint32_t e = l * nthreads + tid;
+        if (e < n_el) {
+            uint32_t a = row_fast ? (e & ((1u << R) - 1)) : (e >> d.lg_w);
+            uint32_t c = row_fast ? (e >> R) : (e & ((1u << d.lg_w) - 1));
+            v[l] = in[base + ((uint64_t)a << d.in_lg_sa) + ((uint64_t)c << d.in_lg_sc)];
+        }
+    }
+#pragma unroll
+    for (uint32_t l = 0; l < EPT; l++) {
+        uint32_t e = l * nthreads + tid;
+        if (e < n_el) {
+            uint32_t a = row_fast ? (e & ((1u << R) - 1)) : (e >> d.lg_w);
+            uint32_t c = row_fast ? (e >> R) : (e & ((1u << d.lg_w) - 1));
+            T x = F::load(v[l]);
+            uint32_t nat = d.in_rev ? brev32(a, R) : a;          // natural row index
+            if (d.tw_mode == TW_LOAD) {
+                uint32_t colv = tw_column_value(d, base + ((uint64_t)c << d.in_lg_sc));
+                x = F::mul(x, twiddle<F>(tb, (nat * colv) << d.tw_lsh));
+            }
+            smem[c * cs + pad(brev32(nat, R))] = x;               // DIT wants bit-reversed rows
+        }
+    }
+}
+
+// ---- phase 2: LOG_E radix-2 DIT stages on 2^LOG_E registers -----------------------
+// Rows p0 + m*2^b, m < 2^LOG_E; stage t pairs m with m | (1<<t), half-size h = 2^(b+t),
+// twiddle dense[h + (m mod 2^t)*2^b + j].
+template<class F, uint32_t LOG_E>
+HD void phase_step(const Pass& d, typename F::T* smem, uint32_t b, uint32_t tid)
+{
+    typedef typename F::T T;
+    constexpr uint32_t E = 1u << LOG_E;
+    const uint32_t R = d.lg_r, cs = col_stride(R);
+    const uint32_t lg_tpc = R >= LG_EPT ? R - LG_EPT : 0;       // threads per column
+    const uint32_t c = tid >> lg_tpc, tau = tid & ((1u << lg_tpc) - 1);
+    T* col = smem + c * cs;
+    const T* tw = smem + (cs << d.lg_w);
+    const uint32_t groups = 1u << (R - LOG_E);
+
+    for (uint32_t g = tau; g < groups; g += (1u << lg_tpc)) {
+        const uint32_t j = g & ((1u << b) - 1), hi = g >> b;
+        const uint32_t p0 = (hi << (b + LOG_E)) + j;
+        T x[E];
+#pragma unroll
+        for (uint32_t m = 0; m < E; m++)
+            x[m] = col[pad(p0 + (m << b))];
+#pragma unroll
+        for (uint32_t t = 0; t < LOG_E; t++) {
+            const uint32_t h = 1u << (b + t);
+#pragma unroll
+            for (uint32_t m0 = 0; m0 < E; m0++) {
+                if (m0 & (1u << t)) continue;
+                const uint32_t m1 = m0 | (1u << t);
+                T tt;
+                if (b + t == 0) {
+                    tt = x[m1];                                  // w = 1, value canonical since load
+                } else {
+                    const uint32_t idx = ((m0 & ((1u << t) - 1)) << b) + j;
+                    tt = F::mul(x[m1], tw[h + idx]);
+                }
+                x[m1] = F::sub(x[m0], tt);
+                x[m0] = F::add(x[m0], tt);
+            }
+        }
+#pragma unroll
+        for (uint32_t m = 0; m < E; m++)
+            col[pad(p0 + (m << b))] = x[m];
+    }
+}
+
+template<class F>
+HD void phase_step_dyn(const Pass& d, typename F::T* smem, uint32_t b, uint32_t log_e, uint32_t tid)
+{
+    switch (log_e) {
+    case 1: phase_step<F, 1>(d, smem, b, tid); break;
+    case 2: phase_step<F, 2>(d, smem, b, tid); break;
+    case 3: phase_step<F, 3>(d, smem, b, tid); break;
+    default: phase_step<F, 4>(d, smem, b, tid); break;
+    }
+}
+
+// stage schedule for a 2^R sub-NTT: full 4-stage steps first, remainder last
+HD uint32_t step_count(uint32_t R) { return (R + LG_EPT - 1) / LG_EPT; }
+HD uint32_t step_log_e(uint32_t R, uint32_t s)
+{
+    uint32_t done = s * LG_EPT;
+    return R - done >= LG_EPT ? LG_EPT : R - done;
+}
+
+// ---- phase 3: shared memory -> HBM -------------------------------------------------
+template<class F>
+HD void phase_store(const Pass& d, const Tables<F>& tb, typename F::T* out,
+                    const typename F::T* smem, uint32_t t, uint32_t tid, uint32_t nthreads)
+{
+    typedef typename F::T T;
+    const uint32_t R = d.lg_r, n_el = (1u << R) << d.lg_w, cs = col_stride(R);
+    const uint64_t ibase = tile_base(t, d.in_lg_tlo, d.in_tl, d.in_th);
+    const uint64_t obase = tile_base(t, d.out_lg_tlo, d.out_tl, d.out_th);
+    const bool row_fast = d.out_lg_sa == 0;
+#pragma unroll
+    for (uint32_t l = 0; l < EPT; l++) {
+        uint32_t e = l * nthreads + tid;
+        if (e < n_el) {
+            uint32_t v = row_fast ? (e & ((1u << R) - 1)) : (e >> d.lg_w);
+            uint32_t c = row_fast ? (e >> R) : (e & ((1u << d.lg_w) - 1));
+            uint32_t ka = d.out_rev ? brev32(v, R) : v;          // natural output row
+            T x = smem[c * cs + pad(ka)];
+            if (d.tw_mode == TW_STORE) {
+                uint32_t colv = tw_column_value(d, ibase + ((uint64_t)c << d.in_lg_sc));
+                x = F::mul(x, twiddle<F>(tb, (ka * colv) << d.tw_lsh));
+            }
+            if (d.scale)
+                x = F::mul(x, tb.ninv);
+            out[obase + ((uint64_t)v << d.out_lg_sa) + ((uint64_t)c << d.out_lg_sc)] = F::canon(x);
+        }
+    }
+}
+
+}  // namespace ntt

@@ -1,0 +1,145 @@
+// Host-side planner: turns (lg_n, order) into the pass descriptors of ntt_core.cuh.
+//
+// Mirrors the role of NTT_internal / CT_NTT / GS_NTT in the reference (ntt/ntt.cuh:100-213):
+// pick the algorithm from the requested input/output order and split lg_n into launches.
+// Orders are the reference's InputOutputOrder {NN, NR, RN, RR} (ntt/ntt.cuh:33).
+//
+// Index digits: n = s_1 + ... + s_P, A_p = s_1+..+s_(p-1) bits above digit p,
+// B_p = s_(p+1)+..+s_P bits below it.  See the derivations in DESIGN.md section 4.
+#pragma once
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "ntt_core.cuh"
+
+namespace ntt {
+
+enum Order : int { NN = 0, NR = 1, RN = 2, RR = 3 };
+
+struct Plan {
+    uint32_t lg_n;
+    std::vector<Pass> passes;
+    bool needs_scratch;
+};
+
+// lg_tile = log2 of the most elements one CTA may hold in shared memory
+inline std::vector<uint32_t> split_digits(uint32_t lg_n, uint32_t max_lg_r = LG_DENSE)
+{
+    std::vector<uint32_t> s;
+    if (const char* env = getenv("SPPARK_B200_NTT_SPLIT")) {
+        // e.g. "8,8,8": honoured when it sums to lg_n (experiments / tests)
+        uint32_t sum = 0;
+        std::vector<uint32_t> t;
+        for (const char* p = env; *p;) {
+            uint32_t v = (uint32_t)strtoul(p, const_cast<char**>(&p), 10);
+            if (v == 0 || v > max_lg_r) { t.clear(); break; }
+            t.push_back(v);
+            sum += v;
+            if (*p == ',') p++;
+        }
+        if (!t.empty() && sum == lg_n) return t;
+    }
+    uint32_t P = (lg_n + max_lg_r - 1) / max_lg_r;
+    if (P == 0) P = 1;
+    for (uint32_t p = 0; p < P; p++)            // larger digits first
+        s.push_back(lg_n / P + (p < lg_n % P ? 1 : 0));
+    return s;
+}
+
+inline Plan make_plan(uint32_t lg_n, int order, bool inverse, uint32_t lg_tile,
+                      uint32_t max_lg_w = 6)
+{
+    Plan plan;
+    plan.lg_n = lg_n;
+    const std::vector<uint32_t> s = split_digits(lg_n);
+    const uint32_t P = (uint32_t)s.size();
+    std::vector<uint32_t> A(P), B(P);
+    for (uint32_t p = 0, acc = 0; p < P; p++) { A[p] = acc; acc += s[p]; }
+    for (uint32_t p = 0; p < P; p++) B[p] = lg_n - A[p] - s[p];
+
+    const bool pingpong = (order == NN || order == RR) && P > 1;
+    plan.needs_scratch = pingpong;
+    uint32_t where = 0;                                   // buffer currently holding the data
+
+    for (uint32_t step = 0; step < P; step++) {
+        // RN runs bottom digit first, everything else top digit first
+        const uint32_t p = order == RN ? P - 1 - step : step;
+        const uint32_t R = s[p], a = A[p], b = B[p];
+        Pass d;
+        memset(&d, 0, sizeof(d));
+        d.lg_r = R;
+
+        // how many columns: fill the tile, but never wider than the digits that supply them
+        uint32_t lg_w = lg_tile > R ? lg_tile - R : 0;
+        if (lg_w > max_lg_w) lg_w = max_lg_w;
+        uint32_t avail;                                   // bits the column index may draw from
+        if (order == NR || order == RN) avail = b ? b : a;
+        else if (order == NN) avail = p == 0 ? lg_n - R : (a < lg_n - R ? a : lg_n - R);
+        else avail = p == P - 1 ? lg_n - R : (b < lg_n - R ? b : lg_n - R);
+        if (lg_w > avail) lg_w = avail;
+        d.lg_w = lg_w;
+        const uint64_t W = 1ull << lg_w;
+
+        if (order == NR || order == RN) {
+            // in place: position = hi << (R+b) | row << b | low
+            if (b) {
+                d.in_lg_tlo = b - lg_w; d.in_tl = W; d.in_th = 1ull << (R + b);
+                d.in_lg_sa = b; d.in_lg_sc = 0;
+            } else {
+                d.in_lg_tlo = 32; d.in_tl = W << R; d.in_th = 0;
+                d.in_lg_sa = 0; d.in_lg_sc = R;
+            }
+            d.out_lg_tlo = d.in_lg_tlo; d.out_tl = d.in_tl; d.out_th = d.in_th;
+            d.out_lg_sa = d.in_lg_sa; d.out_lg_sc = d.in_lg_sc;
+            d.in_rev = order == RN; d.out_rev = order == NR;
+            if (b) {
+                d.tw_mode = order == NR ? TW_STORE : TW_LOAD;
+                d.tw_rsh = 0; d.tw_bits = b; d.tw_brev = 0; d.tw_lsh = a;
+            }
+            d.src = d.dst = 0;
+        } else if (order == NN) {
+            // gather: position = row << (n-R) | q ; scatter: Jrest << (a+R) | k << a | Kdone
+            d.in_lg_tlo = 32; d.in_tl = W; d.in_th = 0;
+            d.in_lg_sa = lg_n - R; d.in_lg_sc = 0;
+            if (a == 0) {
+                d.out_lg_tlo = 32; d.out_tl = W << R; d.out_th = 0;
+                d.out_lg_sa = 0; d.out_lg_sc = R;
+            } else {
+                d.out_lg_tlo = a - lg_w; d.out_tl = W; d.out_th = 1ull << (a + R);
+                d.out_lg_sa = a; d.out_lg_sc = 0;
+            }
+            d.in_rev = 0; d.out_rev = 0;
+            if (b) {
+                d.tw_mode = TW_STORE; d.tw_rsh = a; d.tw_bits = b; d.tw_brev = 0; d.tw_lsh = a;
+            }
+        } else {
+            // RR gather: position = Q << R | row ; scatter: Kdone_r << (R+b) | rk << b | Jrest_r
+            d.in_lg_tlo = 32; d.in_tl = W << R; d.in_th = 0;
+            d.in_lg_sa = 0; d.in_lg_sc = R;
+            if (b == 0) {
+                d.out_lg_tlo = 32; d.out_tl = W << R; d.out_th = 0;
+                d.out_lg_sa = 0; d.out_lg_sc = R;
+            } else {
+                d.out_lg_tlo = b - lg_w; d.out_tl = W; d.out_th = 1ull << (R + b);
+                d.out_lg_sa = b; d.out_lg_sc = 0;
+            }
+            d.in_rev = 1; d.out_rev = 1;
+            if (b) {
+                d.tw_mode = TW_STORE; d.tw_rsh = R; d.tw_bits = b; d.tw_brev = 1; d.tw_lsh = a;
+            }
+        }
+
+        if (pingpong) {
+            // the last pass keeps positions, so it may run in place or hop back to the caller's buffer
+            d.src = where;
+            d.dst = step == P - 1 ? 0 : (where ^ 1);
+            where = d.dst;
+        }
+        d.scale = inverse && step == P - 1;
+        plan.passes.push_back(d);
+    }
+    return plan;
+}
+
+}  // namespace ntt

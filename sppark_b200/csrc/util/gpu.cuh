@@ -1,0 +1,110 @@
+// Device / stream plumbing for the hot paths.
+//
+// Plays the role of the reference's util/gpu_t.cuh (gpu_t, stream_t, select_gpu, CUDA_OK;
+// util/gpu_t.cuh:20-267, util/exception.cuh:12-21) with the same public names, redesigned
+// around stream-ordered allocation: one gpu_t per visible device, every scratch buffer comes
+// from the device's cudaMemPool (no cudaMalloc on the hot path once the pool is warm), and
+// work can be enqueued on a caller-supplied stream (PyTorch's current stream in bench.py).
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../../include/sppark_b200.h"
+
+class cuda_error : public std::runtime_error {
+    int _code;
+public:
+    cuda_error(int code, const std::string& what) : std::runtime_error(what), _code(code) {}
+    int code() const { return _code; }
+};
+
+#define CUDA_OK(expr) do {                                                          \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+        (void)cudaGetLastError();                                                   \
+        throw cuda_error(-(int)_e, std::string(cudaGetErrorString(_e)) + " @" +     \
+                         __FILE__ + ":" + std::to_string(__LINE__));                \
+    }                                                                               \
+} while (0)
+
+inline RustError rust_ok() { return RustError{0, nullptr}; }
+inline RustError rust_err(int code, const std::string& msg)
+{   return RustError{code, msg.empty() ? nullptr : strdup(msg.c_str())};   }
+
+extern std::atomic<uint64_t> g_launch_count;      // defined in api.cu
+#define COUNT_LAUNCH() (g_launch_count.fetch_add(1, std::memory_order_relaxed))
+
+class stream_t {
+    cudaStream_t s;
+    bool owned;
+public:
+    explicit stream_t(cudaStream_t borrowed) : s(borrowed), owned(false) {}
+    stream_t() : owned(true) { CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); }
+    ~stream_t() { if (owned) cudaStreamDestroy(s); }
+    stream_t(const stream_t&) = delete;
+    operator cudaStream_t() const { return s; }
+
+    void* Dmalloc(size_t bytes) const
+    {   void* p; CUDA_OK(cudaMallocAsync(&p, bytes ? bytes : 1, s)); return p;   }
+    void Dfree(void* p) const { if (p) (void)cudaFreeAsync(p, s); }
+    void HtoD(void* dst, const void* src, size_t bytes) const
+    {   CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));   }
+    void DtoH(void* dst, const void* src, size_t bytes) const
+    {   CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));   }
+    // strided host rows -> packed device rows (reference: stream_t::HtoD with pitch, util/gpu_t.cuh:84-93)
+    void HtoD2D(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows) const
+    {   CUDA_OK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyHostToDevice, s));   }
+    void sync() const { CUDA_OK(cudaStreamSynchronize(s)); }
+};
+
+// stream-ordered scratch buffer
+template<typename T> class dev_ptr_t {
+    T* p;
+    const stream_t& st;
+public:
+    dev_ptr_t(size_t n, const stream_t& s) : p((T*)s.Dmalloc(n * sizeof(T))), st(s) {}
+    ~dev_ptr_t() { st.Dfree(p); }
+    dev_ptr_t(const dev_ptr_t&) = delete;
+    operator T*() const { return p; }
+    T* get() const { return p; }
+};
+
+class gpu_t {
+    int gpu_id, cuda_id;
+    cudaDeviceProp prop;
+    std::unique_ptr<stream_t> streams[3];
+public:
+    std::mutex cache_mtx;                                   // guards per-device table caches
+    std::map<uint64_t, void*> cache;
+
+    gpu_t(int id, int cid) : gpu_id(id), cuda_id(cid)
+    {
+        CUDA_OK(cudaSetDevice(cid));
+        CUDA_OK(cudaGetDeviceProperties(&prop, cid));
+        for (auto& s : streams) s.reset(new stream_t());
+        cudaMemPool_t pool;
+        CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, cid));
+        uint64_t keep = ~0ull;                              // keep freed scratch in the pool
+        CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    int id() const { return gpu_id; }
+    int cid() const { return cuda_id; }
+    int sm_count() const { return prop.multiProcessorCount; }
+    const cudaDeviceProp& props() const { return prop; }
+    void select() const { CUDA_OK(cudaSetDevice(cuda_id)); }
+    const stream_t& operator[](size_t i) const { return *streams[i % 3]; }
+    void sync() const { for (auto& s : streams) s->sync(); }
+};
+
+const gpu_t& select_gpu(int id = 0);     // id == -1: the caller's current device
+size_t ngpus();
+const std::vector<const gpu_t*>& all_gpus();
+const gpu_t& gpu_of_current_device();

