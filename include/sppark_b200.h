@@ -97,6 +97,11 @@ RustError sppark_b200_msm(int curve, void *out_jacobian, const void *points_affi
 RustError sppark_b200_msm_dev(int curve, void *out_jacobian, const void *d_points,
                               size_t npoints, const void *d_scalars, void *stream);
 
+/* device self-test hook for the known-answer tests: r[i] = a[i] (op) b[i] through the PTX field
+ * arithmetic; field 0 = BLS12-381 fp (48 B), 1 = BLS12-381 fr, 2 = Pallas fp, 3 = Vesta fp
+ * (32 B each); op 0 mul (Montgomery), 1 add, 2 sub, 3 sqr.  Host arrays. */
+RustError sppark_b200_selftest_field(int field, int op, size_t n, void *r, const void *a, const void *b);
+
 /* introspection */
 int         sppark_b200_sm_count(int device_id);
 const char *sppark_b200_version(void);

@@ -28,6 +28,7 @@ _SIGS = {
     "sppark_b200_ntt_dev": [C.c_int, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "sppark_b200_msm": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t],
     "sppark_b200_msm_dev": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p],
+    "sppark_b200_selftest_field": [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p],
 }
 
 # every symbol include/sppark_b200.h declares (tests check the .so exports all of them)
@@ -43,7 +44,7 @@ def lib():
                               "(there is no CPU fallback)")
         l = C.CDLL(LIB_PATH)
         for name, args in _SIGS.items():
-            fn = getattr(l, name)
+            fn = getattr(l, name)      # every symbol of include/sppark_b200.h must be exported
             fn.argtypes = args
             fn.restype = RustError
         l.cuda_available.restype = C.c_int

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsppark_b200.so")
 
-SOURCES = ["api.cu", "util/gpu.cu", "ntt/ntt.cu", "msm/msm.cu"]
+SOURCES = ["api.cu", "util/gpu.cu", "ntt/ntt.cu", "msm/msm.cu", "msm/msm_bls12_381.cu", "msm/msm_pasta.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--threads", "4"]
 

@@ -23,14 +23,35 @@ struct gl64 {
     // a loose, b canonical -> loose
     static HD T add(T a, T b)
     {
+#if defined(__CUDA_ARCH__)
+        uint32_t lo, hi, c;
+        asm("{ .reg .u32 a0, a1, b0, b1;\n\t"
+            "mov.b64 {a0, a1}, %3; mov.b64 {b0, b1}, %4;\n\t"
+            "add.cc.u32 %0, a0, b0; addc.cc.u32 %1, a1, b1; addc.u32 %2, 0, 0;\n\t"
+            "neg.s32 %2, %2;\n\t"                        // 0 or 0xffffffff == EPS
+            "add.cc.u32 %0, %0, %2; addc.u32 %1, %1, 0; }"
+            : "=r"(lo), "=r"(hi), "=r"(c) : "l"(a), "l"(b));
+        return ((T)hi << 32) | lo;
+#else
         T s = a + b;
         return s < a ? s + EPS : s;           // wrapped: +2^64 == +EPS; cannot wrap twice as b < p
+#endif
     }
     // a loose, b canonical -> loose
     static HD T sub(T a, T b)
     {
+#if defined(__CUDA_ARCH__)
+        uint32_t lo, hi, c;
+        asm("{ .reg .u32 a0, a1, b0, b1;\n\t"
+            "mov.b64 {a0, a1}, %3; mov.b64 {b0, b1}, %4;\n\t"
+            "sub.cc.u32 %0, a0, b0; subc.cc.u32 %1, a1, b1; subc.u32 %2, 0, 0;\n\t"   // 0 or EPS
+            "sub.cc.u32 %0, %0, %2; subc.u32 %1, %1, 0; }"
+            : "=r"(lo), "=r"(hi), "=r"(c) : "l"(a), "l"(b));
+        return ((T)hi << 32) | lo;
+#else
         T d = a - b;
         return a < b ? d - EPS : d;           // borrowed: -2^64 == -EPS; cannot borrow twice as b < p
+#endif
     }
     static HD T reduce128(T lo, T hi)
     {
@@ -47,7 +68,27 @@ struct gl64 {
     static HD T mul(T a, T b)
     {
 #if defined(__CUDA_ARCH__)
-        return reduce128(a * b, __umul64hi(a, b));
+        // 4 wide products (each mad.lo.cc/madc.hi.cc pair is one IMAD.WIDE.U32) -> r3:r2:r1:r0,
+        // then r0 + r1*2^32 + r2*EPS - r3, one conditional +-EPS per wrap, final canonical fix
+        uint32_t r0, r1;
+        asm("{ .reg .u32 a0, a1, b0, b1, r2, r3, t;\n\t"
+            ".reg .pred q;\n\t"
+            "mov.b64 {a0, a1}, %2; mov.b64 {b0, b1}, %3;\n\t"
+            "mul.lo.u32 %0, a0, b0; mul.hi.u32 %1, a0, b0;\n\t"
+            "mul.lo.u32 r2, a1, b1; mul.hi.u32 r3, a1, b1;\n\t"
+            "mad.lo.cc.u32 %1, a0, b1, %1; madc.hi.cc.u32 r2, a0, b1, r2; addc.u32 r3, r3, 0;\n\t"
+            "mad.lo.cc.u32 %1, a1, b0, %1; madc.hi.cc.u32 r2, a1, b0, r2; addc.u32 r3, r3, 0;\n\t"
+            "sub.cc.u32 %0, %0, r3; subc.cc.u32 %1, %1, 0; subc.u32 t, 0, 0;\n\t"      // - r3*2^96
+            "sub.cc.u32 %0, %0, t; subc.u32 %1, %1, 0;\n\t"
+            "mad.lo.cc.u32 %0, r2, 0xffffffff, %0; madc.hi.cc.u32 %1, r2, 0xffffffff, %1; addc.u32 t, 0, 0;\n\t"
+            "neg.s32 t, t;\n\t"
+            "add.cc.u32 %0, %0, t; addc.u32 %1, %1, 0;\n\t"
+            "setp.eq.u32 q, %1, 0xffffffff;\n\t"
+            "@q setp.ne.u32 q, %0, 0;\n\t"
+            "@q sub.u32 %0, %0, 1;\n\t"
+            "@q mov.u32 %1, 0; }"
+            : "=r"(r0), "=r"(r1) : "l"(a), "l"(b));
+        return ((T)r1 << 32) | r0;
 #else
         unsigned __int128 x = (unsigned __int128)a * b;
         return reduce128((T)x, (T)(x >> 64));

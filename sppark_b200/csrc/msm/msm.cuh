@@ -1,0 +1,226 @@
+// msm_t<Curve>: device-side Pippenger driver (the role of the reference's msm_t,
+// msm/pippenger.cuh:325-747).  Kernels are thin __global__ wrappers over msm_core.cuh.
+#pragma once
+#include "../util/gpu.cuh"
+#include "msm_core.cuh"
+
+namespace msm {
+
+constexpr uint32_t ACC_THREADS = 128;       // accumulate CTA size
+constexpr uint32_t HEAVY_THREADS = 128;
+
+static __global__ void count_kernel(const Config cfg, const uint32_t* scalars, uint32_t* counts)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cfg.npoints; i += gridDim.x * blockDim.x)
+        count_body(cfg, scalars, counts, i);
+}
+
+// one CTA per window: exclusive prefix of the bucket histogram; heavy buckets are appended to
+// heavy_list (heavy_list[0] = count)
+static __global__ void __launch_bounds__(1024)
+scan_kernel(const Config cfg, const uint32_t* counts, uint32_t* offsets, uint32_t* cursor,
+            uint32_t* heavy_list, uint32_t heavy_cap)
+{
+    __shared__ uint32_t partial[1024];
+    const uint32_t w = blockIdx.x, nb = 1u << cfg.lg_nb;
+    const uint32_t per = (nb + blockDim.x - 1) / blockDim.x;
+    const uint32_t first = threadIdx.x * per, last = min(first + per, nb);
+    const size_t base = (size_t)w << cfg.lg_nb;
+    uint32_t sum = 0;
+    for (uint32_t b = first; b < last; b++) sum += counts[base + b];
+    partial[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the per-thread sums
+    for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
+        uint32_t v = threadIdx.x >= d ? partial[threadIdx.x - d] : 0;
+        __syncthreads();
+        partial[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = partial[threadIdx.x] - sum;
+    for (uint32_t b = first; b < last; b++) {
+        uint32_t c = counts[base + b];
+        offsets[base + b] = run;
+        cursor[base + b] = run;
+        if (c > cfg.heavy) {
+            uint32_t slot = atomicAdd(&heavy_list[0], 1);
+            if (slot < heavy_cap) heavy_list[1 + slot] = (uint32_t)(base + b);
+        }
+        run += c;
+    }
+}
+
+static __global__ void scatter_kernel(const Config cfg, const uint32_t* scalars, uint32_t* cursor, uint32_t* sorted)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cfg.npoints; i += gridDim.x * blockDim.x)
+        scatter_body(cfg, scalars, cursor, sorted, i);
+}
+
+template<class F>
+__global__ void __launch_bounds__(ACC_THREADS)
+accumulate_kernel(const Config cfg, const uint32_t* points, const uint32_t* sorted,
+                  const uint32_t* offsets, const uint32_t* counts, uint32_t* buckets,
+                  uint32_t* task_counter)
+{
+    accumulate_body<F>(cfg, points, sorted, offsets, counts, buckets, task_counter);
+}
+
+// one CTA per heavy bucket: strided partial sums, then a shared-memory tree of full adds
+template<class F>
+__global__ void __launch_bounds__(HEAVY_THREADS)
+heavy_kernel(const Config cfg, const uint32_t* points, const uint32_t* sorted,
+             const uint32_t* offsets, const uint32_t* counts, uint32_t* buckets,
+             const uint32_t* heavy_list, uint32_t heavy_cap)
+{
+    extern __shared__ __align__(16) uint32_t tree[];         // HEAVY_THREADS xyzz slots
+    uint32_t nheavy = min(heavy_list[0], heavy_cap);
+    for (uint32_t hidx = blockIdx.x; hidx < nheavy; hidx += gridDim.x) {
+        const uint32_t t = heavy_list[1 + hidx], cnt = counts[t];
+        const uint32_t* run = sorted + (size_t)(t >> cfg.lg_nb) * cfg.npoints + offsets[t];
+        ec::xyzz_t<F> acc;
+        acc.set_inf();
+        for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x)
+            acc.madd(load_point<F>(points, run[k]));
+        store_bucket<F>(tree, threadIdx.x, acc);
+        __syncthreads();
+        for (uint32_t d = blockDim.x / 2; d > 0; d >>= 1) {
+            if (threadIdx.x < d) {
+                acc.add(load_bucket<F>(tree, threadIdx.x + d));
+                store_bucket<F>(tree, threadIdx.x, acc);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) store_bucket<F>(buckets, t, acc);
+        __syncthreads();
+    }
+}
+
+template<class F>
+__global__ void __launch_bounds__(128)
+reduce1_kernel(const Config cfg, const uint32_t* buckets, uint32_t lg_l, uint32_t nitems,
+               uint32_t* outR, uint32_t* outS)
+{
+    uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item < nitems) reduce1_body<F>(cfg, buckets, lg_l, outR, outS, item);
+}
+
+template<class F>
+__global__ void __launch_bounds__(128)
+combine_kernel(const uint32_t* inR, const uint32_t* inS, uint32_t G, uint32_t lg_span,
+               uint32_t nitems, uint32_t* outR, uint32_t* outS)
+{
+    uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item < nitems) combine_body<F>(inR, inS, G, lg_span, outR, outS, item);
+}
+
+template<class F>
+__global__ void finish_kernel(const Config cfg, const uint32_t* winR, uint32_t* out)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) finish_body<F>(cfg, winR, out);
+}
+
+// host rows {X, Y, [flag]} at `stride` bytes -> packed {X, Y}; flagged rows become (0,0)
+// (reference: Affine_inf_t::mem_t, ec/affine_t.hpp:91-121; stream_t::HtoD pitch copy)
+static __global__ void pack_points_kernel(const uint8_t* in, size_t stride, uint32_t words, bool has_flag,
+                                   uint32_t* out, uint32_t npoints)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npoints; i += gridDim.x * blockDim.x) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (size_t)i * stride);
+        bool inf = has_flag && (in[(size_t)i * stride + 4 * words] & 1);
+        for (uint32_t k = 0; k < words; k++) out[(size_t)i * words + k] = inf ? 0 : src[k];
+    }
+}
+
+template<class F>
+class msm_t {
+    const gpu_t& gpu;
+    static constexpr uint32_t PW = 2 * F::N, BW = 4 * F::N, JW = 3 * F::N;   // words per affine/xyzz/jacobian
+
+public:
+    explicit msm_t(const gpu_t& g) : gpu(g) {}
+
+    // all inputs device-resident: d_points packed affine, d_scalars 8 words each.
+    // d_out: JW words of device memory.  Enqueues on `stream`; no synchronisation.
+    void invoke_dev(uint32_t* d_out, const uint32_t* d_points, size_t npoints,
+                    const uint32_t* d_scalars, cudaStream_t stream)
+    {
+        if (npoints == 0) {
+            CUDA_OK(cudaMemsetAsync(d_out, 0, JW * 4, stream));
+            return;
+        }
+        if (npoints >= (1ull << 31))
+            throw cuda_error(-(int)cudaErrorInvalidValue, "msm: npoints must be < 2^31");
+        const Config cfg = make_config(npoints);
+        const size_t nslots = (size_t)cfg.nwins << cfg.lg_nb;
+        const uint32_t heavy_cap = (uint32_t)((uint64_t)cfg.nwins * npoints / (cfg.heavy ? cfg.heavy : 1) + 1);
+        const uint32_t sms = (uint32_t)gpu.sm_count();
+
+        // level-1 chunking of the running sums: at most 4096 items per window
+        const uint32_t lg_l = cfg.lg_nb > 12 ? cfg.lg_nb - 12 : 0;
+        const uint32_t items1 = cfg.nwins << (cfg.lg_nb - lg_l);
+
+        // one stream-ordered blob
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+        const size_t o_counts = take(nslots * 4), o_offsets = take(nslots * 4), o_cursor = take(nslots * 4);
+        const size_t o_misc = take((2 + heavy_cap) * 4);
+        const size_t o_sorted = take((size_t)cfg.nwins * npoints * 4);
+        const size_t o_buckets = take(nslots * BW * 4);
+        const size_t o_r0 = take((size_t)items1 * BW * 4), o_s0 = take((size_t)items1 * BW * 4);
+        const size_t o_r1 = take((size_t)items1 * BW * 4 / 2 + 4096), o_s1 = take((size_t)items1 * BW * 4 / 2 + 4096);
+        uint8_t* blob;
+        CUDA_OK(cudaMallocAsync((void**)&blob, off, stream));
+        auto U32 = [&](size_t o) { return reinterpret_cast<uint32_t*>(blob + o); };
+        uint32_t *counts = U32(o_counts), *offsets = U32(o_offsets), *cursor = U32(o_cursor);
+        uint32_t *task_counter = U32(o_misc), *heavy_list = U32(o_misc) + 1;
+        uint32_t *sorted = U32(o_sorted), *buckets = U32(o_buckets);
+
+        CUDA_OK(cudaMemsetAsync(counts, 0, nslots * 4, stream));
+        CUDA_OK(cudaMemsetAsync(task_counter, 0, 8, stream));
+
+        const uint32_t nblk = (uint32_t)std::min<size_t>((npoints + 255) / 256, (size_t)sms * 16);
+        count_kernel<<<nblk, 256, 0, stream>>>(cfg, d_scalars, counts);
+        COUNT_LAUNCH();
+        scan_kernel<<<cfg.nwins, 1024, 0, stream>>>(cfg, counts, offsets, cursor, heavy_list, heavy_cap);
+        COUNT_LAUNCH();
+        scatter_kernel<<<nblk, 256, 0, stream>>>(cfg, d_scalars, cursor, sorted);
+        COUNT_LAUNCH();
+        CUDA_OK(cudaGetLastError());
+
+        int occ = 1;
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, accumulate_kernel<F>, ACC_THREADS, 0));
+        if (occ < 1) occ = 1;
+        size_t want = (nslots + ACC_THREADS - 1) / ACC_THREADS;
+        uint32_t acc_blocks = (uint32_t)std::min<size_t>(want, (size_t)sms * occ);
+        accumulate_kernel<F><<<acc_blocks, ACC_THREADS, 0, stream>>>(cfg, d_points, sorted, offsets, counts,
+                                                                    buckets, task_counter);
+        COUNT_LAUNCH();
+        heavy_kernel<F><<<sms, HEAVY_THREADS, HEAVY_THREADS * BW * 4, stream>>>(
+            cfg, d_points, sorted, offsets, counts, buckets, heavy_list, heavy_cap);
+        COUNT_LAUNCH();
+        CUDA_OK(cudaGetLastError());
+
+        // running sums
+        uint32_t *R[2] = {U32(o_r0), U32(o_r1)}, *S[2] = {U32(o_s0), U32(o_s1)};
+        reduce1_kernel<F><<<(items1 + 127) / 128, 128, 0, stream>>>(cfg, buckets, lg_l, items1, R[0], S[0]);
+        COUNT_LAUNCH();
+        uint32_t per_win = 1u << (cfg.lg_nb - lg_l), lg_span = lg_l, cur = 0;
+        while (per_win > 1) {
+            uint32_t lg_g = 31 - __builtin_clz(per_win);
+            if (lg_g > 4) lg_g = 4;                         // radix 16 keeps the serial chains short
+            uint32_t G = 1u << lg_g, nitems = cfg.nwins * (per_win >> lg_g);
+            combine_kernel<F><<<(nitems + 127) / 128, 128, 0, stream>>>(R[cur], S[cur], G, lg_span, nitems,
+                                                                       R[cur ^ 1], S[cur ^ 1]);
+            COUNT_LAUNCH();
+            per_win >>= lg_g;
+            lg_span += lg_g;
+            cur ^= 1;
+        }
+        finish_kernel<F><<<1, 32, 0, stream>>>(cfg, R[cur], d_out);
+        COUNT_LAUNCH();
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaFreeAsync(blob, stream));
+    }
+};
+
+}  // namespace msm

@@ -1,0 +1,271 @@
+// Pippenger bucket MSM: per-thread bodies of every kernel on the path, written HD so that
+// tests/emu/msm_emu.cpp can single-step the same logic on the CPU.
+//
+// Pipeline (one slice of points, all device-resident):
+//   count      scalars -> signed c-bit digits, histogram per (window, bucket)   [L2 atomics]
+//   scan       per-window exclusive prefix -> bucket offsets, list of heavy buckets
+//   scatter    scalars -> digits again, point index (+sign) into its bucket's slot
+//   accumulate every lane owns one bucket at a time and streams its points through an XYZZ
+//              mixed add; lanes fetch the next bucket from a global counter the moment they
+//              finish, so a warp never waits for its longest bucket
+//   heavy      buckets longer than `heavy` entries: one CTA each, strided partial sums + tree
+//   reduce     sum_b (b+1)*B[w][b] by chunked running sums, then radix-G combine levels
+//   finish     Horner over the windows, XYZZ -> Jacobian
+//
+// Reference counterparts: breakdown (msm/pippenger.cuh:72-121), sort (msm/sort.cuh:366),
+// accumulate (:145-223), batch_addition (msm/batch_addition.cuh:134), integrate (:225-296),
+// host collect (:627-727).  Digit convention differs (plain two's-complement-free signed
+// windows here, Booth there); only the group element is part of the contract
+// (poc/msm-cuda/tests/msm.rs:27-38 compares after affine normalisation).
+#pragma once
+#include "../ec/xyzz.cuh"
+
+namespace msm {
+
+struct Config {
+    uint32_t wbits;        // c: window width
+    uint32_t nwins;        // ceil(256 / c)
+    uint32_t lg_nb;        // c - 1: log2(buckets per window)
+    uint32_t npoints;
+    uint32_t heavy;        // buckets with more entries go to the cooperative kernel
+};
+
+HD uint32_t atomic_inc(uint32_t* p, uint32_t v = 1)
+{
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#else
+    uint32_t old = *p;
+    *p += v;
+    return old;
+#endif
+}
+
+// 256-bit little-endian scalar -> signed digits d_w in (-2^(c-1), 2^(c-1)], sum d_w 2^(cw) = s.
+struct Digits {
+    uint32_t s[8];
+    uint32_t carry;
+    HD explicit Digits(const uint32_t* p) : carry(0)
+    {
+#if defined(__CUDA_ARCH__)
+        uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
+        s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
+        s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+#else
+        for (int i = 0; i < 8; i++) s[i] = p[i];
+#endif
+    }
+    // windows must be requested in order w = 0, 1, ...; returns bucket (|d|-1) and sign,
+    // or false for a zero digit
+    HD bool next(uint32_t w, uint32_t c, uint32_t& bucket, uint32_t& neg)
+    {
+        uint32_t off = w * c, i = off >> 5, sh = off & 31;
+        uint32_t lo = i < 8 ? s[i] : 0, hi = i + 1 < 8 ? s[i + 1] : 0;
+        uint32_t raw = sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+        raw = (c < 32 ? raw & ((1u << c) - 1) : raw) + carry;
+        const uint32_t half = 1u << (c - 1);
+        if (raw > half) {
+            neg = 1;
+            carry = 1;
+            raw = (1u << c) - raw;             // magnitude of the negative digit
+        } else {
+            neg = 0;
+            carry = 0;
+        }
+        bucket = raw - 1;
+        return raw != 0;
+    }
+};
+
+// ---- count / scatter -----------------------------------------------------------------
+HD void count_body(const Config& cfg, const uint32_t* scalars, uint32_t* counts, uint32_t i)
+{
+    Digits d(scalars + 8 * (size_t)i);
+    for (uint32_t w = 0; w < cfg.nwins; w++) {
+        uint32_t b, neg;
+        if (d.next(w, cfg.wbits, b, neg))
+            atomic_inc(&counts[((size_t)w << cfg.lg_nb) + b]);
+    }
+}
+
+HD void scatter_body(const Config& cfg, const uint32_t* scalars, uint32_t* cursor,
+                     uint32_t* sorted, uint32_t i)
+{
+    Digits d(scalars + 8 * (size_t)i);
+    for (uint32_t w = 0; w < cfg.nwins; w++) {
+        uint32_t b, neg;
+        if (d.next(w, cfg.wbits, b, neg)) {
+            uint32_t pos = atomic_inc(&cursor[((size_t)w << cfg.lg_nb) + b]);
+            sorted[(size_t)w * cfg.npoints + pos] = i | (neg << 31);
+        }
+    }
+}
+
+// ---- point gather -----------------------------------------------------------------------
+template<class F>
+HD ec::affine_t<F> load_point(const uint32_t* points, uint32_t entry)
+{
+    constexpr int W = 2 * F::N;                       // words per affine point
+    const uint32_t* p = points + (size_t)(entry & 0x7fffffffu) * W;
+    ec::affine_t<F> a;
+#if defined(__CUDA_ARCH__)
+    static_assert(W % 4 == 0, "affine point must be a whole number of 16-byte words");
+    uint32_t buf[W];
+#pragma unroll
+    for (int k = 0; k < W / 4; k++) {
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + k);
+        buf[4 * k] = v.x; buf[4 * k + 1] = v.y; buf[4 * k + 2] = v.z; buf[4 * k + 3] = v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < F::N; k++) { a.X.l[k] = buf[k]; a.Y.l[k] = buf[F::N + k]; }
+#else
+    for (int k = 0; k < F::N; k++) { a.X.l[k] = p[k]; a.Y.l[k] = p[F::N + k]; }
+#endif
+    if (entry >> 31) a.Y = a.Y.neg();
+    return a;
+}
+
+template<class F>
+HD void store_bucket(uint32_t* buckets, size_t slot, const ec::xyzz_t<F>& b)
+{
+    constexpr int W = 4 * F::N;
+    uint32_t* p = buckets + slot * W;
+#pragma unroll
+    for (int k = 0; k < F::N; k++) {
+        p[k] = b.X.l[k]; p[F::N + k] = b.Y.l[k]; p[2 * F::N + k] = b.ZZZ.l[k]; p[3 * F::N + k] = b.ZZ.l[k];
+    }
+}
+
+template<class F>
+HD ec::xyzz_t<F> load_bucket(const uint32_t* buckets, size_t slot)
+{
+    constexpr int W = 4 * F::N;
+    const uint32_t* p = buckets + slot * W;
+    ec::xyzz_t<F> b;
+#pragma unroll
+    for (int k = 0; k < F::N; k++) {
+        b.X.l[k] = p[k]; b.Y.l[k] = p[F::N + k]; b.ZZZ.l[k] = p[2 * F::N + k]; b.ZZ.l[k] = p[3 * F::N + k];
+    }
+    return b;
+}
+
+// ---- accumulate: one lane, many buckets ---------------------------------------------------
+// Every lane repeatedly claims the next (window,bucket) from `task_counter` and folds that
+// bucket's points.  Empty buckets are written as infinity, heavy ones are skipped (the
+// cooperative kernel owns them).
+template<class F>
+HD void accumulate_body(const Config& cfg, const uint32_t* points, const uint32_t* sorted,
+                        const uint32_t* offsets, const uint32_t* counts, uint32_t* buckets,
+                        uint32_t* task_counter)
+{
+    const uint32_t total = cfg.nwins << cfg.lg_nb;
+    ec::xyzz_t<F> acc;
+    for (;;) {
+        uint32_t t, cnt;
+        for (;;) {
+            t = atomic_inc(task_counter);
+            if (t >= total) return;
+            cnt = counts[t];
+            if (cnt == 0) {
+                acc.set_inf();
+                store_bucket<F>(buckets, t, acc);
+                continue;
+            }
+            if (cnt > cfg.heavy) continue;
+            break;
+        }
+        const uint32_t* run = sorted + (size_t)(t >> cfg.lg_nb) * cfg.npoints + offsets[t];
+        acc.set_inf();
+        for (uint32_t k = 0; k < cnt; k++)
+            acc.madd(load_point<F>(points, run[k]));
+        store_bucket<F>(buckets, t, acc);
+    }
+}
+
+// ---- reduce: chunked running sums -----------------------------------------------------------
+// level 1: item = one bucket.  Thread (w, chunk) folds L = 2^lg_l consecutive buckets into
+//   S = sum B_k,  R = sum (k+1) B_k   (k local)
+template<class F>
+HD void reduce1_body(const Config& cfg, const uint32_t* buckets, uint32_t lg_l,
+                     uint32_t* outR, uint32_t* outS, uint32_t item)
+{
+    const size_t first = (size_t)item << lg_l;
+    ec::xyzz_t<F> acc, res;
+    acc.set_inf();
+    res.set_inf();
+    for (uint32_t k = 1u << lg_l; k-- > 0;) {
+        acc.add(load_bucket<F>(buckets, first + k));
+        res.add(acc);
+    }
+    store_bucket<F>(outR, item, res);
+    store_bucket<F>(outS, item, acc);
+}
+
+// level >= 2: G consecutive items (R_i, S_i), each spanning 2^lg_span buckets, become one:
+//   S = sum S_i,  R = sum R_i + 2^lg_span * sum i*S_i
+template<class F>
+HD void combine_body(const uint32_t* inR, const uint32_t* inS, uint32_t G, uint32_t lg_span,
+                     uint32_t* outR, uint32_t* outS, uint32_t item)
+{
+    const size_t first = (size_t)item * G;
+    ec::xyzz_t<F> acc, weighted, rsum;
+    acc.set_inf();
+    weighted.set_inf();
+    rsum.set_inf();
+    for (uint32_t i = G; i-- > 0;) {
+        rsum.add(load_bucket<F>(inR, first + i));
+        acc.add(load_bucket<F>(inS, first + i));
+        if (i) weighted.add(acc);                    // sum_{i>=1} i*S_i
+    }
+    for (uint32_t d = 0; d < lg_span; d++) weighted.dbl();
+    rsum.add(weighted);
+    store_bucket<F>(outR, item, rsum);
+    store_bucket<F>(outS, item, acc);
+}
+
+// finish: out = sum_w 2^(c*w) * R_w, as a Jacobian point with canonical coordinates
+template<class F>
+HD void finish_body(const Config& cfg, const uint32_t* winR, uint32_t* out_jacobian)
+{
+    ec::xyzz_t<F> acc = load_bucket<F>(winR, cfg.nwins - 1);
+    for (uint32_t w = cfg.nwins - 1; w-- > 0;) {
+        for (uint32_t d = 0; d < cfg.wbits; d++) acc.dbl();
+        acc.add(load_bucket<F>(winR, w));
+    }
+    ec::jacobian_t<F> j = acc.to_jacobian();
+#pragma unroll
+    for (int k = 0; k < F::N; k++) {
+        out_jacobian[k] = j.X.l[k]; out_jacobian[F::N + k] = j.Y.l[k]; out_jacobian[2 * F::N + k] = j.Z.l[k];
+    }
+}
+
+// window width minimising  nwins*(n + ~2.8*2^(c-1))  mixed-add equivalents
+inline uint32_t choose_wbits(size_t npoints)
+{
+    uint32_t best = 4;
+    double best_cost = 1e300;
+    for (uint32_t c = 4; c <= 22; c++) {
+        uint32_t nwins = (256 + c - 1) / c;
+        double cost = (double)nwins * ((double)npoints + 2.8 * (double)(1u << (c - 1)));
+        if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    if (const char* env = getenv("SPPARK_B200_MSM_WBITS")) {
+        uint32_t c = (uint32_t)atoi(env);
+        if (c >= 2 && c <= 24) best = c;
+    }
+    return best;
+}
+
+inline Config make_config(size_t npoints)
+{
+    Config cfg;
+    cfg.wbits = choose_wbits(npoints);
+    cfg.nwins = (256 + cfg.wbits - 1) / cfg.wbits;
+    cfg.lg_nb = cfg.wbits - 1;
+    cfg.npoints = (uint32_t)npoints;
+    cfg.heavy = 2048;
+    if (const char* env = getenv("SPPARK_B200_MSM_HEAVY")) cfg.heavy = (uint32_t)atoi(env);
+    return cfg;
+}
+
+}  // namespace msm

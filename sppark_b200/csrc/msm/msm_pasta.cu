@@ -1,0 +1,14 @@
+// Pallas / Vesta MSM (BASELINE.json config 4; the reference has no PoC boundary for Pasta, so
+// these are reached through sppark_b200_msm / sppark_b200_msm_dev).
+#include "msm_host.cuh"
+
+RustError msm_host_pallas(void* out, const void* points, size_t npoints, const void* scalars,
+                          size_t stride, bool has_flag)
+{   return msm_host<ff::pallas_fp_t>(out, points, npoints, scalars, stride, has_flag);   }
+RustError msm_dev_pallas(void* out, const void* d_points, size_t npoints, const void* d_scalars, void* stream)
+{   return msm_dev<ff::pallas_fp_t>(out, d_points, npoints, d_scalars, stream);   }
+RustError msm_host_vesta(void* out, const void* points, size_t npoints, const void* scalars,
+                         size_t stride, bool has_flag)
+{   return msm_host<ff::vesta_fp_t>(out, points, npoints, scalars, stride, has_flag);   }
+RustError msm_dev_vesta(void* out, const void* d_points, size_t npoints, const void* d_scalars, void* stream)
+{   return msm_dev<ff::vesta_fp_t>(out, d_points, npoints, d_scalars, stream);   }

@@ -8,9 +8,11 @@
 #if defined(__CUDACC__)
 # define HD __host__ __device__ __forceinline__
 # define DEV __device__ __forceinline__
+# define HD_NOINLINE __host__ __device__ __noinline__
 #else
 # define HD inline
 # define DEV inline
+# define HD_NOINLINE
 #endif
 
 HD uint32_t brev32(uint32_t x, uint32_t nbits)

@@ -1,0 +1,98 @@
+"""Host-side mirror of the reference's msm-cuda crate (poc/msm-cuda/src/lib.rs:18-81):
+multi_scalar_mult (blst layout, 96-byte affine points) and multi_scalar_mult_arkworks
+(arkworks layout, 104-byte G1Affine with an infinity flag), through the C-ABI.
+
+Arrays: points (n, 12) uint64 [or (n, 13) for the arkworks layout: X, Y, flag word],
+scalars (n, 4) uint64 little-endian, result (18,) uint64 = Jacobian {X, Y, Z} in Montgomery form.
+"""
+import numpy as np
+
+from . import _lib
+
+BLS12_381_G1, PALLAS, VESTA = 0, 1, 2
+_LIMBS = {BLS12_381_G1: 6, PALLAS: 4, VESTA: 4}
+
+
+def _check(points, scalars):
+    if points.shape[0] != scalars.shape[0]:
+        raise ValueError("length mismatch")                  # same panic as the crate (lib.rs:33-35)
+    if not (points.flags["C_CONTIGUOUS"] and scalars.flags["C_CONTIGUOUS"]):
+        raise TypeError("points and scalars must be C-contiguous")
+    if points.dtype != np.uint64 or scalars.dtype != np.uint64 or scalars.shape[1] != 4:
+        raise TypeError("points/scalars must be uint64 limb arrays")
+
+
+def multi_scalar_mult(points, scalars):
+    """blst_p1_affine[] x blst_scalar[] -> blst_p1  via mult_pippenger."""
+    _check(points, scalars)
+    assert points.shape[1] == 12
+    out = np.zeros(18, dtype=np.uint64)
+    err = _lib.lib().mult_pippenger(out.ctypes.data, points.ctypes.data, points.shape[0], scalars.ctypes.data)
+    _lib.check(err)
+    return out
+
+
+def multi_scalar_mult_arkworks(points, scalars):
+    """ark G1Affine[] (X, Y, infinity flag; size_of::<G1Affine>() == 104) x BigInteger256[]
+    via mult_pippenger_inf."""
+    _check(points, scalars)
+    assert points.shape[1] == 13
+    out = np.zeros(18, dtype=np.uint64)
+    err = _lib.lib().mult_pippenger_inf(out.ctypes.data, points.ctypes.data, points.shape[0],
+                                        scalars.ctypes.data, points.strides[0])
+    _lib.check(err)
+    return out
+
+
+def msm(curve, points, scalars):
+    """Any supported curve, packed affine host arrays."""
+    _check(points, scalars)
+    nl = _LIMBS[curve]
+    assert points.shape[1] == 2 * nl
+    out = np.zeros(3 * nl, dtype=np.uint64)
+    err = _lib.lib().sppark_b200_msm(curve, out.ctypes.data, points.ctypes.data, points.shape[0],
+                                     scalars.ctypes.data, points.strides[0])
+    _lib.check(err)
+    return out
+
+
+def msm_dev(curve, d_points, d_scalars, npoints=None, stream=None):
+    """msm_t::invoke with device-resident inputs (msm/pippenger.cuh:582-601): torch CUDA tensors
+    of packed affine points / 32-byte scalars; synchronises the stream and returns the Jacobian
+    result as a host array."""
+    import torch
+    nl = _LIMBS[curve]
+    assert d_points.is_cuda and d_scalars.is_cuda and d_points.is_contiguous() and d_scalars.is_contiguous()
+    n = npoints if npoints is not None else d_scalars.numel() * d_scalars.element_size() // 32
+    out = np.zeros(3 * nl, dtype=np.uint64)
+    with torch.cuda.device(d_points.device):
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        err = _lib.lib().sppark_b200_msm_dev(curve, out.ctypes.data, d_points.data_ptr(), n,
+                                             d_scalars.data_ptr(), s)
+    _lib.check(err)
+    return out
+
+
+def selftest_field(field, op, a, b):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    b = np.ascontiguousarray(b, dtype=np.uint64)
+    r = np.zeros_like(a)
+    err = _lib.lib().sppark_b200_selftest_field(field, {"mul": 0, "add": 1, "sub": 2, "sqr": 3}[op],
+                                                a.shape[0], r.ctypes.data, a.ctypes.data, b.ctypes.data)
+    _lib.check(err)
+    return r
+
+
+def smoke():
+    """One tiny MSM on cuda:0 checked against the CPU oracle (used by __graft_entry__.smoke)."""
+    from oracle import pyoracle
+    rng = np.random.default_rng(7)
+    n = 1000
+    pts = pyoracle.gen_points("bls12_381", 64)[np.arange(n) % 64].copy()
+    sc = rng.integers(0, 2**63, size=(n, 4), dtype=np.uint64)
+    sc[:, 3] >>= np.uint64(2)
+    got = multi_scalar_mult(pts, sc)
+    want = pyoracle.msm("bls12_381", pts, sc, "pippenger", ncpus=4)
+    a = pyoracle.jac_to_affine("bls12_381", got)
+    b = pyoracle.jac_to_affine("bls12_381", want)
+    assert np.array_equal(a, b), "MSM mismatch vs oracle"

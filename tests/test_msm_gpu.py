@@ -1,0 +1,144 @@
+"""GPU parity for the MSM path: CUDA through the C-ABI vs the CPU oracle.  MSM results are
+compared as group elements (affine-normalised), as the reference's own tests do
+(poc/msm-cuda/tests/msm.rs:27-38); field arithmetic is compared bit-exactly."""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+R_BLS = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+FIELDS = [("bls12_381_fp", 0, 6), ("bls12_381_fr", 1, 4), ("pallas_fp", 2, 4), ("vesta_fp", 3, 4)]
+
+
+def _limbs(x, n):
+    return [(x >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(n)]
+
+
+def _int(row):
+    return sum(int(v) << (64 * i) for i, v in enumerate(row))
+
+
+@pytest.mark.parametrize("name,fid,nl", FIELDS)
+def test_field_kat_ptx(oracle, name, fid, nl):
+    """PTX Montgomery arithmetic vs Python big integers (bit-exact), incl. edge values."""
+    from sppark_b200 import msm
+    p = oracle.ff_consts(name)["p"]
+    R = 1 << (64 * nl)
+    rnd = random.Random(fid)
+    vals = [0, 1, p - 1, p - 2, 2, (1 << (64 * nl - 1)) % p, R % p] + [rnd.randrange(p) for _ in range(2000)]
+    a = np.array([_limbs(v, nl) for v in vals], dtype=np.uint64)
+    b = np.array([_limbs(v, nl) for v in reversed(vals)], dtype=np.uint64)
+    Rinv = pow(R, -1, p)
+    for op, fn in (("mul", lambda x, y: x * y * Rinv % p), ("add", lambda x, y: (x + y) % p),
+                   ("sub", lambda x, y: (x - y) % p), ("sqr", lambda x, y: x * x * Rinv % p)):
+        r = msm.selftest_field(fid, op, a, b)
+        for i in range(len(vals)):
+            assert _int(r[i]) == fn(vals[i], vals[len(vals) - 1 - i]), (name, op, i)
+
+
+def _scalars(n, seed, r=R_BLS):
+    rnd = random.Random(seed)
+    return np.array([_limbs(rnd.randrange(r), 4) for _ in range(n)], dtype=np.uint64).reshape(n, 4)
+
+
+def _same_point(oracle, curve, a, b):
+    return np.array_equal(oracle.jac_to_affine(curve, a), oracle.jac_to_affine(curve, b))
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 193, 1000, 4096, 1 << 14])
+def test_bls12_381_msm_matches_oracle(oracle, n):
+    from sppark_b200 import msm
+    base = oracle.gen_points("bls12_381", min(n, 2048))
+    pts = base[np.arange(n) % base.shape[0]].copy()
+    if n > 3:
+        pts[3] = 0                                  # point at infinity, as util.rs:29-31 plants one
+    sc = _scalars(n, n)
+    got = msm.multi_scalar_mult(pts, sc)
+    want = oracle.msm("bls12_381", pts, sc, "pippenger", ncpus=8)
+    assert _same_point(oracle, "bls12_381", got, want)
+
+
+@pytest.mark.parametrize("kind", ["zero", "one", "r_minus_1", "all_same", "pm_pairs", "one_heavy"])
+def test_bls12_381_msm_adversarial(oracle, kind):
+    from sppark_b200 import msm
+    n = 5000
+    base = oracle.gen_points("bls12_381", 16)
+    pts = base[np.arange(n) % 16].copy()
+    p = oracle.ff_consts("bls12_381_fp")["p"]
+    if kind == "zero":
+        sc = np.zeros((n, 4), dtype=np.uint64)
+    elif kind == "one":
+        sc = np.tile(np.array(_limbs(1, 4), dtype=np.uint64), (n, 1))
+    elif kind == "r_minus_1":
+        sc = np.tile(np.array(_limbs(R_BLS - 1, 4), dtype=np.uint64), (n, 1))
+    elif kind == "all_same":
+        sc = np.tile(np.array(_limbs(0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF, 4), dtype=np.uint64), (n, 1))
+    elif kind == "pm_pairs":
+        sc = np.tile(np.array(_limbs(12345, 4), dtype=np.uint64), (n, 1))
+        for i in range(1, n, 2):                    # odd rows: the negated previous point
+            pts[i, :6] = pts[i - 1, :6]
+            pts[i, 6:] = np.array(_limbs(p - _int(pts[i - 1, 6:]), 6), dtype=np.uint64)
+    else:
+        sc = _scalars(n, 99)
+        sc[: n // 2] = sc[0]                        # half of the points share every bucket
+    got = msm.multi_scalar_mult(pts, sc)
+    want = oracle.msm("bls12_381", pts, sc, "pippenger", ncpus=8)
+    assert _same_point(oracle, "bls12_381", got, want)
+    if kind in ("zero", "pm_pairs"):
+        assert not got[12:].any()                   # infinity encodes as Z == 0
+
+
+def test_mult_pippenger_inf_layout(oracle):
+    """arkworks G1Affine layout: 104-byte rows, infinity flag in the byte after Y
+    (pippenger_inf.cu:28-34, ec/affine_t.hpp:91-96)."""
+    from sppark_b200 import msm
+    n = 3000
+    base = oracle.gen_points("bls12_381", 128)
+    pts = np.zeros((n, 13), dtype=np.uint64)
+    pts[:, :12] = base[np.arange(n) % 128]
+    pts[::7, 12] = 1                                # flagged rows keep garbage coordinates on purpose
+    sc = _scalars(n, 5)
+    got = msm.multi_scalar_mult_arkworks(pts, sc)
+    clean = pts[:, :12].copy()
+    clean[::7] = 0
+    want = oracle.msm("bls12_381", clean, sc, "pippenger", ncpus=8)
+    assert _same_point(oracle, "bls12_381", got, want)
+
+
+@pytest.mark.parametrize("curve,cid", [("pallas", 1), ("vesta", 2)])
+def test_pasta_msm_matches_oracle(oracle, curve, cid):
+    from sppark_b200 import msm
+    n = 6000
+    r = oracle.ff_consts("vesta_fp" if curve == "pallas" else "pallas_fp")["p"]
+    base = oracle.gen_points(curve, 256)
+    pts = base[np.arange(n) % 256].copy()
+    sc = _scalars(n, 11, r)
+    got = msm.msm(cid, pts, sc)
+    want = oracle.msm(curve, pts, sc, "pippenger", ncpus=8)
+    assert _same_point(oracle, curve, got, want)
+
+
+def test_bls12_381_msm_2pow20_folded(oracle):
+    """2^20 points = 2^10 distinct points replicated: sum_i s_i P_(i mod m) equals the m-point MSM
+    with scalars folded mod r, which the oracle finishes in seconds."""
+    from sppark_b200 import msm
+    n, m = 1 << 20, 1 << 10
+    base = oracle.gen_points("bls12_381", m)
+    pts = np.tile(base, (n // m, 1))
+    rng = np.random.default_rng(42)
+    sc = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
+    sc[:, 3] >>= np.uint64(2)                         # < 2^254 < r
+    got = msm.multi_scalar_mult(pts, sc)
+    folded = np.zeros((m, 4), dtype=np.uint64)
+    ints = [0] * m
+    scl = sc.reshape(n // m, m, 4)
+    for limb in range(4):
+        col = scl[:, :, limb].astype(object).sum(axis=0)
+        for j in range(m):
+            ints[j] += int(col[j]) << (64 * limb)
+    for j in range(m):
+        folded[j] = _limbs(ints[j] % R_BLS, 4)
+    want = oracle.msm("bls12_381", base, folded, "pippenger", ncpus=8)
+    assert _same_point(oracle, "bls12_381", got, want)
