@@ -48,8 +48,11 @@ typedef struct {
  * bb31        uint32 Montgomery residue, R = 2^32                 (ff/mont32_t.cuh:20-41)
  */
 
-enum { SPPARK_NTT_NN = 0, SPPARK_NTT_NR = 1, SPPARK_NTT_RN = 2, SPPARK_NTT_RR = 3 };
-                                               /* NTT::InputOutputOrder, ntt/ntt.cuh:33 */
+enum { SPPARK_NTT_NN = 0, SPPARK_NTT_NR = 1, SPPARK_NTT_RN = 2, SPPARK_NTT_RR = 3,
+                                               /* NTT::InputOutputOrder, ntt/ntt.cuh:33.  RR follows
+                                                  the reference: same transform as NN (its tests
+                                                  assert NN == RR), bit-reversed coset exponents */
+       SPPARK_NTT_BB = 4 };                    /* extension: bit-reversed input AND output */
 enum { SPPARK_NTT_FORWARD = 0, SPPARK_NTT_INVERSE = 1 };   /* NTT::Direction, ntt/ntt.cuh:34 */
 enum { SPPARK_NTT_STANDARD = 0, SPPARK_NTT_COSET = 1 };    /* NTT::Type,      ntt/ntt.cuh:35 */
 

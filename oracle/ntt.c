@@ -169,8 +169,13 @@ static inline size_t bitrev(size_t i, unsigned lg)
         size_t n = (size_t)1 << lg;                                                            \
         for (size_t i = 0; i < n; i++)                                                         \
             a[i] = REDUCE(a[i]);                                                               \
-        int in_rev = order == ORACLE_RN || order == ORACLE_RR;                                 \
-        int out_rev = order == ORACLE_NR || order == ORACLE_RR;                                \
+        /* reference semantics (ntt/ntt.cuh:174-212): RR = GS on NATURAL input + bit_rev,    */ \
+        /* i.e. the same transform as NN (its own tests assert NN == RR, tests/ntt.rs:28-30); */ \
+        /* only its coset exponents are bit-reversed (LDE_powers is handed bitrev = true).    */ \
+        /* ORACLE_BB is the strict bit-reversed-in / bit-reversed-out transform.              */ \
+        int in_rev = order == ORACLE_RN || order == ORACLE_BB;                                 \
+        int out_rev = order == ORACLE_NR || order == ORACLE_BB;                                \
+        int quirk = order == ORACLE_RR;                                                        \
         if (in_rev)                                                                            \
             for (size_t i = 0; i < n; i++) {                                                   \
                 size_t r = bitrev(i, lg);                                                      \
@@ -182,8 +187,10 @@ static inline size_t bitrev(size_t i, unsigned lg)
             }                                                                                  \
         if (!direction && type) {                                                              \
             T g = GEN, pw = 1;                                                                 \
-            for (size_t i = 0; i < n; i++, pw = MUL(pw, g))                                    \
-                a[i] = MUL(a[i], pw);                                                          \
+            for (size_t i = 0; i < n; i++, pw = MUL(pw, g)) {                                  \
+                size_t k = quirk ? bitrev(i, lg) : i;                                          \
+                a[k] = MUL(a[k], pw);                                                          \
+            }                                                                                  \
         }                                                                                      \
         T w = ROOT(lg, direction);                                                             \
         if (algo == 1)                                                                         \
@@ -196,8 +203,10 @@ static inline size_t bitrev(size_t i, unsigned lg)
                 a[i] = MUL(a[i], ninv);                                                        \
             if (type) {                                                                        \
                 T gi = POW(GEN, PM2), pw = 1;                                                  \
-                for (size_t i = 0; i < n; i++, pw = MUL(pw, gi))                               \
-                    a[i] = MUL(a[i], pw);                                                      \
+                for (size_t i = 0; i < n; i++, pw = MUL(pw, gi)) {                             \
+                    size_t k = quirk ? bitrev(i, lg) : i;                                      \
+                    a[k] = MUL(a[k], pw);                                                      \
+                }                                                                              \
             }                                                                                  \
         }                                                                                      \
         if (out_rev)                                                                           \

@@ -11,8 +11,12 @@
  *   coset:   forward multiplies x[j] by group_gen^j first; inverse multiplies
  *            the result by group_gen^-j last     (ntt/ntt.cuh:196-209,
  *            ntt/kernels.cu:131-153)
- *   orders:  NN/NR/RN/RR = natural / bit-reversed input, output
- *            (ntt/ntt.cuh:33,174-194,211-212)
+ *   orders:  NN natural->natural, NR natural->bit-reversed, RN bit-reversed->natural;
+ *            RR is, in the reference, GS on natural input followed by bit_rev, i.e. the SAME
+ *            transform as NN (ntt/ntt.cuh:186-189,211-212; poc/ntt-cuda/tests/ntt.rs:28-30
+ *            asserts NN == RR), with bit-reversed coset exponents.  ORACLE_BB (4) is the strict
+ *            bit-reversed-in / bit-reversed-out transform (an extension, not a reference order).
+ *            Pinned by tests/golden/ntt_ref_gpu.npz (the reference's own kernels on a B200).
  * Root conventions (derived, and checked against the ntt/parameters headers by
  * tests/test_params_pin.py):
  *   Goldilocks  w_2^32 = 7^((p-1)/2^32), group_gen = 7   (goldilocks.h:84-160, default branch)
@@ -29,7 +33,7 @@
 extern "C" {
 #endif
 
-enum { ORACLE_NN = 0, ORACLE_NR = 1, ORACLE_RN = 2, ORACLE_RR = 3 };
+enum { ORACLE_NN = 0, ORACLE_NR = 1, ORACLE_RN = 2, ORACLE_RR = 3, ORACLE_BB = 4 };
 
 /* in place; direction 0 forward / 1 inverse; type 0 standard / 1 coset;
  * algo 0 fast radix-2 (nthreads>1 uses pthreads), 1 O(n^2) definition */

@@ -18,7 +18,7 @@ CURVES = {"bls12_381": 0, "pallas": 1, "vesta": 2}
 FIELDS = {"bls12_381_fp": 0, "bls12_381_fr": 1, "pallas_fp": 2, "vesta_fp": 3}
 FIELD_LIMBS = {0: 6, 1: 4, 2: 4, 3: 4}
 CURVE_LIMBS = {0: 6, 1: 4, 2: 4}
-NN, NR, RN, RR = 0, 1, 2, 3
+NN, NR, RN, RR, BB = 0, 1, 2, 3, 4
 
 _lib = None
 

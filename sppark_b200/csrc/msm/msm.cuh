@@ -15,11 +15,14 @@ static __global__ void count_kernel(const Config cfg, const uint32_t* scalars, u
         count_body(cfg, scalars, counts, i);
 }
 
-// one CTA per window: exclusive prefix of the bucket histogram; heavy buckets are appended to
-// heavy_list (heavy_list[0] = count)
+constexpr uint32_t HEAVY_CHUNK = 4096;      // entries of a heavy bucket folded by one CTA
+
+// control block: [0] task counter, [1] #heavy buckets, [2] #chunks
+// heavy bucket h: heavy_list[3h] = slot, [3h+1] = first chunk, [3h+2] = #chunks; chunk_map[c] = h
+// one CTA per window: exclusive prefix of the bucket histogram; heavy buckets get chunked
 static __global__ void __launch_bounds__(1024)
 scan_kernel(const Config cfg, const uint32_t* counts, uint32_t* offsets, uint32_t* cursor,
-            uint32_t* heavy_list, uint32_t heavy_cap)
+            uint32_t* ctrl, uint32_t* heavy_list, uint32_t* chunk_map)
 {
     __shared__ uint32_t partial[1024];
     const uint32_t w = blockIdx.x, nb = 1u << cfg.lg_nb;
@@ -43,8 +46,12 @@ scan_kernel(const Config cfg, const uint32_t* counts, uint32_t* offsets, uint32_
         offsets[base + b] = run;
         cursor[base + b] = run;
         if (c > cfg.heavy) {
-            uint32_t slot = atomicAdd(&heavy_list[0], 1);
-            if (slot < heavy_cap) heavy_list[1 + slot] = (uint32_t)(base + b);
+            uint32_t h = atomicAdd(&ctrl[1], 1), nch = (c + HEAVY_CHUNK - 1) / HEAVY_CHUNK;
+            uint32_t first_chunk = atomicAdd(&ctrl[2], nch);
+            heavy_list[3 * h] = (uint32_t)(base + b);
+            heavy_list[3 * h + 1] = first_chunk;
+            heavy_list[3 * h + 2] = nch;
+            for (uint32_t k = 0; k < nch; k++) chunk_map[first_chunk + k] = h;
         }
         run += c;
     }
@@ -65,31 +72,60 @@ accumulate_kernel(const Config cfg, const uint32_t* points, const uint32_t* sort
     accumulate_body<F>(cfg, points, sorted, offsets, counts, buckets, task_counter);
 }
 
-// one CTA per heavy bucket: strided partial sums, then a shared-memory tree of full adds
+// block-wide sum of one xyzz per thread through shared memory; result valid in thread 0
+template<class F>
+DEV void block_sum(ec::xyzz_t<F>& acc, uint32_t* tree)
+{
+    store_bucket<F>(tree, threadIdx.x, acc);
+    __syncthreads();
+    for (uint32_t d = blockDim.x / 2; d > 0; d >>= 1) {
+        if (threadIdx.x < d) {
+            acc.add(load_bucket<F>(tree, threadIdx.x + d));
+            store_bucket<F>(tree, threadIdx.x, acc);
+        }
+        __syncthreads();
+    }
+}
+
+// heavy buckets, phase A: one CTA per HEAVY_CHUNK entries -> one partial sum per chunk, so a
+// bucket holding most of the points is spread over the whole GPU
 template<class F>
 __global__ void __launch_bounds__(HEAVY_THREADS)
-heavy_kernel(const Config cfg, const uint32_t* points, const uint32_t* sorted,
-             const uint32_t* offsets, const uint32_t* counts, uint32_t* buckets,
-             const uint32_t* heavy_list, uint32_t heavy_cap)
+heavy_chunks_kernel(const Config cfg, const uint32_t* points, const uint32_t* sorted,
+                    const uint32_t* offsets, const uint32_t* counts, const uint32_t* ctrl,
+                    const uint32_t* heavy_list, const uint32_t* chunk_map, uint32_t* partials)
 {
     extern __shared__ __align__(16) uint32_t tree[];         // HEAVY_THREADS xyzz slots
-    uint32_t nheavy = min(heavy_list[0], heavy_cap);
-    for (uint32_t hidx = blockIdx.x; hidx < nheavy; hidx += gridDim.x) {
-        const uint32_t t = heavy_list[1 + hidx], cnt = counts[t];
+    const uint32_t nchunks = ctrl[2];
+    for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const uint32_t h = chunk_map[ch], t = heavy_list[3 * h], k0 = (ch - heavy_list[3 * h + 1]) * HEAVY_CHUNK;
+        const uint32_t cnt = counts[t], k1 = min(k0 + HEAVY_CHUNK, cnt);
         const uint32_t* run = sorted + (size_t)(t >> cfg.lg_nb) * cfg.npoints + offsets[t];
         ec::xyzz_t<F> acc;
         acc.set_inf();
-        for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x)
+        for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x)
             acc.madd(load_point<F>(points, run[k]));
-        store_bucket<F>(tree, threadIdx.x, acc);
+        block_sum<F>(acc, tree);
+        if (threadIdx.x == 0) store_bucket<F>(partials, ch, acc);
         __syncthreads();
-        for (uint32_t d = blockDim.x / 2; d > 0; d >>= 1) {
-            if (threadIdx.x < d) {
-                acc.add(load_bucket<F>(tree, threadIdx.x + d));
-                store_bucket<F>(tree, threadIdx.x, acc);
-            }
-            __syncthreads();
-        }
+    }
+}
+
+// phase B: one CTA per heavy bucket folds that bucket's chunk partials
+template<class F>
+__global__ void __launch_bounds__(HEAVY_THREADS)
+heavy_fold_kernel(const uint32_t* ctrl, const uint32_t* heavy_list, const uint32_t* partials,
+                  uint32_t* buckets)
+{
+    extern __shared__ __align__(16) uint32_t tree[];
+    const uint32_t nheavy = ctrl[1];
+    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+        const uint32_t t = heavy_list[3 * h], first = heavy_list[3 * h + 1], nch = heavy_list[3 * h + 2];
+        ec::xyzz_t<F> acc;
+        acc.set_inf();
+        for (uint32_t k = threadIdx.x; k < nch; k += blockDim.x)
+            acc.add(load_bucket<F>(partials, first + k));
+        block_sum<F>(acc, tree);
         if (threadIdx.x == 0) store_bucket<F>(buckets, t, acc);
         __syncthreads();
     }
@@ -152,7 +188,9 @@ public:
             throw cuda_error(-(int)cudaErrorInvalidValue, "msm: npoints must be < 2^31");
         const Config cfg = make_config(npoints);
         const size_t nslots = (size_t)cfg.nwins << cfg.lg_nb;
-        const uint32_t heavy_cap = (uint32_t)((uint64_t)cfg.nwins * npoints / (cfg.heavy ? cfg.heavy : 1) + 1);
+        const size_t entries = (size_t)cfg.nwins * npoints;
+        const size_t heavy_cap = entries / (cfg.heavy + 1) + 1;                 // most heavy buckets possible
+        const size_t chunk_cap = entries / HEAVY_CHUNK + heavy_cap;            // most chunks possible
         const uint32_t sms = (uint32_t)gpu.sm_count();
 
         // level-1 chunking of the running sums: at most 4096 items per window
@@ -163,7 +201,8 @@ public:
         size_t off = 0;
         auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
         const size_t o_counts = take(nslots * 4), o_offsets = take(nslots * 4), o_cursor = take(nslots * 4);
-        const size_t o_misc = take((2 + heavy_cap) * 4);
+        const size_t o_ctrl = take(16), o_heavy = take(heavy_cap * 12), o_cmap = take(chunk_cap * 4);
+        const size_t o_partials = take(chunk_cap * BW * 4);
         const size_t o_sorted = take((size_t)cfg.nwins * npoints * 4);
         const size_t o_buckets = take(nslots * BW * 4);
         const size_t o_r0 = take((size_t)items1 * BW * 4), o_s0 = take((size_t)items1 * BW * 4);
@@ -172,16 +211,17 @@ public:
         CUDA_OK(cudaMallocAsync((void**)&blob, off, stream));
         auto U32 = [&](size_t o) { return reinterpret_cast<uint32_t*>(blob + o); };
         uint32_t *counts = U32(o_counts), *offsets = U32(o_offsets), *cursor = U32(o_cursor);
-        uint32_t *task_counter = U32(o_misc), *heavy_list = U32(o_misc) + 1;
+        uint32_t *ctrl = U32(o_ctrl), *task_counter = ctrl, *heavy_list = U32(o_heavy);
+        uint32_t *chunk_map = U32(o_cmap), *partials = U32(o_partials);
         uint32_t *sorted = U32(o_sorted), *buckets = U32(o_buckets);
 
         CUDA_OK(cudaMemsetAsync(counts, 0, nslots * 4, stream));
-        CUDA_OK(cudaMemsetAsync(task_counter, 0, 8, stream));
+        CUDA_OK(cudaMemsetAsync(ctrl, 0, 16, stream));
 
         const uint32_t nblk = (uint32_t)std::min<size_t>((npoints + 255) / 256, (size_t)sms * 16);
         count_kernel<<<nblk, 256, 0, stream>>>(cfg, d_scalars, counts);
         COUNT_LAUNCH();
-        scan_kernel<<<cfg.nwins, 1024, 0, stream>>>(cfg, counts, offsets, cursor, heavy_list, heavy_cap);
+        scan_kernel<<<cfg.nwins, 1024, 0, stream>>>(cfg, counts, offsets, cursor, ctrl, heavy_list, chunk_map);
         COUNT_LAUNCH();
         scatter_kernel<<<nblk, 256, 0, stream>>>(cfg, d_scalars, cursor, sorted);
         COUNT_LAUNCH();
@@ -195,8 +235,10 @@ public:
         accumulate_kernel<F><<<acc_blocks, ACC_THREADS, 0, stream>>>(cfg, d_points, sorted, offsets, counts,
                                                                     buckets, task_counter);
         COUNT_LAUNCH();
-        heavy_kernel<F><<<sms, HEAVY_THREADS, HEAVY_THREADS * BW * 4, stream>>>(
-            cfg, d_points, sorted, offsets, counts, buckets, heavy_list, heavy_cap);
+        heavy_chunks_kernel<F><<<sms * 4, HEAVY_THREADS, HEAVY_THREADS * BW * 4, stream>>>(
+            cfg, d_points, sorted, offsets, counts, ctrl, heavy_list, chunk_map, partials);
+        COUNT_LAUNCH();
+        heavy_fold_kernel<F><<<sms, HEAVY_THREADS, HEAVY_THREADS * BW * 4, stream>>>(ctrl, heavy_list, partials, buckets);
         COUNT_LAUNCH();
         CUDA_OK(cudaGetLastError());
 
@@ -219,6 +261,13 @@ public:
         finish_kernel<F><<<1, 32, 0, stream>>>(cfg, R[cur], d_out);
         COUNT_LAUNCH();
         CUDA_OK(cudaGetLastError());
+        if (getenv("SPPARK_B200_MSM_DEBUG")) {
+            uint32_t dbg[3];
+            CUDA_OK(cudaMemcpyAsync(dbg, ctrl, 12, cudaMemcpyDeviceToHost, stream));
+            CUDA_OK(cudaStreamSynchronize(stream));
+            fprintf(stderr, "[msm] n=%u wbits=%u nwins=%u heavy_thr=%u tasks_claimed=%u nheavy=%u nchunks=%u acc_blocks=%u items1=%u\n",
+                    cfg.npoints, cfg.wbits, cfg.nwins, cfg.heavy, dbg[0], dbg[1], dbg[2], acc_blocks, items1);
+        }
         CUDA_OK(cudaFreeAsync(blob, stream));
     }
 };

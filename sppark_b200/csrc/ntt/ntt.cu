@@ -15,7 +15,7 @@ template<class F>
 static RustError ntt_host(size_t device_id, void* inout, uint32_t lg, int order, int direction, int type)
 {
     typedef ntt::NTT<F> N;
-    if (order < 0 || order > 3 || direction < 0 || direction > 1 || type < 0 || type > 1)
+    if (order < 0 || order > 4 || direction < 0 || direction > 1 || type < 0 || type > 1)
         return rust_err(-(int)cudaErrorInvalidValue, "compute_ntt: bad order/direction/type");
     try {
         const gpu_t& gpu = select_gpu((int)device_id);
@@ -32,7 +32,7 @@ template<class F>
 static RustError ntt_dev(void* d_inout, uint32_t lg, int order, int direction, int type, void* stream)
 {
     typedef ntt::NTT<F> N;
-    if (order < 0 || order > 3 || direction < 0 || direction > 1 || type < 0 || type > 1)
+    if (order < 0 || order > 4 || direction < 0 || direction > 1 || type < 0 || type > 1)
         return rust_err(-(int)cudaErrorInvalidValue, "ntt_dev: bad order/direction/type");
     try {
         const gpu_t& gpu = gpu_of_current_device();

@@ -86,7 +86,7 @@ template<class F>
 class NTT {
     typedef typename F::T T;
 public:
-    enum class InputOutputOrder { NN, NR, RN, RR };
+    enum class InputOutputOrder { NN, NR, RN, RR, BB };
     enum class Direction { forward, inverse };
     enum class Type { standard, coset };
 
@@ -160,8 +160,10 @@ public:
         if (lg_n > (uint32_t)F::MAX_LG || lg_n > 30)
             throw cuda_error(-(int)cudaErrorInvalidValue, "NTT: lg_domain_size out of range");
         const bool inverse = direction == Direction::inverse;
-        const bool in_rev = order == InputOutputOrder::RN || order == InputOutputOrder::RR;
-        const bool out_rev = order == InputOutputOrder::NR || order == InputOutputOrder::RR;
+        // coset exponents follow the reference's `bitrev` flags exactly (ntt/ntt.cuh:174-209):
+        // for RR they are bit-reversed although the data is in natural order.
+        const bool in_rev = order != InputOutputOrder::NN && order != InputOutputOrder::NR;
+        const bool out_rev = order != InputOutputOrder::NN && order != InputOutputOrder::RN;
 
         if (!inverse && type == Type::coset)
             coset_scale(gpu, d_inout, lg_n, in_rev, false, stream);

@@ -15,7 +15,11 @@
 
 namespace ntt {
 
-enum Order : int { NN = 0, NR = 1, RN = 2, RR = 3 };
+// NN/NR/RN/RR are the reference's InputOutputOrder values.  In the reference RR is "GS on
+// natural input, then bit_rev" (ntt/ntt.cuh:186-189,211-212): the same transform as NN, and its
+// own tests assert NN == RR (poc/ntt-cuda/tests/ntt.rs:28-30).  BB is this library's extension:
+// bit-reversed input AND output, in two passes without any permutation kernel.
+enum Order : int { NN = 0, NR = 1, RN = 2, RR = 3, BB = 4 };
 
 struct Plan {
     uint32_t lg_n;
@@ -58,7 +62,8 @@ inline Plan make_plan(uint32_t lg_n, int order, bool inverse, uint32_t lg_tile,
     for (uint32_t p = 0, acc = 0; p < P; p++) { A[p] = acc; acc += s[p]; }
     for (uint32_t p = 0; p < P; p++) B[p] = lg_n - A[p] - s[p];
 
-    const bool pingpong = (order == NN || order == RR) && P > 1;
+    if (order == RR) order = NN;
+    const bool pingpong = (order == NN || order == BB) && P > 1;
     plan.needs_scratch = pingpong;
     uint32_t where = 0;                                   // buffer currently holding the data
 
@@ -114,7 +119,7 @@ inline Plan make_plan(uint32_t lg_n, int order, bool inverse, uint32_t lg_tile,
                 d.tw_mode = TW_STORE; d.tw_rsh = a; d.tw_bits = b; d.tw_brev = 0; d.tw_lsh = a;
             }
         } else {
-            // RR gather: position = Q << R | row ; scatter: Kdone_r << (R+b) | rk << b | Jrest_r
+            // BB gather: position = Q << R | row ; scatter: Kdone_r << (R+b) | rk << b | Jrest_r
             d.in_lg_tlo = 32; d.in_tl = W << R; d.in_th = 0;
             d.in_lg_sa = 0; d.in_lg_sc = R;
             if (b == 0) {

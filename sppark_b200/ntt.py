@@ -7,6 +7,7 @@ import numpy as np
 from . import _lib
 
 NN, NR, RN, RR = 0, 1, 2, 3            # sppark::NTTInputOutputOrder (rust/src/lib.rs:99-105)
+BB = 4                                 # extension: bit-reversed in and out (RR == NN in the reference)
 FORWARD, INVERSE = 0, 1                # sppark::NTTDirection
 STANDARD, COSET = 0, 1                 # sppark::NTTType
 GL64, BB31 = 0, 1

@@ -1,0 +1,108 @@
+"""Generates the committed golden vectors from THE REFERENCE ITSELF (not from the oracle):
+
+  ntt_ref_gpu.npz   inputs/outputs of the reference's own CUDA NTT (poc/ntt-cuda/cuda/ntt_api.cu
+                    compiled for sm_100a into oracle/_ref by oracle/Makefile), Goldilocks and
+                    BabyBear, lg 1..10, every order x direction x type.  Needs a GPU: run as
+                    `gpurun -- python tests/golden/make_golden.py gpu` and copy gpurun_out/golden/*.
+  msm_ref_gpu.npz   same for the reference's CUDA mult_pippenger (BLS12-381 G1).
+  msm_ref_cpu.npz   the reference's CPU msm/pippenger.hpp (oracle/_ref/libref_msm_cpu.so);
+                    runs anywhere: `python tests/golden/make_golden.py cpu`.
+
+tests/test_oracle.py checks the CPU oracle against all three, which is what pins it.
+Inputs are seeded; nothing here reads /root/reference at run time (only the prebuilt _ref .so).
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as o  # noqa: E402
+
+GL_P = 2**64 - 2**32 + 1
+BB_P = 0x78000001
+R_BLS = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+
+
+class RE(C.Structure):
+    _fields_ = [("code", C.c_int), ("message", C.c_void_p)]
+
+
+def msm_inputs():
+    """A few small deterministic MSM instances (points = multiples of G, incl. infinity)."""
+    rng = np.random.default_rng(2024)
+    base = o.gen_points("bls12_381", 64)
+    cases = {}
+    for n in (1, 2, 33, 200, 1000):
+        pts = base[np.arange(n) % 64].copy()
+        if n > 3:
+            pts[3] = 0
+        sc = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
+        sc[:, 3] >>= np.uint64(2)
+        if n >= 33:
+            sc[5] = 0
+            sc[6] = [1, 0, 0, 0]
+            sc[7] = o.int_to_limbs(R_BLS - 1, 4)
+        cases[n] = (pts, sc)
+    return cases
+
+
+def gen_cpu(outdir):
+    cases = msm_inputs()
+    out = {}
+    for n, (pts, sc) in cases.items():
+        jac = o.ref_cpu_msm(pts, sc, nthreads=4)
+        out[f"pts_{n}"] = pts
+        out[f"sc_{n}"] = sc
+        out[f"affine_{n}"] = o.jac_to_affine("bls12_381", jac)
+    np.savez_compressed(os.path.join(outdir, "msm_ref_cpu.npz"), **out)
+    print("wrote msm_ref_cpu.npz")
+
+
+def gen_gpu(outdir):
+    out = {}
+    for field, dtype, p, so in (("gl64", np.uint64, GL_P, "libref_ntt_gl64_gpu.so"),
+                                ("bb31", np.uint32, BB_P, "libref_ntt_bb31_gpu.so")):
+        lib = C.CDLL(o.ref_path(so))
+        lib.compute_ntt.restype = RE
+        lib.compute_ntt.argtypes = [C.c_size_t, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int]
+        rng = np.random.default_rng(7)
+        for lg in range(1, 11):
+            x = rng.integers(0, p, size=1 << lg, dtype=dtype)
+            out[f"{field}_in_{lg}"] = x
+            for order in range(4):
+                for direction in range(2):
+                    for typ in range(2):
+                        y = x.copy()
+                        e = lib.compute_ntt(0, y.ctypes.data, lg, order, direction, typ)
+                        assert e.code == 0
+                        out[f"{field}_out_{lg}_{order}{direction}{typ}"] = y
+    np.savez_compressed(os.path.join(outdir, "ntt_ref_gpu.npz"), **out)
+    print("wrote ntt_ref_gpu.npz")
+
+    lib = C.CDLL(o.ref_path("libref_msm_gpu.so"))
+    lib.mult_pippenger.restype = RE
+    lib.mult_pippenger.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    out = {}
+    for n, (pts, sc) in msm_inputs().items():
+        jac = np.zeros(18, dtype=np.uint64)
+        e = lib.mult_pippenger(jac.ctypes.data, pts.ctypes.data, n, sc.ctypes.data)
+        assert e.code == 0
+        out[f"pts_{n}"] = pts
+        out[f"sc_{n}"] = sc
+        out[f"affine_{n}"] = o.jac_to_affine("bls12_381", jac)
+    np.savez_compressed(os.path.join(outdir, "msm_ref_gpu.npz"), **out)
+    print("wrote msm_ref_gpu.npz")
+
+
+if __name__ == "__main__":
+    mode = sys.argv[1] if len(sys.argv) > 1 else "cpu"
+    if mode == "cpu":
+        gen_cpu(HERE)
+    else:
+        outdir = os.path.join(ROOT, "gpurun_out", "golden")
+        os.makedirs(outdir, exist_ok=True)
+        gen_gpu(outdir)

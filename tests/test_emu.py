@@ -1,0 +1,109 @@
+"""CPU single-steppers (tests/emu): the exact HD kernel bodies of the CUDA path, executed
+phase by phase on the host and compared with the oracle.  Validates the NTT planner / butterfly
+schedule and the whole MSM pipeline logic without a GPU.  (The emulators are test
+infrastructure; they are not part of libsppark_b200.so.)"""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+EMU = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+R_BLS = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+
+
+def _build(name):
+    so, src = os.path.join(EMU, f"lib{name}.so"), os.path.join(EMU, f"{name}.cpp")
+    csrc = os.path.join(os.path.dirname(EMU), "..", "sppark_b200", "csrc")
+    newest = max(os.path.getmtime(os.path.join(r, f)) for r, _, fs in os.walk(csrc) for f in fs)
+    if not os.path.exists(so) or os.path.getmtime(so) < max(newest, os.path.getmtime(src)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", so, src])
+    return C.CDLL(so)
+
+
+@pytest.fixture(scope="module")
+def ntt_emu():
+    l = _build("ntt_emu")
+    l.emu_ntt_gl64.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_uint]
+    l.emu_ntt_bb31.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_uint]
+    return l
+
+
+@pytest.fixture(scope="module")
+def msm_emu():
+    l = _build("msm_emu")
+    l.emu_msm_bls12_381.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint, C.c_uint]
+    l.emu_msm_pallas.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint, C.c_uint]
+    l.emu_fp_op.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    return l
+
+
+CASES = [(lg, None) for lg in list(range(1, 15)) + [16]] + [
+    (6, "2,2,2"), (6, "1,5"), (6, "5,1"), (9, "3,3,3"), (9, "4,2,3"), (9, "1,1,7"), (9, "7,1,1"),
+    (9, "2,2,2,3"), (13, "5,4,4"), (13, "6,7"), (10, "4,3,3"), (10, "3,7")]
+
+
+@pytest.mark.parametrize("lg,split", CASES)
+def test_ntt_plan_and_schedule(oracle, ntt_emu, lg, split, monkeypatch):
+    if split:
+        monkeypatch.setenv("SPPARK_B200_NTT_SPLIT", split)
+    else:
+        monkeypatch.delenv("SPPARK_B200_NTT_SPLIT", raising=False)
+    rng = np.random.default_rng(lg)
+    x = rng.integers(0, 2**64 - 2**32 + 1, size=1 << lg, dtype=np.uint64)
+    xb = rng.integers(0, 0x78000001, size=1 << lg, dtype=np.uint32)
+    for order in range(5):
+        for inv in (0, 1):
+            for lg_tile in (14, 7):
+                y = x.copy()
+                ntt_emu.emu_ntt_gl64(y.ctypes.data, lg, order, inv, lg_tile)
+                assert np.array_equal(y, oracle.ntt_gl64(x, order, bool(inv))), (order, inv, lg_tile)
+            yb = xb.copy()
+            ntt_emu.emu_ntt_bb31(yb.ctypes.data, lg, order, inv, 14)
+            assert np.array_equal(yb, oracle.ntt_bb31(xb, order, bool(inv))), (order, inv)
+
+
+def _scalars(vals):
+    return np.array([[(v >> (64 * i)) & (2**64 - 1) for i in range(4)] for v in vals], dtype=np.uint64).reshape(len(vals), 4)
+
+
+def _run(oracle, emu, pts, sc, wbits, heavy):
+    out = np.zeros(18, dtype=np.uint64)
+    emu.emu_msm_bls12_381(out.ctypes.data, pts.ctypes.data, pts.shape[0], sc.ctypes.data, wbits, heavy)
+    want = oracle.msm("bls12_381", pts, sc, "pippenger", ncpus=4)
+    return np.array_equal(oracle.jac_to_affine("bls12_381", out), oracle.jac_to_affine("bls12_381", want))
+
+
+@pytest.mark.parametrize("n,wbits,heavy", [(1, 0, 0), (2, 0, 0), (33, 0, 0), (300, 0, 0), (300, 5, 0),
+                                           (300, 9, 3), (800, 7, 4), (500, 4, 2), (64, 13, 0)])
+def test_msm_pipeline_logic(oracle, msm_emu, n, wbits, heavy):
+    rnd = random.Random(n * 31 + wbits)
+    pts = oracle.gen_points("bls12_381", 64)[np.arange(n) % 64].copy()
+    if n > 3:
+        pts[3] = 0
+    assert _run(oracle, msm_emu, pts, _scalars([rnd.randrange(R_BLS) for _ in range(n)]), wbits, heavy)
+
+
+@pytest.mark.parametrize("val", [0, 1, R_BLS - 1, (1 << 254) + 12345, 0x8000000080000000800000008000])
+def test_msm_pipeline_adversarial_scalars(oracle, msm_emu, val):
+    n = 150
+    pts = oracle.gen_points("bls12_381", 4)[np.arange(n) % 4].copy()
+    p = oracle.ff_consts("bls12_381_fp")["p"]
+    y1 = sum(int(v) << (64 * i) for i, v in enumerate(pts[1][6:]))
+    pts[5][6:] = [((p - y1) >> (64 * i)) & (2**64 - 1) for i in range(6)]     # a (P, -P) pair in one bucket
+    assert _run(oracle, msm_emu, pts, _scalars([val] * n), 6, 8)
+    assert _run(oracle, msm_emu, pts, _scalars([val] * n), 5, 0)
+
+
+def test_portable_field_branch(oracle, msm_emu):
+    p = oracle.ff_consts("bls12_381_fp")["p"]
+    R = 1 << 384
+    rnd = random.Random(9)
+    for _ in range(300):
+        a, b = rnd.randrange(p), rnd.randrange(p)
+        A, B, r = oracle.int_to_limbs(a, 6), oracle.int_to_limbs(b, 6), np.zeros(6, dtype=np.uint64)
+        for op, exp in ((0, a * b * pow(R, -1, p) % p), (1, (a + b) % p), (2, (a - b) % p)):
+            msm_emu.emu_fp_op(op, r.ctypes.data, A.ctypes.data, B.ctypes.data)
+            assert oracle.limbs_to_int(r) == exp

@@ -1,0 +1,79 @@
+"""Derived parameters vs the tables the reference hard-codes.  Needs /root/reference (the
+authoring container); skipped elsewhere.  Nothing from the reference is copied: roots of unity,
+Montgomery constants and generators used by this repo are re-derived from first principles and
+merely compared here."""
+import os
+import re
+
+import pytest
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="/root/reference not present")
+
+
+def _small_table(path, name):
+    s = open(path).read()
+    tail = s.split("#endif")[-1]
+    if "#else" in s:
+        s = s.split("#else")[1].split("#endif")[0]
+    m = re.search(r"const fr_t %s\[S \+ 1\] = \{(.*?)\};" % name, s + tail, re.S)
+    return [int(x, 16) for x in re.findall(r"fr_t\((0x[0-9a-f]+)u?\)", m.group(1))]
+
+
+def test_goldilocks_roots(oracle):
+    p = 2**64 - 2**32 + 1
+    fwd = _small_table(f"{REF}/ntt/parameters/goldilocks.h", "forward_roots_of_unity")
+    inv = _small_table(f"{REF}/ntt/parameters/goldilocks.h", "inverse_roots_of_unity")
+    dsi = _small_table(f"{REF}/ntt/parameters/goldilocks.h", "domain_size_inverse")
+    for lg in range(33):
+        assert oracle.lib().oracle_gl64_root(lg, 0) == fwd[lg]
+        assert oracle.lib().oracle_gl64_root(lg, 1) == inv[lg]
+        assert pow(2, -lg, p) == dsi[lg]
+    assert fwd[32] == 0x185629dcda58878c == pow(7, (p - 1) >> 32, p)   # value hard-wired in ff/gl64.cuh
+
+
+def test_babybear_roots(oracle):
+    p, R = 0x78000001, 1 << 32
+    fwd = _small_table(f"{REF}/ntt/parameters/baby_bear.h", "forward_roots_of_unity")
+    inv = _small_table(f"{REF}/ntt/parameters/baby_bear.h", "inverse_roots_of_unity")
+    dsi = _small_table(f"{REF}/ntt/parameters/baby_bear.h", "domain_size_inverse")
+    for lg in range(28):
+        assert oracle.lib().oracle_bb31_root(lg, 0) * R % p == fwd[lg]     # tables are Montgomery words
+        assert oracle.lib().oracle_bb31_root(lg, 1) * R % p == inv[lg]
+        assert pow(2, -lg, p) * R % p == dsi[lg]
+    assert fwd[27] * pow(R, -1, p) % p == 137
+
+
+def test_msm_field_constants():
+    """sppark_b200/csrc/ff/fields.cuh (generated) vs ff/bls12-381.hpp:14-52, ff/pasta.hpp:14-50."""
+    gen = open(os.path.join(os.path.dirname(__file__), "..", "sppark_b200", "csrc", "ff", "fields.cuh")).read()
+
+    def ours(struct, name):
+        blk = gen.split(f"struct {struct}_params")[1].split("typedef")[0]
+        m = re.search(r"%s\(int i\) \{ constexpr uint32_t t\[\d+\] = \{(.*?)\}" % name, blk)
+        return [int(x.rstrip("u"), 16) for x in m.group(1).split(", ")]
+
+    def theirs(path, name):
+        s = open(path).read().split("namespace device")[1]
+        m = re.search(r"%s\[\d+\] = \{(.*?)\};" % name, s, re.S)
+        words = []
+        for v in re.findall(r"TO_CUDA_T\((0x[0-9a-f]+)\)", m.group(1)):
+            v = int(v, 16)
+            words += [v & 0xFFFFFFFF, v >> 32]
+        if not words:                                   # pasta.hpp lists plain 32-bit words
+            words = [int(v, 16) for v in re.findall(r"0x[0-9a-f]{8}", m.group(1))]
+        return words
+
+    b = f"{REF}/ff/bls12-381.hpp"
+    assert ours("bls12_381_fp", "P") == theirs(b, "BLS12_381_P")
+    assert ours("bls12_381_fp", "RR") == theirs(b, "BLS12_381_RR")
+    assert ours("bls12_381_fp", "ONE") == theirs(b, "BLS12_381_one")
+    assert ours("bls12_381_fr", "P") == theirs(b, "BLS12_381_r")
+    assert ours("bls12_381_fr", "ONE") == theirs(b, "BLS12_381_rone")
+    q = f"{REF}/ff/pasta.hpp"
+    assert ours("pallas_fp", "P") == theirs(q, "Pallas_P")
+    assert ours("pallas_fp", "RR") == theirs(q, "Pallas_RR")
+    assert ours("pallas_fp", "ONE") == theirs(q, "Pallas_one")
+    assert ours("vesta_fp", "P") == theirs(q, "Vesta_P")
+    assert ours("vesta_fp", "ONE") == theirs(q, "Vesta_one")
+    assert "M0 = 0xfffcfffdu" in gen.split("struct bls12_381_fp_params")[1].split("typedef")[0]
