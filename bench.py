@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the MSM / NTT hot paths.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--lg-msm 26] [--lg-ntt 24]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one BLS12-381 G1 MSM over 2^26 synthetic points (BASELINE.json's headline metric),
+sharded by point-chunk over the N ranks with one all-gather of the per-rank partial results
+(strong scaling: the MSM size is fixed).  `value` is device-resident throughput, `e2e` goes
+through the drop-in C-ABI `mult_pippenger` with HOST (pinned) buffers.  The Goldilocks 2^24 NTT
+(the metric's second half) is measured in the same run and reported under "ntt".
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over
+ranks.  Inputs (8.6 GB MSM, 2 x 128 MiB NTT + L2 flush) exceed the 126 MB L2.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R_BLS = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+GL_P = 2**64 - 2**32 + 1
+LG_DISTINCT = 16            # distinct points, replicated (the reference's util.rs replicates 2^11)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 4 + k and r[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        busy = [v for v in sm if v > 0.5 * (mx[0] if mx else 1)] or sm
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def fold_scalars(sc, m):
+    """sum of scalars per residue class i mod m, reduced mod r -> (m, 4) uint64."""
+    n = sc.shape[0]
+    v = sc.reshape(n // m, m, 4)
+    lo = (v & np.uint64(0xFFFFFFFF)).sum(axis=0, dtype=np.uint64)       # < 2^32 * n/m
+    hi = (v >> np.uint64(32)).sum(axis=0, dtype=np.uint64)
+    out = np.zeros((m, 4), dtype=np.uint64)
+    for j in range(m):
+        t = 0
+        for k in range(4):
+            t += (int(lo[j, k]) + (int(hi[j, k]) << 32)) << (64 * k)
+        t %= R_BLS
+        for k in range(4):
+            out[j, k] = (t >> (64 * k)) & 0xFFFFFFFFFFFFFFFF
+    return out
+
+
+def cpu_reference_msm(points, scalars, nthreads):
+    """sppark's CPU path on the host cores: the reference's own msm/pippenger.hpp when oracle/_ref
+    holds it (built in the authoring container from /root/reference), else the C restatement."""
+    from oracle import pyoracle
+    t0 = time.perf_counter()
+    if pyoracle.ref_cpu() is not None:
+        out = pyoracle.ref_cpu_msm(points, scalars, nthreads=nthreads)
+        kind = "reference"
+    else:
+        out = pyoracle.msm("bls12_381", points, scalars, "pippenger", ncpus=nthreads)
+        kind = "port"
+    return out, time.perf_counter() - t0, kind
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on this box's cores."""
+    if rank != 0:
+        return
+    from oracle import pyoracle          # the reference arm runs no kernel of this repository
+    lg_s = args.lg_cpu_sample
+    n = 1 << lg_s
+    cores = os.cpu_count() or 1
+    base = pyoracle.gen_points("bls12_381", 1 << min(12, lg_s))
+    pts = np.tile(base, (n // base.shape[0], 1))
+    rng = np.random.default_rng(1234)
+    sc = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
+    sc[:, 3] >>= np.uint64(2)
+    for _ in range(args.warmup):
+        cpu_reference_msm(pts[: n // 8], sc[: n // 8], cores)
+    t = 0.0
+    kind = "port"
+    for _ in range(args.steps):
+        _, dt, kind = cpu_reference_msm(pts, sc, cores)
+        t += dt
+    per_step = t / args.steps
+    value = (n / per_step) / (1 << args.lg_msm)        # MSM/s at 2^lg_msm points, by point throughput
+    sample = (f"2^{lg_s}-point MSM per step on {cores} host threads; value = points/s / 2^{args.lg_msm} "
+              "(Pippenger cost per point falls slowly with size, so this slightly under-estimates 2^26)")
+    line = {"impl": "reference", "metric": f"BLS12-381 G1 MSM/s @2^{args.lg_msm} points", "value": value,
+            "unit": "MSM/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64x6 Montgomery (portable, no blst asm)", "data": "synthetic",
+            "config": {"workload": f"bls12_381_g1_msm_2^{args.lg_msm}", "cpu_sample": f"2^{lg_s}"},
+            "cpu_baseline": {"value": value, "unit": "MSM/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "MSM/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lg-msm", type=int, default=26)
+    ap.add_argument("--lg-ntt", type=int, default=24)
+    ap.add_argument("--lg-cpu-sample", type=int, default=22)
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from sppark_b200 import _lib, msm, ntt
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------------------------------------------------------- synthetic MSM shard
+    n_total = 1 << args.lg_msm
+    n = n_total // world
+    m = 1 << min(LG_DISTINCT, args.lg_msm - (world.bit_length() - 1))
+    base_dev = msm.generate_points_dev(msm.BLS12_381_G1, m)
+    torch.cuda.synchronize()
+    base = base_dev.cpu().numpy().view(np.uint64)                     # (m, 12)
+    rng = np.random.default_rng(42 + rank)
+    need_host = not args.skip_e2e and world == 1
+    if need_host:
+        pts_host_t = torch.empty((n, 12), dtype=torch.int64, pin_memory=True)
+        sc_host_t = torch.empty((n, 4), dtype=torch.int64, pin_memory=True)
+        pts_host, sc_host = pts_host_t.numpy().view(np.uint64), sc_host_t.numpy().view(np.uint64)
+    else:
+        sc_host = np.empty((n, 4), dtype=np.uint64)
+    blk = 1 << 22
+    for s in range(0, n, blk):
+        e = min(n, s + blk)
+        sc_host[s:e] = rng.integers(0, 2**64, size=(e - s, 4), dtype=np.uint64)
+    sc_host[:, 3] >>= np.uint64(2)                                     # uniform below 2^254 < r
+    d_points = base_dev.repeat(n // m, 1).contiguous()
+    d_scalars = torch.from_numpy(sc_host.view(np.int64)).cuda()
+    if need_host:
+        pts_host.reshape(n // m, m, 12)[:] = base
+    torch.cuda.synchronize()
+
+    def msm_step():
+        part = msm.msm_dev(msm.BLS12_381_G1, d_points, d_scalars)      # synchronises its stream
+        if world == 1:
+            return part
+        t = torch.from_numpy(part.view(np.int64)).cuda()
+        gathered = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)                                   # 144 B per rank over NVLink
+        return msm.combine(msm.BLS12_381_G1, torch.stack(gathered).cpu().numpy().view(np.uint64))
+
+    launches0 = _lib.launch_count()
+    for _ in range(args.warmup):
+        result = msm_step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches1 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        result = msm_step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    gpu_launches = _lib.launch_count() - launches1
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    value = 1e3 / ms_step
+
+    # ---- roofline leg: the dominant kernel (bucket accumulation), timed live with CUDA events
+    _lib.profile_enable(True)
+    acc_ms = []
+    for _ in range(2):
+        msm.msm_dev(msm.BLS12_381_G1, d_points, d_scalars)
+        phases = dict(_lib.profile_read())
+        acc_ms.append(phases.get("accumulate", 0.0))
+    _lib.profile_enable(False)
+    phases = {k: round(v, 3) for k, v in phases.items()}
+    peak, peak_src = measured_peaks()
+    alg_bytes = n * 128                              # 96-B affine point + 32-B scalar, read once
+    acc = sum(acc_ms) / len(acc_ms)
+    achieved = alg_bytes / (acc * 1e-3) / 1e9 if acc > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "msm::accumulate_kernel", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": acc, "phases_ms": phases,
+                "note": "bucket accumulation is bounded by INT32 multiply issue (IMAD.WIDE at 32 lanes/clk/SM), "
+                        "not HBM; see DESIGN.md section 6 for the integer roofline"}
+
+    # ---- self-check at full size (size-independent property, no oracle): folding the scalars of
+    # the replicated points onto the m distinct points must give the same group element
+    check = None
+    if world == 1:
+        folded = fold_scalars(sc_host, m)
+        small = msm.msm_dev(msm.BLS12_381_G1, base_dev, torch.from_numpy(folded.view(np.int64)).cuda())
+        check = "folded-msm " + ("ok" if _jac_equal(result, small, msm) else "MISMATCH")
+
+    # ---------------------------------------------------------------- e2e through the C-ABI
+    e2e = None
+    if need_host:
+        del d_points, d_scalars
+        torch.cuda.empty_cache()
+        msm.multi_scalar_mult(pts_host, sc_host)                        # warm the pools
+        t0 = time.perf_counter()
+        for _ in range(max(1, args.steps)):
+            r2 = msm.multi_scalar_mult(pts_host, sc_host)
+        dt = (time.perf_counter() - t0) / max(1, args.steps)
+        e2e = {"value": 1.0 / dt, "unit": "MSM/s", "h2d_bytes_per_step": int(n * 128),
+               "d2h_bytes_per_step": 144, "ms_per_step": dt * 1e3, "api": "mult_pippenger (host pointers, pinned)",
+               "same_result": bool(_jac_equal(r2, result, msm))}
+    elif world > 1:
+        e2e = {"value": None, "unit": "MSM/s", "h2d_bytes_per_step": int(n * 128), "d2h_bytes_per_step": 144,
+               "note": "host-pointer e2e is measured at N=1"}
+
+    # ---------------------------------------------------------------- Goldilocks NTT (second half of the metric)
+    ntt_res = bench_ntt(args, torch, ntt, _lib, peak, peak_src, barrier, max_over_ranks, world)
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        lg_s = min(args.lg_cpu_sample, args.lg_msm)
+        ns = 1 << lg_s
+        cores = os.cpu_count() or 1
+        hp = pts_host[:ns] if need_host else np.tile(base, (ns // m, 1))
+        _, dt, kind = cpu_reference_msm(np.ascontiguousarray(hp), np.ascontiguousarray(sc_host[:ns]), cores)
+        cpu = {"value": (ns / dt) / n_total, "unit": "MSM/s", "cores": cores, "kind": kind,
+               "sample": f"one 2^{lg_s}-point MSM ({dt:.2f} s) on {cores} host threads, scaled by point "
+                         f"throughput to 2^{args.lg_msm}; sppark msm/pippenger.hpp on portable (non-blst) arithmetic"}
+
+    if rank == 0:
+        line = {"metric": f"BLS12-381 G1 MSM/s @2^{args.lg_msm} points", "value": value, "unit": "MSM/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u32x12 (384-bit Montgomery integers)", "data": "synthetic",
+                "config": {"workload": f"bls12_381_g1_msm_2^{args.lg_msm}",
+                           "points": f"(i+1)*G, 2^{min(LG_DISTINCT, args.lg_msm)} distinct, replicated",
+                           "scalars": "uniform < 2^254, seed 42+rank", "sharding": f"point-chunk x{world}, all-gather of partials",
+                           "l2": "inputs (8.6 GB at 2^26) exceed L2; no flush needed"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
+                "cpu_baseline": cpu, "check": check, "ntt": ntt_res}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _jac_equal(a, b, msm):
+    """Equality of two Jacobian points as group elements, by cross-multiplied coordinates
+    (X1*Z2^2 == X2*Z1^2, Y1*Z2^3 == Y2*Z1^3), using the library's own field multiply (no oracle
+    on this path)."""
+    a = np.asarray(a, dtype=np.uint64)
+    b = np.asarray(b, dtype=np.uint64)
+    za, zb = a[12:], b[12:]
+    if not za.any() or not zb.any():
+        return (not za.any()) and (not zb.any())
+    mul = lambda x, y: msm.selftest_field(0, "mul", x.reshape(1, 6), y.reshape(1, 6))[0]   # noqa: E731
+    za2, zb2 = mul(za, za), mul(zb, zb)
+    if not np.array_equal(mul(a[:6], zb2), mul(b[:6], za2)):
+        return False
+    return np.array_equal(mul(a[6:12], mul(zb2, zb)), mul(b[6:12], mul(za2, za)))
+
+
+def bench_ntt(args, torch, ntt, _lib, peak, peak_src, barrier, max_over_ranks, world):
+    """Goldilocks 2^lg NTT, NN order, device-resident (NTT::Base_dev_ptr path) and e2e
+    (compute_ntt with a pinned host buffer).  N ranks run N independent transforms (replicas);
+    the slab-sharded single transform is exercised by tests, see DESIGN.md."""
+    lg = args.lg_ntt
+    n = 1 << lg
+    rng = np.random.default_rng(7)
+    host_t = torch.empty(n, dtype=torch.int64, pin_memory=True)
+    host = host_t.numpy().view(np.uint64)
+    host[:] = rng.integers(0, GL_P, size=n, dtype=np.uint64)
+    d = host_t.cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    iters = max(10, args.steps * 5)
+    for _ in range(max(3, args.warmup)):
+        ntt.ntt_dev(d, ntt.NN)
+    barrier()
+    tot = 0.0
+    for _ in range(iters):
+        flush.zero_()                                                   # evict L2 between iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ntt.ntt_dev(d, ntt.NN)
+        e1.record()
+        e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    ms = max_over_ranks(tot / iters)
+    _lib.profile_enable(True)
+    flush.zero_()
+    ntt.ntt_dev(d, ntt.NN)
+    torch.cuda.synchronize()
+    passes = [v for _, v in _lib.profile_read()]
+    _lib.profile_enable(False)
+    alg = 2 * n * 8
+    worst = max(passes) if passes else ms
+    res = {"metric": f"Goldilocks NTT/s @2^{lg} (NN, forward)", "value": world * 1e3 / ms, "unit": "NTT/s",
+           "ms_per_ntt": ms, "scaling": "replicas", "iters": iters, "l2": "256 MiB write between iterations",
+           "roofline": {"bound": "hbm", "kernel": "ntt::pass_kernel<gl64> (slowest pass)",
+                        "achieved": alg / (worst * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / (worst * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                        "pass_ms": [round(p, 4) for p in passes],
+                        "whole_transform_frac": alg / (ms * 1e-3) / 1e9 / peak}}
+    # e2e: in place on the pinned host buffer through compute_ntt
+    ntt.NTT(0 if world == 1 else torch.cuda.current_device(), host, ntt.NN)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        ntt.NTT(0 if world == 1 else torch.cuda.current_device(), host, ntt.NN)
+    dt = (time.perf_counter() - t0) / reps
+    res["e2e"] = {"value": 1.0 / dt, "unit": "NTT/s", "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
+                  "api": "compute_ntt (host pointer, pinned)"}
+    return res
+
+
+if __name__ == "__main__":
+    main()

@@ -100,6 +100,13 @@ RustError sppark_b200_msm(int curve, void *out_jacobian, const void *points_affi
 RustError sppark_b200_msm_dev(int curve, void *out_jacobian, const void *d_points,
                               size_t npoints, const void *d_scalars, void *stream);
 
+/* synthetic inputs: d_out[i] = (i+1)*G as packed affine points in DEVICE memory (the role of
+ * util::generate_points_scalars, poc/msm-cuda/src/util.rs:11-38); enqueued on `stream`. */
+RustError sppark_b200_generate_points_dev(int curve, void *d_out, size_t n, void *stream);
+/* sum of `count` Jacobian points (host arrays): combines per-GPU partial MSM results after the
+ * all-gather of a sharded MSM (NCCL cannot add curve points). */
+RustError sppark_b200_msm_combine(int curve, void *out_jacobian, const void *partials, size_t count);
+
 /* device self-test hook for the known-answer tests: r[i] = a[i] (op) b[i] through the PTX field
  * arithmetic; field 0 = BLS12-381 fp (48 B), 1 = BLS12-381 fr, 2 = Pallas fp, 3 = Vesta fp
  * (32 B each); op 0 mul (Montgomery), 1 add, 2 sub, 3 sqr.  Host arrays. */
@@ -110,6 +117,10 @@ int         sppark_b200_sm_count(int device_id);
 const char *sppark_b200_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t    sppark_b200_launch_count(void);
+/* phase timing of the LAST MSM / NTT call with CUDA events on the call's own stream (the
+ * roofline leg of bench.py): enable, run, synchronise, read (name, ms) pairs. */
+void        sppark_b200_profile_enable(int on);
+int         sppark_b200_profile_read(const char **names, float *ms, int cap);
 
 #ifdef __cplusplus
 }

@@ -28,12 +28,15 @@ _SIGS = {
     "sppark_b200_ntt_dev": [C.c_int, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "sppark_b200_msm": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t],
     "sppark_b200_msm_dev": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p],
+    "sppark_b200_generate_points_dev": [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p],
+    "sppark_b200_msm_combine": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t],
     "sppark_b200_selftest_field": [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p],
 }
 
 # every symbol include/sppark_b200.h declares (tests check the .so exports all of them)
 EXPORTS = list(_SIGS) + ["cuda_available", "drop_error_message", "sppark_b200_sm_count",
-                         "sppark_b200_version", "sppark_b200_launch_count"]
+                         "sppark_b200_version", "sppark_b200_launch_count",
+                         "sppark_b200_profile_enable", "sppark_b200_profile_read"]
 
 
 def lib():
@@ -52,6 +55,9 @@ def lib():
         l.sppark_b200_sm_count.argtypes = [C.c_int]
         l.sppark_b200_version.restype = C.c_char_p
         l.sppark_b200_launch_count.restype = C.c_uint64
+        l.sppark_b200_profile_enable.argtypes = [C.c_int]
+        l.sppark_b200_profile_read.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+        l.sppark_b200_profile_read.restype = C.c_int
         _lib = l
     return _lib
 
@@ -68,3 +74,15 @@ def check(err):
 
 def launch_count():
     return int(lib().sppark_b200_launch_count())
+
+
+def profile_enable(on=True):
+    lib().sppark_b200_profile_enable(int(on))
+
+
+def profile_read():
+    """[(phase, ms)] of the last profiled call (synchronise first)."""
+    names = (C.c_char_p * 16)()
+    ms = (C.c_float * 16)()
+    n = lib().sppark_b200_profile_read(names, ms, 16)
+    return [(names[i].decode(), float(ms[i])) for i in range(n)]

@@ -8,6 +8,34 @@ RustError msm_dev_pallas(void*, const void*, size_t, const void*, void*);
 RustError msm_host_vesta(void*, const void*, size_t, const void*, size_t, bool);
 RustError msm_dev_vesta(void*, const void*, size_t, const void*, void*);
 
+RustError gen_points_bls12_381(void*, size_t, void*);
+RustError gen_points_pallas(void*, size_t, void*);
+RustError gen_points_vesta(void*, size_t, void*);
+RustError combine_bls12_381(void*, const void*, size_t);
+RustError combine_pallas(void*, const void*, size_t);
+RustError combine_vesta(void*, const void*, size_t);
+
+extern "C" RustError sppark_b200_generate_points_dev(int curve, void* d_out, size_t n, void* stream)
+{
+    if (n >= (1ull << 31)) return rust_err(-(int)cudaErrorInvalidValue, "generate_points: n too large");
+    switch (curve) {
+    case SPPARK_CURVE_BLS12_381_G1: return gen_points_bls12_381(d_out, n, stream);
+    case SPPARK_CURVE_PALLAS: return gen_points_pallas(d_out, n, stream);
+    case SPPARK_CURVE_VESTA: return gen_points_vesta(d_out, n, stream);
+    default: return rust_err(-(int)cudaErrorInvalidValue, "generate_points: unknown curve");
+    }
+}
+
+extern "C" RustError sppark_b200_msm_combine(int curve, void* out, const void* partials, size_t count)
+{
+    switch (curve) {
+    case SPPARK_CURVE_BLS12_381_G1: return combine_bls12_381(out, partials, count);
+    case SPPARK_CURVE_PALLAS: return combine_pallas(out, partials, count);
+    case SPPARK_CURVE_VESTA: return combine_vesta(out, partials, count);
+    default: return rust_err(-(int)cudaErrorInvalidValue, "msm_combine: unknown curve");
+    }
+}
+
 extern "C" RustError sppark_b200_msm(int curve, void* out, const void* points, size_t npoints,
                                      const void* scalars, size_t ffi_affine_sz)
 {

@@ -215,6 +215,8 @@ public:
         uint32_t *chunk_map = U32(o_cmap), *partials = U32(o_partials);
         uint32_t *sorted = U32(o_sorted), *buckets = U32(o_buckets);
 
+        g_profile.reset();
+        g_profile.mark("sort", stream);
         CUDA_OK(cudaMemsetAsync(counts, 0, nslots * 4, stream));
         CUDA_OK(cudaMemsetAsync(ctrl, 0, 16, stream));
 
@@ -227,6 +229,7 @@ public:
         COUNT_LAUNCH();
         CUDA_OK(cudaGetLastError());
 
+        g_profile.mark("accumulate", stream);
         int occ = 1;
         CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, accumulate_kernel<F>, ACC_THREADS, 0));
         if (occ < 1) occ = 1;
@@ -235,6 +238,7 @@ public:
         accumulate_kernel<F><<<acc_blocks, ACC_THREADS, 0, stream>>>(cfg, d_points, sorted, offsets, counts,
                                                                     buckets, task_counter);
         COUNT_LAUNCH();
+        g_profile.mark("heavy", stream);
         heavy_chunks_kernel<F><<<sms * 4, HEAVY_THREADS, HEAVY_THREADS * BW * 4, stream>>>(
             cfg, d_points, sorted, offsets, counts, ctrl, heavy_list, chunk_map, partials);
         COUNT_LAUNCH();
@@ -243,6 +247,7 @@ public:
         CUDA_OK(cudaGetLastError());
 
         // running sums
+        g_profile.mark("reduce", stream);
         uint32_t *R[2] = {U32(o_r0), U32(o_r1)}, *S[2] = {U32(o_s0), U32(o_s1)};
         reduce1_kernel<F><<<(items1 + 127) / 128, 128, 0, stream>>>(cfg, buckets, lg_l, items1, R[0], S[0]);
         COUNT_LAUNCH();
@@ -258,8 +263,10 @@ public:
             lg_span += lg_g;
             cur ^= 1;
         }
+        g_profile.mark("finish", stream);
         finish_kernel<F><<<1, 32, 0, stream>>>(cfg, R[cur], d_out);
         COUNT_LAUNCH();
+        g_profile.mark("end", stream);
         CUDA_OK(cudaGetLastError());
         if (getenv("SPPARK_B200_MSM_DEBUG")) {
             uint32_t dbg[3];

@@ -7,6 +7,11 @@ RustError msm_host_bls12_381(void* out, const void* points, size_t npoints, cons
 RustError msm_dev_bls12_381(void* out, const void* d_points, size_t npoints, const void* d_scalars, void* stream)
 {   return msm_dev<ff::bls12_381_fp_t>(out, d_points, npoints, d_scalars, stream);   }
 
+RustError gen_points_bls12_381(void* d_out, size_t n, void* stream)
+{   return gen_points_dev<ff::bls12_381_g1_gen>(d_out, n, stream);   }
+RustError combine_bls12_381(void* out, const void* partials, size_t count)
+{   return combine_host<ff::bls12_381_fp_t>(out, partials, count);   }
+
 extern "C" RustError mult_pippenger(void* out, const void* points, size_t npoints, const void* scalars)
 {   return msm_host_bls12_381(out, points, npoints, scalars, 96, false);   }
 

@@ -80,4 +80,78 @@ RustError msm_dev(void* out, const void* d_points, size_t npoints, const void* d
     return rust_ok();
 }
 
+
+// ---- synthetic inputs: out[i] = (i+1)*G, affine (role of util::generate_points_scalars,
+// poc/msm-cuda/src/util.rs:11-38, which replicates 2^11 random points) ------------------------
+template<class G>
+__global__ void gen_points_kernel(uint32_t* out, uint32_t n)
+{
+    typedef typename G::F F;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ec::affine_t<F> g;
+    for (int k = 0; k < F::N; k++) { g.X.l[k] = G::X(k); g.Y.l[k] = G::Y(k); }
+    ec::xyzz_t<F> acc;
+    acc.set_inf();
+    for (int bit = 31 - __clz(i + 1); bit >= 0; bit--) {
+        acc.dbl();
+        if (((i + 1) >> bit) & 1) acc.madd(g);
+    }
+    F x = acc.X * acc.ZZ.inv(), y = acc.Y * acc.ZZZ.inv();
+    for (int k = 0; k < F::N; k++) { out[(size_t)i * 2 * F::N + k] = x.l[k]; out[(size_t)i * 2 * F::N + F::N + k] = y.l[k]; }
+}
+
+template<class G>
+RustError gen_points_dev(void* d_out, size_t n, void* stream)
+{
+    try {
+        gen_points_kernel<G><<<(unsigned)((n + 63) / 64), 64, 0, (cudaStream_t)stream>>>((uint32_t*)d_out, (uint32_t)n);
+        COUNT_LAUNCH();
+        CUDA_OK(cudaGetLastError());
+    } catch (const cuda_error& e) {
+        return rust_err(e.code(), e.what());
+    }
+    return rust_ok();
+}
+
+// ---- sum of partial results (multi-GPU: every rank's Jacobian result -> one point) ----------
+template<class F>
+__global__ void combine_points_kernel(const uint32_t* partials, uint32_t count, uint32_t* out)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    ec::xyzz_t<F> acc;
+    acc.set_inf();
+    for (uint32_t i = 0; i < count; i++) {
+        const uint32_t* p = partials + (size_t)i * 3 * F::N;
+        ec::xyzz_t<F> q;
+        F z;
+        for (int k = 0; k < F::N; k++) { q.X.l[k] = p[k]; q.Y.l[k] = p[F::N + k]; z.l[k] = p[2 * F::N + k]; }
+        q.ZZ = z.sqr();                      // Jacobian (X, Y, Z) == XYZZ (X, Y, Z^3, Z^2)
+        q.ZZZ = q.ZZ * z;
+        acc.add(q);
+    }
+    ec::jacobian_t<F> j = acc.to_jacobian();
+    for (int k = 0; k < F::N; k++) { out[k] = j.X.l[k]; out[F::N + k] = j.Y.l[k]; out[2 * F::N + k] = j.Z.l[k]; }
+}
+
+template<class F>
+RustError combine_host(void* out, const void* partials, size_t count)
+{
+    constexpr size_t JB = 3 * F::N * 4;
+    try {
+        const gpu_t& gpu = select_gpu(-1);
+        const stream_t& s = gpu[0];
+        dev_ptr_t<uint32_t> d_in(count * JB / 4, s), d_out(JB / 4, s);
+        s.HtoD(d_in, partials, count * JB);
+        combine_points_kernel<F><<<1, 32, 0, s>>>(d_in, (uint32_t)count, d_out);
+        COUNT_LAUNCH();
+        CUDA_OK(cudaGetLastError());
+        s.DtoH(out, d_out, JB);
+        s.sync();
+    } catch (const cuda_error& e) {
+        return rust_err(e.code(), e.what());
+    }
+    return rust_ok();
+}
+
 }  // namespace

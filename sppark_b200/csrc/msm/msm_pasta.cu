@@ -12,3 +12,11 @@ RustError msm_host_vesta(void* out, const void* points, size_t npoints, const vo
 {   return msm_host<ff::vesta_fp_t>(out, points, npoints, scalars, stride, has_flag);   }
 RustError msm_dev_vesta(void* out, const void* d_points, size_t npoints, const void* d_scalars, void* stream)
 {   return msm_dev<ff::vesta_fp_t>(out, d_points, npoints, d_scalars, stream);   }
+RustError gen_points_pallas(void* d_out, size_t n, void* stream)
+{   return gen_points_dev<ff::pallas_gen>(d_out, n, stream);   }
+RustError gen_points_vesta(void* d_out, size_t n, void* stream)
+{   return gen_points_dev<ff::vesta_gen>(d_out, n, stream);   }
+RustError combine_pallas(void* out, const void* partials, size_t count)
+{   return combine_host<ff::pallas_fp_t>(out, partials, count);   }
+RustError combine_vesta(void* out, const void* partials, size_t count)
+{   return combine_host<ff::vesta_fp_t>(out, partials, count);   }

@@ -182,13 +182,16 @@ public:
                                          (int)gpu.props().sharedMemPerBlockOptin));
             attr_done[gpu.cid() & 63] = true;
         }
+        g_profile.reset();
         for (const Pass& d : plan.passes) {
+            g_profile.mark("pass", stream);
             uint32_t ntiles = 1u << (lg_n - d.lg_r - d.lg_w);
             size_t smem = smem_elems(d) * sizeof(T);
             pass_kernel<F><<<ntiles, tile_threads(d), smem, stream>>>(d, tb, buf[d.src], buf[d.dst]);
             COUNT_LAUNCH();
             CUDA_OK(cudaGetLastError());
         }
+        g_profile.mark("end", stream);
         if (scratch) CUDA_OK(cudaFreeAsync(scratch, stream));
 
         if (inverse && type == Type::coset)

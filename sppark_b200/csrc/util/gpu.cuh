@@ -40,6 +40,26 @@ inline RustError rust_err(int code, const std::string& msg)
 {   return RustError{code, msg.empty() ? nullptr : strdup(msg.c_str())};   }
 
 extern std::atomic<uint64_t> g_launch_count;      // defined in api.cu
+
+// Optional phase timing (bench.py's roofline leg): when enabled, the drivers drop CUDA events
+// on their own stream at phase boundaries of the LAST call; sppark_b200_profile_read() turns
+// them into milliseconds once the caller has synchronised.  Off by default (no events).
+struct phase_profile_t {
+    static constexpr int MAX = 16;
+    bool enabled = false;
+    int n = 0;
+    cudaEvent_t ev[MAX] = {};
+    const char* name[MAX] = {};
+    void mark(const char* what, cudaStream_t s)
+    {
+        if (!enabled || n >= MAX) return;
+        if (!ev[n]) cudaEventCreate(&ev[n]);
+        cudaEventRecord(ev[n], s);
+        name[n++] = what;
+    }
+    void reset() { n = 0; }
+};
+extern phase_profile_t g_profile;
 #define COUNT_LAUNCH() (g_launch_count.fetch_add(1, std::memory_order_relaxed))
 
 class stream_t {

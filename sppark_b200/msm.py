@@ -73,6 +73,26 @@ def msm_dev(curve, d_points, d_scalars, npoints=None, stream=None):
     return out
 
 
+def generate_points_dev(curve, n, device=None):
+    """(n, 2*limbs) int64 CUDA tensor holding (i+1)*G, i < n, as packed Montgomery affine points."""
+    import torch
+    nl = _LIMBS[curve]
+    out = torch.empty((n, 2 * nl), dtype=torch.int64, device=device or "cuda")
+    with torch.cuda.device(out.device):
+        err = _lib.lib().sppark_b200_generate_points_dev(curve, out.data_ptr(), n,
+                                                         torch.cuda.current_stream().cuda_stream)
+    _lib.check(err)
+    return out
+
+
+def combine(curve, partials):
+    """Sum of Jacobian points: partials (count, 3*limbs) uint64 host array."""
+    partials = np.ascontiguousarray(partials, dtype=np.uint64)
+    out = np.zeros(3 * _LIMBS[curve], dtype=np.uint64)
+    _lib.check(_lib.lib().sppark_b200_msm_combine(curve, out.ctypes.data, partials.ctypes.data, partials.shape[0]))
+    return out
+
+
 def selftest_field(field, op, a, b):
     a = np.ascontiguousarray(a, dtype=np.uint64)
     b = np.ascontiguousarray(b, dtype=np.uint64)

@@ -105,3 +105,34 @@ def test_bad_arguments_return_errors():
         l.drop_error_message(err.message)
     err = l.compute_ntt(0, buf.ctypes.data, 0, 0, 0, 0)     # lg == 0: no-op success
     assert err.code == 0
+
+
+def test_matches_reference_gpu_golden():
+    """Bit-exact against outputs of the reference's own CUDA NTT recorded on a B200
+    (tests/golden/ntt_ref_gpu.npz, made by tests/golden/make_golden.py): every order x direction
+    x type, lg 1..10, Goldilocks."""
+    import os
+    from sppark_b200 import _lib
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ntt_ref_gpu.npz"))
+    l = _lib.lib()
+    for lg in range(1, 11):
+        x = g[f"gl64_in_{lg}"]
+        for order in range(4):
+            for d in range(2):
+                for t in range(2):
+                    y = x.copy()
+                    _lib.check(l.compute_ntt(0, y.ctypes.data, lg, order, d, t))
+                    assert np.array_equal(y, g[f"gl64_out_{lg}_{order}{d}{t}"]), (lg, order, d, t)
+
+
+@pytest.mark.parametrize("field", ["gl64", "bb31"])
+def test_bb_extension_order(oracle, field):
+    """BB (bit-reversed in and out) is this library's extension; checked against the oracle."""
+    from sppark_b200 import ntt
+    ofn = oracle.ntt_gl64 if field == "gl64" else oracle.ntt_bb31
+    for lg in (1, 4, 12, 13, 18):
+        x = _rand(field, 1 << lg, 900 + lg)
+        for inverse in (False, True):
+            y = x.copy()
+            (ntt.iNTT if inverse else ntt.NTT)(0, y, ntt.BB)
+            assert np.array_equal(y, ofn(x, oracle.BB, inverse, nthreads=8))
