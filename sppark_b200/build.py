@@ -9,10 +9,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libsppark_b200.so")
+LIB = os.environ.get("SPPARK_B200_LIB") or os.path.join(HERE, "libsppark_b200.so")   # override: experiments only
 
 SOURCES = ["api.cu", "util/gpu.cu", "ntt/ntt.cu", "msm/msm.cu", "msm/msm_bls12_381.cu", "msm/msm_pasta.cu"]
-NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+# SPPARK_B200_MUL_OUTLINE: one shared copy of the Montgomery ladder per kernel (mont.cuh)
+NVCC_FLAGS = ["-std=c++17", "-O3", "-DSPPARK_B200_MUL_OUTLINE", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--threads", "4"]
 
 
@@ -34,11 +35,12 @@ def build(force=False, verbose=False):
         return LIB
     objs = []
     procs = []
-    objdir = os.path.join(HERE, "build")
+    extra = os.environ.get("SPPARK_B200_NVCC_EXTRA", "").split()
+    objdir = os.path.join(HERE, "build" + ("_" + os.path.basename(LIB) if extra else ""))
     os.makedirs(objdir, exist_ok=True)
     for src in _sources():
         obj = os.path.join(objdir, os.path.basename(src).replace(".cu", ".o"))
-        cmd = ["nvcc", *NVCC_FLAGS, "-c", "-o", obj, src]
+        cmd = ["nvcc", *NVCC_FLAGS, *extra, "-c", "-o", obj, src]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((subprocess.Popen(cmd), cmd))

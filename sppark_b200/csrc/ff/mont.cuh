@@ -212,7 +212,16 @@ struct mont_t {
     }
 #endif
 
-    friend HD mont_t operator*(const mont_t& a, const mont_t& b)
+#if defined(__CUDA_ARCH__) && defined(SPPARK_B200_MUL_OUTLINE)
+    // one shared copy of the ladder per kernel: the unrolled product is ~450 instructions and a
+    // mixed add has ten of them, which overflows the instruction cache when everything is inlined
+    static __device__ __noinline__ mont_t mul_outlined(mont_t a, mont_t b) { return mul_inline(a, b); }
+    friend DEV mont_t operator*(const mont_t& a, const mont_t& b) { return mul_outlined(a, b); }
+#else
+    friend HD mont_t operator*(const mont_t& a, const mont_t& b) { return mul_inline(a, b); }
+#endif
+
+    static HD mont_t mul_inline(const mont_t& a, const mont_t& b)
     {
         mont_t r;
 #if defined(__CUDA_ARCH__)
@@ -270,8 +279,12 @@ struct mont_t {
     {
         mont_t acc = one(), base = *this;
         uint32_t e[N];
-        for (int i = 0; i < N; i++) e[i] = C::P(i);
-        e[0] -= 2;
+        uint32_t borrow = 2;                          // e = p - 2, with borrow (P(0) may be 1)
+        for (int i = 0; i < N; i++) {
+            uint32_t pi = C::P(i);
+            e[i] = pi - borrow;
+            borrow = pi < borrow ? 1 : 0;
+        }
         for (int i = N * 32 - 1; i >= 0; i--) {
             acc = acc.sqr();
             if ((e[i / 32] >> (i % 32)) & 1) acc = acc * base;

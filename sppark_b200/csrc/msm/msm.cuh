@@ -15,7 +15,7 @@ static __global__ void count_kernel(const Config cfg, const uint32_t* scalars, u
         count_body(cfg, scalars, counts, i);
 }
 
-constexpr uint32_t HEAVY_CHUNK = 4096;      // entries of a heavy bucket folded by one CTA
+constexpr uint32_t HEAVY_CHUNK = 16384;     // entries of a heavy bucket folded by one CTA
 
 // control block: [0] task counter, [1] #heavy buckets, [2] #chunks
 // heavy bucket h: heavy_list[3h] = slot, [3h+1] = first chunk, [3h+2] = #chunks; chunk_map[c] = h
@@ -64,7 +64,7 @@ static __global__ void scatter_kernel(const Config cfg, const uint32_t* scalars,
 }
 
 template<class F>
-__global__ void __launch_bounds__(ACC_THREADS)
+__global__ void __launch_bounds__(ACC_THREADS, 3)
 accumulate_kernel(const Config cfg, const uint32_t* points, const uint32_t* sorted,
                   const uint32_t* offsets, const uint32_t* counts, uint32_t* buckets,
                   uint32_t* task_counter)
@@ -114,8 +114,8 @@ heavy_chunks_kernel(const Config cfg, const uint32_t* points, const uint32_t* so
 // phase B: one CTA per heavy bucket folds that bucket's chunk partials
 template<class F>
 __global__ void __launch_bounds__(HEAVY_THREADS)
-heavy_fold_kernel(const uint32_t* ctrl, const uint32_t* heavy_list, const uint32_t* partials,
-                  uint32_t* buckets)
+heavy_fold_kernel(const Config cfg, const uint32_t* ctrl, const uint32_t* heavy_list,
+                  const uint32_t* partials, uint32_t* buckets)
 {
     extern __shared__ __align__(16) uint32_t tree[];
     const uint32_t nheavy = ctrl[1];
@@ -126,7 +126,10 @@ heavy_fold_kernel(const uint32_t* ctrl, const uint32_t* heavy_list, const uint32
         for (uint32_t k = threadIdx.x; k < nch; k += blockDim.x)
             acc.add(load_bucket<F>(partials, first + k));
         block_sum<F>(acc, tree);
-        if (threadIdx.x == 0) store_bucket<F>(buckets, t, acc);
+        if (threadIdx.x == 0) {
+            if (cfg.merge) acc.add(load_bucket<F>(buckets, t));
+            store_bucket<F>(buckets, t, acc);
+        }
         __syncthreads();
     }
 }
@@ -175,6 +178,131 @@ class msm_t {
 public:
     explicit msm_t(const gpu_t& g) : gpu(g) {}
 
+    // ---- a transform in flight: buckets persist across slices of points ----------------------
+    struct Job {
+        Config cfg;                 // window geometry for the WHOLE MSM; npoints = slice capacity
+        size_t nslots, slice_cap;
+        uint32_t lg_l, items1;
+        uint8_t* blob;
+        uint32_t *counts, *offsets, *cursor, *ctrl, *heavy_list, *chunk_map, *partials, *sorted, *buckets;
+        uint32_t *R[2], *S[2];
+        uint32_t slices_done;
+    };
+
+    // total_points fixes the window width; slice_cap is the most points one slice() call may carry
+    Job begin(size_t total_points, size_t slice_cap, cudaStream_t stream)
+    {
+        if (total_points >= (1ull << 31))
+            throw cuda_error(-(int)cudaErrorInvalidValue, "msm: npoints must be < 2^31");
+        Job j;
+        j.cfg = make_config(total_points);
+        j.cfg.npoints = (uint32_t)slice_cap;
+        j.slice_cap = slice_cap;
+        j.nslots = (size_t)j.cfg.nwins << j.cfg.lg_nb;
+        j.lg_l = j.cfg.lg_nb > 12 ? j.cfg.lg_nb - 12 : 0;          // <= 4096 running-sum items per window
+        j.items1 = j.cfg.nwins << (j.cfg.lg_nb - j.lg_l);
+        j.slices_done = 0;
+        const size_t entries = (size_t)j.cfg.nwins * slice_cap;
+        const size_t heavy_cap = entries / (j.cfg.heavy + 1) + 1;   // most heavy buckets possible
+        const size_t chunk_cap = entries / HEAVY_CHUNK + heavy_cap; // most chunks possible
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+        const size_t o_counts = take(j.nslots * 4), o_offsets = take(j.nslots * 4), o_cursor = take(j.nslots * 4);
+        const size_t o_ctrl = take(16), o_heavy = take(heavy_cap * 12), o_cmap = take(chunk_cap * 4);
+        const size_t o_partials = take(chunk_cap * BW * 4);
+        const size_t o_sorted = take(entries * 4);
+        const size_t o_buckets = take(j.nslots * BW * 4);
+        const size_t o_r0 = take((size_t)j.items1 * BW * 4), o_s0 = take((size_t)j.items1 * BW * 4);
+        const size_t o_r1 = take((size_t)j.items1 * BW * 4 / 2 + 4096), o_s1 = take((size_t)j.items1 * BW * 4 / 2 + 4096);
+        CUDA_OK(cudaMallocAsync((void**)&j.blob, off, stream));
+        auto U32 = [&](size_t o) { return reinterpret_cast<uint32_t*>(j.blob + o); };
+        j.counts = U32(o_counts); j.offsets = U32(o_offsets); j.cursor = U32(o_cursor);
+        j.ctrl = U32(o_ctrl); j.heavy_list = U32(o_heavy); j.chunk_map = U32(o_cmap);
+        j.partials = U32(o_partials); j.sorted = U32(o_sorted); j.buckets = U32(o_buckets);
+        j.R[0] = U32(o_r0); j.S[0] = U32(o_s0); j.R[1] = U32(o_r1); j.S[1] = U32(o_s1);
+        g_profile.reset();
+        return j;
+    }
+
+    // fold `n` (<= slice_cap) device-resident points/scalars into the buckets
+    void slice(Job& j, const uint32_t* d_points, const uint32_t* d_scalars, size_t n, cudaStream_t stream)
+    {
+        if (n == 0) return;
+        Config cfg = j.cfg;
+        cfg.npoints = (uint32_t)n;
+        cfg.merge = j.slices_done ? 1 : 0;
+        const uint32_t sms = (uint32_t)gpu.sm_count();
+        g_profile.mark("sort", stream);
+        CUDA_OK(cudaMemsetAsync(j.counts, 0, j.nslots * 4, stream));
+        CUDA_OK(cudaMemsetAsync(j.ctrl, 0, 16, stream));
+        const uint32_t nblk = (uint32_t)std::min<size_t>((n + 255) / 256, (size_t)sms * 16);
+        count_kernel<<<nblk, 256, 0, stream>>>(cfg, d_scalars, j.counts);
+        COUNT_LAUNCH();
+        scan_kernel<<<cfg.nwins, 1024, 0, stream>>>(cfg, j.counts, j.offsets, j.cursor, j.ctrl, j.heavy_list, j.chunk_map);
+        COUNT_LAUNCH();
+        scatter_kernel<<<nblk, 256, 0, stream>>>(cfg, d_scalars, j.cursor, j.sorted);
+        COUNT_LAUNCH();
+        CUDA_OK(cudaGetLastError());
+
+        g_profile.mark("accumulate", stream);
+        int occ = 1;
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, accumulate_kernel<F>, ACC_THREADS, 0));
+        if (occ < 1) occ = 1;
+        size_t want = (j.nslots + ACC_THREADS - 1) / ACC_THREADS;
+        uint32_t acc_blocks = (uint32_t)std::min<size_t>(want, (size_t)sms * occ);
+        accumulate_kernel<F><<<acc_blocks, ACC_THREADS, 0, stream>>>(cfg, d_points, j.sorted, j.offsets, j.counts,
+                                                                    j.buckets, j.ctrl);
+        COUNT_LAUNCH();
+        g_profile.mark("heavy", stream);
+        heavy_chunks_kernel<F><<<sms * 4, HEAVY_THREADS, HEAVY_THREADS * BW * 4, stream>>>(
+            cfg, d_points, j.sorted, j.offsets, j.counts, j.ctrl, j.heavy_list, j.chunk_map, j.partials);
+        COUNT_LAUNCH();
+        heavy_fold_kernel<F><<<sms, HEAVY_THREADS, HEAVY_THREADS * BW * 4, stream>>>(cfg, j.ctrl, j.heavy_list,
+                                                                                    j.partials, j.buckets);
+        COUNT_LAUNCH();
+        CUDA_OK(cudaGetLastError());
+        if (getenv("SPPARK_B200_MSM_DEBUG")) {
+            uint32_t dbg[3];
+            CUDA_OK(cudaMemcpyAsync(dbg, j.ctrl, 12, cudaMemcpyDeviceToHost, stream));
+            CUDA_OK(cudaStreamSynchronize(stream));
+            fprintf(stderr, "[msm] slice %u n=%u wbits=%u nwins=%u heavy_thr=%u tasks_claimed=%u nheavy=%u nchunks=%u acc_blocks=%u\n",
+                    j.slices_done, cfg.npoints, cfg.wbits, cfg.nwins, cfg.heavy, dbg[0], dbg[1], dbg[2], acc_blocks);
+        }
+        j.slices_done++;
+    }
+
+    // running sums over the buckets, Horner over the windows -> d_out (JW words), frees the job
+    void finish(Job& j, uint32_t* d_out, cudaStream_t stream)
+    {
+        if (j.slices_done == 0) {
+            CUDA_OK(cudaMemsetAsync(d_out, 0, JW * 4, stream));
+        } else {
+            const Config& cfg = j.cfg;
+            g_profile.mark("reduce", stream);
+            reduce1_kernel<F><<<(j.items1 + 127) / 128, 128, 0, stream>>>(cfg, j.buckets, j.lg_l, j.items1, j.R[0], j.S[0]);
+            COUNT_LAUNCH();
+            uint32_t per_win = 1u << (cfg.lg_nb - j.lg_l), lg_span = j.lg_l, cur = 0;
+            while (per_win > 1) {
+                uint32_t lg_g = 31 - __builtin_clz(per_win);
+                if (lg_g > 4) lg_g = 4;                         // radix 16 keeps the serial chains short
+                uint32_t G = 1u << lg_g, nitems = cfg.nwins * (per_win >> lg_g);
+                combine_kernel<F><<<(nitems + 127) / 128, 128, 0, stream>>>(j.R[cur], j.S[cur], G, lg_span, nitems,
+                                                                           j.R[cur ^ 1], j.S[cur ^ 1]);
+                COUNT_LAUNCH();
+                per_win >>= lg_g;
+                lg_span += lg_g;
+                cur ^= 1;
+            }
+            g_profile.mark("finish", stream);
+            finish_kernel<F><<<1, 32, 0, stream>>>(cfg, j.R[cur], d_out);
+            COUNT_LAUNCH();
+            g_profile.mark("end", stream);
+            CUDA_OK(cudaGetLastError());
+        }
+        CUDA_OK(cudaFreeAsync(j.blob, stream));
+        j.blob = nullptr;
+    }
+
     // all inputs device-resident: d_points packed affine, d_scalars 8 words each.
     // d_out: JW words of device memory.  Enqueues on `stream`; no synchronisation.
     void invoke_dev(uint32_t* d_out, const uint32_t* d_points, size_t npoints,
@@ -184,98 +312,9 @@ public:
             CUDA_OK(cudaMemsetAsync(d_out, 0, JW * 4, stream));
             return;
         }
-        if (npoints >= (1ull << 31))
-            throw cuda_error(-(int)cudaErrorInvalidValue, "msm: npoints must be < 2^31");
-        const Config cfg = make_config(npoints);
-        const size_t nslots = (size_t)cfg.nwins << cfg.lg_nb;
-        const size_t entries = (size_t)cfg.nwins * npoints;
-        const size_t heavy_cap = entries / (cfg.heavy + 1) + 1;                 // most heavy buckets possible
-        const size_t chunk_cap = entries / HEAVY_CHUNK + heavy_cap;            // most chunks possible
-        const uint32_t sms = (uint32_t)gpu.sm_count();
-
-        // level-1 chunking of the running sums: at most 4096 items per window
-        const uint32_t lg_l = cfg.lg_nb > 12 ? cfg.lg_nb - 12 : 0;
-        const uint32_t items1 = cfg.nwins << (cfg.lg_nb - lg_l);
-
-        // one stream-ordered blob
-        size_t off = 0;
-        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-        const size_t o_counts = take(nslots * 4), o_offsets = take(nslots * 4), o_cursor = take(nslots * 4);
-        const size_t o_ctrl = take(16), o_heavy = take(heavy_cap * 12), o_cmap = take(chunk_cap * 4);
-        const size_t o_partials = take(chunk_cap * BW * 4);
-        const size_t o_sorted = take((size_t)cfg.nwins * npoints * 4);
-        const size_t o_buckets = take(nslots * BW * 4);
-        const size_t o_r0 = take((size_t)items1 * BW * 4), o_s0 = take((size_t)items1 * BW * 4);
-        const size_t o_r1 = take((size_t)items1 * BW * 4 / 2 + 4096), o_s1 = take((size_t)items1 * BW * 4 / 2 + 4096);
-        uint8_t* blob;
-        CUDA_OK(cudaMallocAsync((void**)&blob, off, stream));
-        auto U32 = [&](size_t o) { return reinterpret_cast<uint32_t*>(blob + o); };
-        uint32_t *counts = U32(o_counts), *offsets = U32(o_offsets), *cursor = U32(o_cursor);
-        uint32_t *ctrl = U32(o_ctrl), *task_counter = ctrl, *heavy_list = U32(o_heavy);
-        uint32_t *chunk_map = U32(o_cmap), *partials = U32(o_partials);
-        uint32_t *sorted = U32(o_sorted), *buckets = U32(o_buckets);
-
-        g_profile.reset();
-        g_profile.mark("sort", stream);
-        CUDA_OK(cudaMemsetAsync(counts, 0, nslots * 4, stream));
-        CUDA_OK(cudaMemsetAsync(ctrl, 0, 16, stream));
-
-        const uint32_t nblk = (uint32_t)std::min<size_t>((npoints + 255) / 256, (size_t)sms * 16);
-        count_kernel<<<nblk, 256, 0, stream>>>(cfg, d_scalars, counts);
-        COUNT_LAUNCH();
-        scan_kernel<<<cfg.nwins, 1024, 0, stream>>>(cfg, counts, offsets, cursor, ctrl, heavy_list, chunk_map);
-        COUNT_LAUNCH();
-        scatter_kernel<<<nblk, 256, 0, stream>>>(cfg, d_scalars, cursor, sorted);
-        COUNT_LAUNCH();
-        CUDA_OK(cudaGetLastError());
-
-        g_profile.mark("accumulate", stream);
-        int occ = 1;
-        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, accumulate_kernel<F>, ACC_THREADS, 0));
-        if (occ < 1) occ = 1;
-        size_t want = (nslots + ACC_THREADS - 1) / ACC_THREADS;
-        uint32_t acc_blocks = (uint32_t)std::min<size_t>(want, (size_t)sms * occ);
-        accumulate_kernel<F><<<acc_blocks, ACC_THREADS, 0, stream>>>(cfg, d_points, sorted, offsets, counts,
-                                                                    buckets, task_counter);
-        COUNT_LAUNCH();
-        g_profile.mark("heavy", stream);
-        heavy_chunks_kernel<F><<<sms * 4, HEAVY_THREADS, HEAVY_THREADS * BW * 4, stream>>>(
-            cfg, d_points, sorted, offsets, counts, ctrl, heavy_list, chunk_map, partials);
-        COUNT_LAUNCH();
-        heavy_fold_kernel<F><<<sms, HEAVY_THREADS, HEAVY_THREADS * BW * 4, stream>>>(ctrl, heavy_list, partials, buckets);
-        COUNT_LAUNCH();
-        CUDA_OK(cudaGetLastError());
-
-        // running sums
-        g_profile.mark("reduce", stream);
-        uint32_t *R[2] = {U32(o_r0), U32(o_r1)}, *S[2] = {U32(o_s0), U32(o_s1)};
-        reduce1_kernel<F><<<(items1 + 127) / 128, 128, 0, stream>>>(cfg, buckets, lg_l, items1, R[0], S[0]);
-        COUNT_LAUNCH();
-        uint32_t per_win = 1u << (cfg.lg_nb - lg_l), lg_span = lg_l, cur = 0;
-        while (per_win > 1) {
-            uint32_t lg_g = 31 - __builtin_clz(per_win);
-            if (lg_g > 4) lg_g = 4;                         // radix 16 keeps the serial chains short
-            uint32_t G = 1u << lg_g, nitems = cfg.nwins * (per_win >> lg_g);
-            combine_kernel<F><<<(nitems + 127) / 128, 128, 0, stream>>>(R[cur], S[cur], G, lg_span, nitems,
-                                                                       R[cur ^ 1], S[cur ^ 1]);
-            COUNT_LAUNCH();
-            per_win >>= lg_g;
-            lg_span += lg_g;
-            cur ^= 1;
-        }
-        g_profile.mark("finish", stream);
-        finish_kernel<F><<<1, 32, 0, stream>>>(cfg, R[cur], d_out);
-        COUNT_LAUNCH();
-        g_profile.mark("end", stream);
-        CUDA_OK(cudaGetLastError());
-        if (getenv("SPPARK_B200_MSM_DEBUG")) {
-            uint32_t dbg[3];
-            CUDA_OK(cudaMemcpyAsync(dbg, ctrl, 12, cudaMemcpyDeviceToHost, stream));
-            CUDA_OK(cudaStreamSynchronize(stream));
-            fprintf(stderr, "[msm] n=%u wbits=%u nwins=%u heavy_thr=%u tasks_claimed=%u nheavy=%u nchunks=%u acc_blocks=%u items1=%u\n",
-                    cfg.npoints, cfg.wbits, cfg.nwins, cfg.heavy, dbg[0], dbg[1], dbg[2], acc_blocks, items1);
-        }
-        CUDA_OK(cudaFreeAsync(blob, stream));
+        Job j = begin(npoints, npoints, stream);
+        slice(j, d_points, d_scalars, npoints, stream);
+        finish(j, d_out, stream);
     }
 };
 

@@ -28,6 +28,7 @@ struct Config {
     uint32_t lg_nb;        // c - 1: log2(buckets per window)
     uint32_t npoints;
     uint32_t heavy;        // buckets with more entries go to the cooperative kernel
+    uint32_t merge;        // 0: first slice of points (buckets start empty); 1: add into the buckets
 };
 
 HD uint32_t atomic_inc(uint32_t* p, uint32_t v = 1)
@@ -167,15 +168,18 @@ HD void accumulate_body(const Config& cfg, const uint32_t* points, const uint32_
             if (t >= total) return;
             cnt = counts[t];
             if (cnt == 0) {
-                acc.set_inf();
-                store_bucket<F>(buckets, t, acc);
+                if (!cfg.merge) {
+                    acc.set_inf();
+                    store_bucket<F>(buckets, t, acc);
+                }
                 continue;
             }
             if (cnt > cfg.heavy) continue;
             break;
         }
         const uint32_t* run = sorted + (size_t)(t >> cfg.lg_nb) * cfg.npoints + offsets[t];
-        acc.set_inf();
+        if (cfg.merge) acc = load_bucket<F>(buckets, t);
+        else acc.set_inf();
         for (uint32_t k = 0; k < cnt; k++)
             acc.madd(load_point<F>(points, run[k]));
         store_bucket<F>(buckets, t, acc);
@@ -239,14 +243,16 @@ HD void finish_body(const Config& cfg, const uint32_t* winR, uint32_t* out_jacob
     }
 }
 
-// window width minimising  nwins*(n + ~2.8*2^(c-1))  mixed-add equivalents
+// window width minimising the measured cost model (B200, profiles/msm_phases_r01.txt):
+//   per (point, window): 1 mixed add + ~0.11 for count/scatter;  per bucket: ~5.5 mixed-add
+//   equivalents for the two full adds of the running sum
 inline uint32_t choose_wbits(size_t npoints)
 {
     uint32_t best = 4;
     double best_cost = 1e300;
     for (uint32_t c = 4; c <= 22; c++) {
         uint32_t nwins = (256 + c - 1) / c;
-        double cost = (double)nwins * ((double)npoints + 2.8 * (double)(1u << (c - 1)));
+        double cost = (double)nwins * (1.11 * (double)npoints + 5.5 * (double)(1u << (c - 1)));
         if (cost < best_cost) { best_cost = cost; best = c; }
     }
     if (const char* env = getenv("SPPARK_B200_MSM_WBITS")) {
@@ -263,7 +269,8 @@ inline Config make_config(size_t npoints)
     cfg.nwins = (256 + cfg.wbits - 1) / cfg.wbits;
     cfg.lg_nb = cfg.wbits - 1;
     cfg.npoints = (uint32_t)npoints;
-    cfg.heavy = 2048;
+    cfg.heavy = 4096;
+    cfg.merge = 0;
     if (const char* env = getenv("SPPARK_B200_MSM_HEAVY")) cfg.heavy = (uint32_t)atoi(env);
     return cfg;
 }

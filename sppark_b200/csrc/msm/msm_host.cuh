@@ -10,6 +10,11 @@
 
 namespace {
 
+// Host-pointer MSM.  The points arrive over PCIe while the GPU is already accumulating: the
+// input is cut into slices, slice k+1 is copied (copy stream, double-buffered) while slice k is
+// sorted and folded into the persistent buckets (compute stream).  The reference overlaps the
+// same way with its batches (msm/pippenger.cuh:505-557); here the bucket file is shared by all
+// slices, so the running sums and the Horner pass run once at the end instead of once per batch.
 template<class F>
 RustError msm_host(void* out, const void* points, size_t npoints, const void* scalars,
                    size_t stride, bool has_flag)
@@ -21,31 +26,53 @@ RustError msm_host(void* out, const void* points, size_t npoints, const void* sc
         if (npoints == 0) { memset(out, 0, JB); return rust_ok(); }
         if (stride < PB + (has_flag ? 1 : 0))
             return rust_err(-(int)cudaErrorInvalidValue, "msm: affine stride too small");
-        const stream_t &s0 = gpu[0], &s1 = gpu[1];
-        dev_ptr_t<uint32_t> d_points(npoints * (PB / 4), s0), d_out(JB / 4, s0);
-        dev_ptr_t<uint32_t> d_scalars(npoints * 8, s1);
-        cudaEvent_t ev;
-        CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        s1.HtoD(d_scalars, scalars, npoints * 32);
-        CUDA_OK(cudaEventRecord(ev, s1));
-        if (stride == PB && !has_flag) {
-            s0.HtoD(d_points, points, npoints * PB);
-        } else {
-            dev_ptr_t<uint8_t> d_raw(npoints * stride, s0);
-            s0.HtoD(d_raw, points, npoints * stride);
-            uint32_t blocks = (uint32_t)std::min<size_t>((npoints + 255) / 256, (size_t)gpu.sm_count() * 16);
-            msm::pack_points_kernel<<<blocks, 256, 0, s0>>>(d_raw, stride, PB / 4, has_flag, d_points,
-                                                           (uint32_t)npoints);
-            COUNT_LAUNCH();
-            CUDA_OK(cudaGetLastError());
-        }
-        CUDA_OK(cudaStreamWaitEvent(s0, ev, 0));
+        const stream_t &compute = gpu[0], &copy = gpu[1];
+        const bool packed = stride == PB && !has_flag;
+
+        size_t nslices = npoints >= (1u << 24) ? 4 : npoints >= (1u << 22) ? 2 : 1;
+        if (const char* env = getenv("SPPARK_B200_MSM_SLICES")) nslices = std::max(1, atoi(env));
+        size_t slice_n = (npoints + nslices - 1) / nslices;
+        slice_n = (slice_n + 31) & ~(size_t)31;
+        nslices = (npoints + slice_n - 1) / slice_n;
+        const size_t nbuf = nslices > 1 ? 2 : 1;
+
+        dev_ptr_t<uint32_t> d_out(JB / 4, compute);
+        dev_ptr_t<uint32_t> d_points(nbuf * slice_n * (PB / 4), compute), d_scalars(nbuf * slice_n * 8, compute);
+        dev_ptr_t<uint8_t> d_raw(packed ? 1 : nbuf * slice_n * stride, compute);
+        cudaEvent_t copied[2], consumed[2], ready;
+        for (auto* e : {&copied[0], &copied[1], &consumed[0], &consumed[1], &ready})
+            CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        CUDA_OK(cudaEventRecord(ready, compute));                 // buffers exist
+        CUDA_OK(cudaStreamWaitEvent(copy, ready, 0));
+
         msm::msm_t<F> m(gpu);
-        m.invoke_dev(d_out, d_points, npoints, d_scalars, s0);
-        s0.DtoH(out, d_out, JB);
-        s0.sync();
-        s1.sync();
-        cudaEventDestroy(ev);
+        auto job = m.begin(npoints, slice_n, compute);
+        for (size_t k = 0; k < nslices; k++) {
+            const size_t b = k & (nbuf - 1), first = k * slice_n, n = std::min(slice_n, npoints - first);
+            uint32_t* dp = d_points + b * slice_n * (PB / 4);
+            uint32_t* ds = d_scalars + b * slice_n * 8;
+            if (k >= nbuf) CUDA_OK(cudaStreamWaitEvent(copy, consumed[b], 0));   // buffer free again
+            copy.HtoD(ds, (const uint8_t*)scalars + first * 32, n * 32);
+            if (packed) {
+                copy.HtoD(dp, (const uint8_t*)points + first * PB, n * PB);
+            } else {
+                uint8_t* dr = d_raw + b * slice_n * stride;
+                copy.HtoD(dr, (const uint8_t*)points + first * stride, n * stride);
+                uint32_t blocks = (uint32_t)std::min<size_t>((n + 255) / 256, (size_t)gpu.sm_count() * 8);
+                msm::pack_points_kernel<<<blocks, 256, 0, copy>>>(dr, stride, PB / 4, has_flag, dp, (uint32_t)n);
+                COUNT_LAUNCH();
+                CUDA_OK(cudaGetLastError());
+            }
+            CUDA_OK(cudaEventRecord(copied[b], copy));
+            CUDA_OK(cudaStreamWaitEvent(compute, copied[b], 0));
+            m.slice(job, dp, ds, n, compute);
+            CUDA_OK(cudaEventRecord(consumed[b], compute));
+        }
+        m.finish(job, d_out, compute);
+        compute.DtoH(out, d_out, JB);
+        compute.sync();
+        copy.sync();
+        for (auto e : {copied[0], copied[1], consumed[0], consumed[1], ready}) cudaEventDestroy(e);
     } catch (const cuda_error& e) {
         memset(out, 0, JB);                      // out->inf(), as the reference does on failure
         return rust_err(e.code(), e.what());

@@ -114,6 +114,9 @@ public:
         CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, cid));
         uint64_t keep = ~0ull;                              // keep freed scratch in the pool
         CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        // the point-arithmetic helpers that are deliberately NOT inlined (xyzz add/dbl, the
+        // outlined Montgomery ladder) keep their operands on the local-memory stack
+        CUDA_OK(cudaDeviceSetLimit(cudaLimitStackSize, 4096));
     }
     int id() const { return gpu_id; }
     int cid() const { return cuda_id; }

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 #include "../../sppark_b200/csrc/ff/fields.cuh"
 #include "../../sppark_b200/csrc/msm/msm_core.cuh"
@@ -11,17 +12,29 @@
 using namespace msm;
 
 template<class F>
-static void emu_msm(uint32_t* out, const uint32_t* points, size_t npoints, const uint32_t* scalars,
-                    uint32_t wbits, uint32_t heavy)
+static void emu_msm(uint32_t* out, const uint32_t* points_all, size_t npoints_all, const uint32_t* scalars_all,
+                    uint32_t wbits, uint32_t heavy, uint32_t nslices = 1)
 {
+    size_t npoints = npoints_all;
     constexpr uint32_t BW = 4 * F::N, JW = 3 * F::N;
     if (npoints == 0) { memset(out, 0, JW * 4); return; }
     Config cfg = make_config(npoints);
     if (wbits) { cfg.wbits = wbits; cfg.nwins = (256 + wbits - 1) / wbits; cfg.lg_nb = wbits - 1; }
     if (heavy) cfg.heavy = heavy;
     const size_t nslots = (size_t)cfg.nwins << cfg.lg_nb;
-    std::vector<uint32_t> counts(nslots, 0), offsets(nslots), cursor(nslots), sorted((size_t)cfg.nwins * npoints);
+    std::vector<uint32_t> counts(nslots, 0), offsets(nslots), cursor(nslots), sorted((size_t)cfg.nwins * npoints_all);
     std::vector<uint32_t> buckets(nslots * BW, 0xdeadbeef), heavy_list;
+    if (nslices == 0) nslices = 1;
+    const size_t slice_n = (npoints_all + nslices - 1) / nslices;
+    for (size_t first = 0, sl = 0; first < npoints_all; first += slice_n, sl++) {
+    // ---- one slice: msm_t::slice() -------------------------------------------------------------
+    npoints = std::min(slice_n, npoints_all - first);
+    const uint32_t* points = points_all + first * 2 * F::N;
+    const uint32_t* scalars = scalars_all + first * 8;
+    cfg.npoints = (uint32_t)npoints;
+    cfg.merge = sl ? 1 : 0;
+    std::fill(counts.begin(), counts.end(), 0);
+    heavy_list.clear();
     for (uint32_t i = 0; i < npoints; i++) count_body(cfg, scalars, counts.data(), i);
     for (uint32_t w = 0; w < cfg.nwins; w++) {                 // scan_kernel
         uint32_t run = 0;
@@ -50,8 +63,10 @@ static void emu_msm(uint32_t* out, const uint32_t* points, size_t npoints, const
                 acc[th].add(load_bucket<F>(tree.data(), th + d));
                 store_bucket<F>(tree.data(), th, acc[th]);
             }
+        if (cfg.merge) acc[0].add(load_bucket<F>(buckets.data(), t));
         store_bucket<F>(buckets.data(), t, acc[0]);
     }
+    }   // slices
     const uint32_t lg_l = cfg.lg_nb > 3 ? cfg.lg_nb - 3 : 0;      // small chunks so that every level runs
     uint32_t per_win = 1u << (cfg.lg_nb - lg_l), items = cfg.nwins * per_win;
     std::vector<uint32_t> R[2], S[2];
@@ -73,6 +88,9 @@ static void emu_msm(uint32_t* out, const uint32_t* points, size_t npoints, const
 extern "C" void emu_msm_bls12_381(uint32_t* out, const uint32_t* points, size_t n, const uint32_t* scalars,
                                   uint32_t wbits, uint32_t heavy)
 {   emu_msm<ff::bls12_381_fp_t>(out, points, n, scalars, wbits, heavy);   }
+extern "C" void emu_msm_bls12_381_sliced(uint32_t* out, const uint32_t* points, size_t n, const uint32_t* scalars,
+                                         uint32_t wbits, uint32_t heavy, uint32_t nslices)
+{   emu_msm<ff::bls12_381_fp_t>(out, points, n, scalars, wbits, heavy, nslices);   }
 extern "C" void emu_msm_pallas(uint32_t* out, const uint32_t* points, size_t n, const uint32_t* scalars,
                                uint32_t wbits, uint32_t heavy)
 {   emu_msm<ff::pallas_fp_t>(out, points, n, scalars, wbits, heavy);   }

@@ -35,6 +35,7 @@ def ntt_emu():
 def msm_emu():
     l = _build("msm_emu")
     l.emu_msm_bls12_381.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint, C.c_uint]
+    l.emu_msm_bls12_381_sliced.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint, C.c_uint, C.c_uint]
     l.emu_msm_pallas.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint, C.c_uint]
     l.emu_fp_op.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return l
@@ -95,6 +96,20 @@ def test_msm_pipeline_adversarial_scalars(oracle, msm_emu, val):
     pts[5][6:] = [((p - y1) >> (64 * i)) & (2**64 - 1) for i in range(6)]     # a (P, -P) pair in one bucket
     assert _run(oracle, msm_emu, pts, _scalars([val] * n), 6, 8)
     assert _run(oracle, msm_emu, pts, _scalars([val] * n), 5, 0)
+
+
+@pytest.mark.parametrize("n,wbits,heavy,nslices", [(300, 6, 0, 3), (501, 5, 3, 4), (64, 9, 2, 2), (40, 4, 0, 40)])
+def test_msm_sliced_bucket_merging(oracle, msm_emu, n, wbits, heavy, nslices):
+    """slices of points folded into persistent buckets (the host-pointer pipeline)"""
+    rnd = random.Random(n + nslices)
+    pts = oracle.gen_points("bls12_381", 16)[np.arange(n) % 16].copy()
+    pts[3] = 0
+    sc = _scalars([rnd.randrange(R_BLS) for _ in range(n)])
+    sc[: n // 3] = sc[0]
+    out = np.zeros(18, dtype=np.uint64)
+    msm_emu.emu_msm_bls12_381_sliced(out.ctypes.data, pts.ctypes.data, n, sc.ctypes.data, wbits, heavy, nslices)
+    want = oracle.msm("bls12_381", pts, sc, "pippenger", ncpus=4)
+    assert np.array_equal(oracle.jac_to_affine("bls12_381", out), oracle.jac_to_affine("bls12_381", want))
 
 
 def test_portable_field_branch(oracle, msm_emu):

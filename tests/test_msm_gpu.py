@@ -179,3 +179,21 @@ def test_device_resident_entry(oracle):
     got = msm.msm_dev(0, torch.from_numpy(pts.view(np.int64)).cuda(), torch.from_numpy(sc.view(np.int64)).cuda())
     want = oracle.msm("bls12_381", pts, sc, "pippenger", ncpus=8)
     assert _same_point(oracle, "bls12_381", got, want)
+
+
+@pytest.mark.parametrize("nslices", [2, 3, 7])
+def test_host_pipeline_slices(oracle, monkeypatch, nslices):
+    """host-pointer path with the input cut into slices that share one bucket file"""
+    from sppark_b200 import msm
+    monkeypatch.setenv("SPPARK_B200_MSM_SLICES", str(nslices))
+    n = 30011
+    pts = np.zeros((n, 13), dtype=np.uint64)
+    pts[:, :12] = oracle.gen_points("bls12_381", 97)[np.arange(n) % 97]
+    pts[::11, 12] = 1
+    sc = _scalars(n, nslices)
+    sc[100:9000] = sc[7]                                # a heavy bucket in every window and slice
+    clean = pts[:, :12].copy()
+    clean[::11] = 0
+    want = oracle.msm("bls12_381", clean, sc, "pippenger", ncpus=8)
+    assert _same_point(oracle, "bls12_381", msm.multi_scalar_mult_arkworks(pts, sc), want)
+    assert _same_point(oracle, "bls12_381", msm.multi_scalar_mult(clean, sc), want)
