@@ -12,8 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("SPPARK_B200_LIB") or os.path.join(HERE, "libsppark_b200.so")   # override: experiments only
 
 SOURCES = ["api.cu", "util/gpu.cu", "ntt/ntt.cu", "msm/msm.cu", "msm/msm_bls12_381.cu", "msm/msm_pasta.cu"]
-# SPPARK_B200_MUL_OUTLINE: one shared copy of the Montgomery ladder per kernel (mont.cuh)
-NVCC_FLAGS = ["-std=c++17", "-O3", "-DSPPARK_B200_MUL_OUTLINE", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--threads", "4"]
 
 

@@ -45,7 +45,7 @@ template<class F> struct xyzz_t {
     }
 
     // doubling of an affine point (mdbl-2008-s-1, a = 0)
-    HD void set_double_of(const affine_t<F>& p)
+    HD_NOINLINE void set_double_of(const affine_t<F>& p)
     {
         F U = p.Y.dbl();
         F V = U.sqr();
@@ -61,25 +61,26 @@ template<class F> struct xyzz_t {
     }
 
     // *this += p2  (p2 affine, Y already sign-adjusted by the caller).  8M + 2S.
+    // This is the hot loop of the MSM: its ten products go through F::mul_shared.
     HD void madd(const affine_t<F>& p2)
     {
         if (p2.is_inf()) return;
         if (is_inf()) { set_affine(p2); return; }
-        F P = p2.X * ZZ - X;                        // U2 - X1
-        F R = p2.Y * ZZZ - Y;                       // S2 - Y1
+        F P = F::mul_shared(p2.X, ZZ) - X;          // U2 - X1
+        F R = F::mul_shared(p2.Y, ZZZ) - Y;         // S2 - Y1
         if (P.is_zero()) {
             if (R.is_zero()) set_double_of(p2);
             else set_inf();
             return;
         }
-        F PP = P.sqr();
-        F PPP = P * PP;
-        F Q = X * PP;
-        F X3 = R.sqr() - PPP - Q - Q;
-        Y = R * (Q - X3) - Y * PPP;
+        F PP = F::mul_shared(P, P);
+        F PPP = F::mul_shared(P, PP);
+        F Q = F::mul_shared(X, PP);
+        F X3 = F::mul_shared(R, R) - PPP - Q - Q;
+        Y = F::mul_shared(R, Q - X3) - F::mul_shared(Y, PPP);
         X = X3;
-        ZZ = ZZ * PP;
-        ZZZ = ZZZ * PPP;
+        ZZ = F::mul_shared(ZZ, PP);
+        ZZZ = F::mul_shared(ZZZ, PPP);
     }
 
     // in-place doubling (dbl-2008-s-1, a = 0); infinity stays infinity

@@ -212,13 +212,16 @@ struct mont_t {
     }
 #endif
 
-#if defined(__CUDA_ARCH__) && defined(SPPARK_B200_MUL_OUTLINE)
-    // one shared copy of the ladder per kernel: the unrolled product is ~450 instructions and a
-    // mixed add has ten of them, which overflows the instruction cache when everything is inlined
-    static __device__ __noinline__ mont_t mul_outlined(mont_t a, mont_t b) { return mul_inline(a, b); }
-    friend DEV mont_t operator*(const mont_t& a, const mont_t& b) { return mul_outlined(a, b); }
-#else
     friend HD mont_t operator*(const mont_t& a, const mont_t& b) { return mul_inline(a, b); }
+
+    // mul_shared: ONE copy of the ladder per kernel, called (not inlined) from the hot loop.  The
+    // unrolled product is ~450 instructions and a mixed add has ten of them; inlining all ten
+    // overflows the instruction cache (ncu: no_instruction was the top stall, profiles/).
+    // Only used from code that is itself inlined into the kernel, so the call depth is one.
+#if defined(__CUDA_ARCH__)
+    static __device__ __noinline__ mont_t mul_shared(mont_t a, mont_t b) { return mul_inline(a, b); }
+#else
+    static inline mont_t mul_shared(const mont_t& a, const mont_t& b) { return mul_inline(a, b); }
 #endif
 
     static HD mont_t mul_inline(const mont_t& a, const mont_t& b)
