@@ -7,6 +7,51 @@ namespace ntt {
 // lg_tile: log2(elements) of one CTA's shared-memory tile: 128 KiB of data for either field
 template<> struct FieldId<gl64> { static constexpr uint32_t id = 1, lg_tile = 14; };
 template<> struct FieldId<bb31> { static constexpr uint32_t id = 2, lg_tile = 14; };
+// ---- statically shaped twins of the passes the planner emits for the common sizes ----------
+// key = (lg_r, lg_w, in row-fast, out row-fast, in_rev, out_rev, tw_mode)
+template<class F, uint32_t R, uint32_t W, bool IRF, bool ORF, bool IREV, bool OREV, uint32_t TW>
+static bool try_static(const Pass& d, const Tables<F>& tb, const typename F::T* in, typename F::T* out,
+                       uint32_t ntiles, size_t smem, cudaStream_t stream)
+{
+    if (d.lg_r != R || d.lg_w != W || (d.in_lg_sa == 0) != IRF || (d.out_lg_sa == 0) != ORF ||
+        (d.in_rev != 0) != IREV || (d.out_rev != 0) != OREV || d.tw_mode != TW)
+        return false;
+    typedef KStat<R, W, IRF, ORF, IREV, OREV, TW> K;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(pass_kernel_static<F, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_done = true;
+    }
+    pass_kernel_static<F, K><<<ntiles, tile_threads(d), smem, stream>>>(d, tb, in, out);
+    return true;
+}
+
+// the seven (in-order, out-order, twiddle) combinations used by NN / NR / RN plans
+template<class F, uint32_t R, uint32_t W>
+static bool try_shapes(const Pass& d, const Tables<F>& tb, const typename F::T* in, typename F::T* out,
+                       uint32_t ntiles, size_t smem, cudaStream_t stream)
+{
+    return try_static<F, R, W, false, true, false, false, TW_STORE>(d, tb, in, out, ntiles, smem, stream)    // NN first
+        || try_static<F, R, W, false, false, false, false, TW_NONE>(d, tb, in, out, ntiles, smem, stream)    // NN last
+        || try_static<F, R, W, false, false, false, false, TW_STORE>(d, tb, in, out, ntiles, smem, stream)   // NN middle
+        || try_static<F, R, W, false, false, false, true, TW_STORE>(d, tb, in, out, ntiles, smem, stream)    // NR strided
+        || try_static<F, R, W, true, true, false, true, TW_NONE>(d, tb, in, out, ntiles, smem, stream)       // NR last
+        || try_static<F, R, W, true, true, true, false, TW_NONE>(d, tb, in, out, ntiles, smem, stream)       // RN first
+        || try_static<F, R, W, false, false, true, false, TW_LOAD>(d, tb, in, out, ntiles, smem, stream);    // RN strided
+}
+
+template<class F> bool launch_static(const Pass& d, const Tables<F>& tb, const typename F::T* in,
+                                     typename F::T* out, uint32_t ntiles, size_t smem, cudaStream_t stream)
+{
+    if (getenv("SPPARK_B200_NTT_GENERIC")) return false;
+    return try_shapes<F, 12, 2>(d, tb, in, out, ntiles, smem, stream)
+        || try_shapes<F, 11, 3>(d, tb, in, out, ntiles, smem, stream)
+        || try_shapes<F, 10, 4>(d, tb, in, out, ntiles, smem, stream);
+}
+
+template bool launch_static<gl64>(const Pass&, const Tables<gl64>&, const uint64_t*, uint64_t*, uint32_t, size_t, cudaStream_t);
+template bool launch_static<bb31>(const Pass&, const Tables<bb31>&, const uint32_t*, uint32_t*, uint32_t, size_t, cudaStream_t);
+
 template class NTT<gl64>;
 template class NTT<bb31>;
 }  // namespace ntt

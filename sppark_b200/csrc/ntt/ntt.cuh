@@ -16,17 +16,47 @@ pass_kernel(const Pass d, const Tables<F> tb, const typename F::T* in, typename 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename F::T* smem = reinterpret_cast<typename F::T*>(smem_raw);
     const uint32_t tid = threadIdx.x, nthreads = blockDim.x, t = blockIdx.x;
+    const KDyn k{d};
 
-    phase_twiddles<F>(d, tb, smem, tid, nthreads);
-    phase_load<F>(d, tb, in, smem, t, tid, nthreads);
+    phase_twiddles<F>(k, tb, smem, tid, nthreads);
+    phase_load<F>(k, d, tb, in, smem, t, tid, nthreads);
     __syncthreads();
     const uint32_t nsteps = step_count(d.lg_r);
     for (uint32_t s = 0; s < nsteps; s++) {
-        phase_step_dyn<F>(d, smem, s * LG_EPT, step_log_e(d.lg_r, s), tid);
+        phase_step_dyn<F>(k, smem, s * LG_EPT, step_log_e(d.lg_r, s), tid);
         __syncthreads();
     }
-    phase_store<F>(d, tb, out, smem, t, tid, nthreads);
+    phase_store<F>(k, d, tb, out, smem, t, tid, nthreads);
 }
+
+// the same pass with its shape fixed at compile time (see KStat in ntt_core.cuh)
+template<class F, class K>
+__global__ void __launch_bounds__(1024)
+pass_kernel_static(const Pass d, const Tables<F> tb, const typename F::T* in, typename F::T* out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typename F::T* smem = reinterpret_cast<typename F::T*>(smem_raw);
+    const uint32_t tid = threadIdx.x, t = blockIdx.x;
+    constexpr uint32_t R = K::lg_r();
+    constexpr uint32_t nthreads = (R >= LG_EPT ? (1u << (R - LG_EPT)) : 1u) << K::lg_w();
+    const K k(d);
+
+    phase_twiddles<F>(k, tb, smem, tid, nthreads);
+    phase_load<F>(k, d, tb, in, smem, t, tid, nthreads);
+    __syncthreads();
+#pragma unroll
+    for (uint32_t s = 0; s < step_count(R); s++) {
+        constexpr uint32_t full = R / LG_EPT;
+        if (s < full) phase_step<F, K, LG_EPT>(k, smem, s * LG_EPT, tid);
+        else phase_step_dyn<F>(k, smem, s * LG_EPT, R - full * LG_EPT, tid);
+        __syncthreads();
+    }
+    phase_store<F>(k, d, tb, out, smem, t, tid, nthreads);
+}
+
+// launcher table for the statically shaped passes; returns false if (d) has no static twin
+template<class F> bool launch_static(const Pass& d, const Tables<F>& tb, const typename F::T* in,
+                                     typename F::T* out, uint32_t ntiles, size_t smem, cudaStream_t stream);
 
 // ---- one-time table generation (role of NTTParameters, ntt/parameters.cuh:147-337) ----
 template<class F>
@@ -187,7 +217,8 @@ public:
             g_profile.mark("pass", stream);
             uint32_t ntiles = 1u << (lg_n - d.lg_r - d.lg_w);
             size_t smem = smem_elems(d) * sizeof(T);
-            pass_kernel<F><<<ntiles, tile_threads(d), smem, stream>>>(d, tb, buf[d.src], buf[d.dst]);
+            if (!launch_static<F>(d, tb, buf[d.src], buf[d.dst], ntiles, smem, stream))
+                pass_kernel<F><<<ntiles, tile_threads(d), smem, stream>>>(d, tb, buf[d.src], buf[d.dst]);
             COUNT_LAUNCH();
             CUDA_OK(cudaGetLastError());
         }

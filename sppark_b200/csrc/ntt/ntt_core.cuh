@@ -54,6 +54,33 @@ template<class F> struct Tables {
     typename F::T ninv;                  // 2^-n
 };
 
+// ---- compile-time / run-time views of the shape of a pass ------------------------------
+// The phase functions read the tile shape through a "knobs" object.  KDyn forwards to the
+// descriptor (any shape, slower index arithmetic); KStat<...> fixes the shape at compile time
+// so that every shift, mask, bit-reversal width and loop bound folds into an immediate.  The
+// hot shapes produced by the planner are instantiated statically in ntt.cu.
+struct KDyn {
+    const Pass& d;
+    HD uint32_t lg_r() const { return d.lg_r; }
+    HD uint32_t lg_w() const { return d.lg_w; }
+    HD bool in_row_fast() const { return d.in_lg_sa == 0; }
+    HD bool out_row_fast() const { return d.out_lg_sa == 0; }
+    HD bool in_rev() const { return d.in_rev != 0; }
+    HD bool out_rev() const { return d.out_rev != 0; }
+    HD uint32_t tw_mode() const { return d.tw_mode; }
+};
+template<uint32_t R, uint32_t W, bool IRF, bool ORF, bool IREV, bool OREV, uint32_t TW>
+struct KStat {
+    HD explicit KStat(const Pass&) {}
+    static HD constexpr uint32_t lg_r() { return R; }
+    static HD constexpr uint32_t lg_w() { return W; }
+    static HD constexpr bool in_row_fast() { return IRF; }
+    static HD constexpr bool out_row_fast() { return ORF; }
+    static HD constexpr bool in_rev() { return IREV; }
+    static HD constexpr bool out_rev() { return OREV; }
+    static HD constexpr uint32_t tw_mode() { return TW; }
+};
+
 HD uint32_t pad(uint32_t i) { return i + (i >> 4); }
 HD uint32_t col_stride(uint32_t lg_r) { return pad(1u << lg_r) + 1; }
 HD uint32_t tile_threads(const Pass& d)
@@ -83,31 +110,31 @@ HD uint32_t tw_column_value(const Pass& d, uint64_t pos0)
 }
 
 // ---- phase 0: per-CTA copy of the sub-NTT twiddles into shared memory -------------
-template<class F>
-HD void phase_twiddles(const Pass& d, const Tables<F>& tb, typename F::T* smem,
+template<class F, class K>
+HD void phase_twiddles(const K k, const Tables<F>& tb, typename F::T* smem,
                        uint32_t tid, uint32_t nthreads)
 {
-    typename F::T* tw = smem + (col_stride(d.lg_r) << d.lg_w);
-    for (uint32_t i = tid; i < (1u << d.lg_r); i += nthreads)
+    typename F::T* tw = smem + (col_stride(k.lg_r()) << k.lg_w());
+    for (uint32_t i = tid; i < (1u << k.lg_r()); i += nthreads)
         tw[i] = tb.dense[i];
 }
 
 // ---- phase 1: HBM -> shared memory -------------------------------------------------
-template<class F>
-HD void phase_load(const Pass& d, const Tables<F>& tb, const typename F::T* in,
+template<class F, class K>
+HD void phase_load(const K k, const Pass& d, const Tables<F>& tb, const typename F::T* in,
                    typename F::T* smem, uint32_t t, uint32_t tid, uint32_t nthreads)
 {
     typedef typename F::T T;
-    const uint32_t R = d.lg_r, n_el = (1u << R) << d.lg_w, cs = col_stride(R);
+    const uint32_t R = k.lg_r(), LW = k.lg_w(), n_el = (1u << R) << LW, cs = col_stride(R);
     const uint64_t base = tile_base(t, d.in_lg_tlo, d.in_tl, d.in_th);
-    const bool row_fast = d.in_lg_sa == 0;      // consecutive threads walk rows, else columns
+    const bool row_fast = k.in_row_fast();      // consecutive threads walk rows, else columns
     T v[EPT];
 #pragma unroll
     for (uint32_t l = 0; l < EPT; l++) {
         uint32_t e = l * nthreads + tid;
         if (e < n_el) {
-            uint32_t a = row_fast ? (e & ((1u << R) - 1)) : (e >> d.lg_w);
-            uint32_t c = row_fast ? (e >> R) : (e & ((1u << d.lg_w) - 1));
+            uint32_t a = row_fast ? (e & ((1u << R) - 1)) : (e >> LW);
+            uint32_t c = row_fast ? (e >> R) : (e & ((1u << LW) - 1));
             v[l] = in[base + ((uint64_t)a << d.in_lg_sa) + ((uint64_t)c << d.in_lg_sc)];
         }
     }
@@ -115,11 +142,11 @@ HD void phase_load(const Pass& d, const Tables<F>& tb, const typename F::T* in,
     for (uint32_t l = 0; l < EPT; l++) {
         uint32_t e = l * nthreads + tid;
         if (e < n_el) {
-            uint32_t a = row_fast ? (e & ((1u << R) - 1)) : (e >> d.lg_w);
-            uint32_t c = row_fast ? (e >> R) : (e & ((1u << d.lg_w) - 1));
+            uint32_t a = row_fast ? (e & ((1u << R) - 1)) : (e >> LW);
+            uint32_t c = row_fast ? (e >> R) : (e & ((1u << LW) - 1));
             T x = F::load(v[l]);
-            uint32_t nat = d.in_rev ? brev32(a, R) : a;          // natural row index
-            if (d.tw_mode == TW_LOAD) {
+            uint32_t nat = k.in_rev() ? brev32(a, R) : a;          // natural row index
+            if (k.tw_mode() == TW_LOAD) {
                 uint32_t colv = tw_column_value(d, base + ((uint64_t)c << d.in_lg_sc));
                 x = F::mul(x, twiddle<F>(tb, (nat * colv) << d.tw_lsh));
             }
@@ -131,16 +158,16 @@ HD void phase_load(const Pass& d, const Tables<F>& tb, const typename F::T* in,
 // ---- phase 2: LOG_E radix-2 DIT stages on 2^LOG_E registers -----------------------
 // Rows p0 + m*2^b, m < 2^LOG_E; stage t pairs m with m | (1<<t), half-size h = 2^(b+t),
 // twiddle dense[h + (m mod 2^t)*2^b + j].
-template<class F, uint32_t LOG_E>
-HD void phase_step(const Pass& d, typename F::T* smem, uint32_t b, uint32_t tid)
+template<class F, class K, uint32_t LOG_E>
+HD void phase_step(const K k, typename F::T* smem, uint32_t b, uint32_t tid)
 {
     typedef typename F::T T;
     constexpr uint32_t E = 1u << LOG_E;
-    const uint32_t R = d.lg_r, cs = col_stride(R);
+    const uint32_t R = k.lg_r(), cs = col_stride(R);
     const uint32_t lg_tpc = R >= LG_EPT ? R - LG_EPT : 0;       // threads per column
     const uint32_t c = tid >> lg_tpc, tau = tid & ((1u << lg_tpc) - 1);
     T* col = smem + c * cs;
-    const T* tw = smem + (cs << d.lg_w);
+    const T* tw = smem + (cs << k.lg_w());
     const uint32_t groups = 1u << (R - LOG_E);
 
     for (uint32_t g = tau; g < groups; g += (1u << lg_tpc)) {
@@ -174,14 +201,14 @@ HD void phase_step(const Pass& d, typename F::T* smem, uint32_t b, uint32_t tid)
     }
 }
 
-template<class F>
-HD void phase_step_dyn(const Pass& d, typename F::T* smem, uint32_t b, uint32_t log_e, uint32_t tid)
+template<class F, class K>
+HD void phase_step_dyn(const K k, typename F::T* smem, uint32_t b, uint32_t log_e, uint32_t tid)
 {
     switch (log_e) {
-    case 1: phase_step<F, 1>(d, smem, b, tid); break;
-    case 2: phase_step<F, 2>(d, smem, b, tid); break;
-    case 3: phase_step<F, 3>(d, smem, b, tid); break;
-    default: phase_step<F, 4>(d, smem, b, tid); break;
+    case 1: phase_step<F, K, 1>(k, smem, b, tid); break;
+    case 2: phase_step<F, K, 2>(k, smem, b, tid); break;
+    case 3: phase_step<F, K, 3>(k, smem, b, tid); break;
+    default: phase_step<F, K, 4>(k, smem, b, tid); break;
     }
 }
 
@@ -194,24 +221,24 @@ HD uint32_t step_log_e(uint32_t R, uint32_t s)
 }
 
 // ---- phase 3: shared memory -> HBM -------------------------------------------------
-template<class F>
-HD void phase_store(const Pass& d, const Tables<F>& tb, typename F::T* out,
+template<class F, class K>
+HD void phase_store(const K k, const Pass& d, const Tables<F>& tb, typename F::T* out,
                     const typename F::T* smem, uint32_t t, uint32_t tid, uint32_t nthreads)
 {
     typedef typename F::T T;
-    const uint32_t R = d.lg_r, n_el = (1u << R) << d.lg_w, cs = col_stride(R);
+    const uint32_t R = k.lg_r(), LW = k.lg_w(), n_el = (1u << R) << LW, cs = col_stride(R);
     const uint64_t ibase = tile_base(t, d.in_lg_tlo, d.in_tl, d.in_th);
     const uint64_t obase = tile_base(t, d.out_lg_tlo, d.out_tl, d.out_th);
-    const bool row_fast = d.out_lg_sa == 0;
+    const bool row_fast = k.out_row_fast();
 #pragma unroll
     for (uint32_t l = 0; l < EPT; l++) {
         uint32_t e = l * nthreads + tid;
         if (e < n_el) {
-            uint32_t v = row_fast ? (e & ((1u << R) - 1)) : (e >> d.lg_w);
-            uint32_t c = row_fast ? (e >> R) : (e & ((1u << d.lg_w) - 1));
-            uint32_t ka = d.out_rev ? brev32(v, R) : v;          // natural output row
+            uint32_t v = row_fast ? (e & ((1u << R) - 1)) : (e >> LW);
+            uint32_t c = row_fast ? (e >> R) : (e & ((1u << LW) - 1));
+            uint32_t ka = k.out_rev() ? brev32(v, R) : v;          // natural output row
             T x = smem[c * cs + pad(ka)];
-            if (d.tw_mode == TW_STORE) {
+            if (k.tw_mode() == TW_STORE) {
                 uint32_t colv = tw_column_value(d, ibase + ((uint64_t)c << d.in_lg_sc));
                 x = F::mul(x, twiddle<F>(tb, (ka * colv) << d.tw_lsh));
             }

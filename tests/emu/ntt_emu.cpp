@@ -64,12 +64,13 @@ static int emu_run(typename F::T* data, uint32_t lg_n, int order, int inverse, u
         // out-of-place passes read src while other tiles write dst: they never alias.
         // in-place passes touch only their own tile.  Either way tile order is free.
         for (uint32_t t = 0; t < ntiles; t++) {
-            for (uint32_t tid = 0; tid < nthreads; tid++) phase_twiddles<F>(d, tb.view, smem.data(), tid, nthreads);
-            for (uint32_t tid = 0; tid < nthreads; tid++) phase_load<F>(d, tb.view, buf[d.src], smem.data(), t, tid, nthreads);
+            const KDyn k{d};
+            for (uint32_t tid = 0; tid < nthreads; tid++) phase_twiddles<F>(k, tb.view, smem.data(), tid, nthreads);
+            for (uint32_t tid = 0; tid < nthreads; tid++) phase_load<F>(k, d, tb.view, buf[d.src], smem.data(), t, tid, nthreads);
             for (uint32_t s = 0; s < step_count(d.lg_r); s++)
                 for (uint32_t tid = 0; tid < nthreads; tid++)
-                    phase_step_dyn<F>(d, smem.data(), s * LG_EPT, step_log_e(d.lg_r, s), tid);
-            for (uint32_t tid = 0; tid < nthreads; tid++) phase_store<F>(d, tb.view, buf[d.dst], smem.data(), t, tid, nthreads);
+                    phase_step_dyn<F>(k, smem.data(), s * LG_EPT, step_log_e(d.lg_r, s), tid);
+            for (uint32_t tid = 0; tid < nthreads; tid++) phase_store<F>(k, d, tb.view, buf[d.dst], smem.data(), t, tid, nthreads);
         }
     }
     return (int)plan.passes.size();
