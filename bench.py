@@ -219,14 +219,14 @@ def main():
         pts_host.reshape(n // m, m, 12)[:] = base
     torch.cuda.synchronize()
 
+    from sppark_b200 import parallel
+
     def msm_step():
-        part = msm.msm_dev(msm.BLS12_381_G1, d_points, d_scalars)      # synchronises its stream
-        if world == 1:
-            return part
-        t = torch.from_numpy(part.view(np.int64)).cuda()
-        gathered = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(gathered, t)                                   # 144 B per rank over NVLink
-        return msm.combine(msm.BLS12_381_G1, torch.stack(gathered).cpu().numpy().view(np.uint64))
+        # local chunk -> one Jacobian point; all-gather of 144 B per rank (NCCL over NVLink);
+        # the partials are added on the GPU by the library (sppark_b200_msm_combine)
+        return parallel.msm_sharded(lambda: msm.msm_dev(msm.BLS12_381_G1, d_points, d_scalars),
+                                    lambda parts: msm.combine(msm.BLS12_381_G1, parts) if world > 1 else parts[0],
+                                    18, device="cuda")
 
     launches0 = _lib.launch_count()
     for _ in range(args.warmup):

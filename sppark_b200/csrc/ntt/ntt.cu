@@ -22,7 +22,12 @@ static bool try_static(const Pass& d, const Tables<F>& tb, const typename F::T* 
         cudaFuncSetAttribute(pass_kernel_static<F, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done = true;
     }
-    pass_kernel_static<F, K><<<ntiles, tile_threads(d), smem, stream>>>(d, tb, in, out);
+    // one CTA per SM (a tile fills the shared memory), each walking ntiles / grid tiles
+    static int sms = 0;
+    if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    uint32_t per_sm = smem <= 48 * 1024 ? 4 : smem <= 100 * 1024 ? 2 : 1;
+    uint32_t grid = ntiles < (uint32_t)sms * per_sm ? ntiles : (uint32_t)sms * per_sm;
+    pass_kernel_static<F, K><<<grid, tile_threads(d), smem, stream>>>(d, tb, in, out, ntiles);
     return true;
 }
 
@@ -46,7 +51,15 @@ template<class F> bool launch_static(const Pass& d, const Tables<F>& tb, const t
     if (getenv("SPPARK_B200_NTT_GENERIC")) return false;
     return try_shapes<F, 12, 2>(d, tb, in, out, ntiles, smem, stream)
         || try_shapes<F, 11, 3>(d, tb, in, out, ntiles, smem, stream)
-        || try_shapes<F, 10, 4>(d, tb, in, out, ntiles, smem, stream);
+        || try_shapes<F, 10, 4>(d, tb, in, out, ntiles, smem, stream)
+        || try_shapes<F, 12, 1>(d, tb, in, out, ntiles, smem, stream)
+        || try_shapes<F, 11, 2>(d, tb, in, out, ntiles, smem, stream)
+        || try_shapes<F, 10, 3>(d, tb, in, out, ntiles, smem, stream)
+        || try_shapes<F, 10, 2>(d, tb, in, out, ntiles, smem, stream)
+        || try_shapes<F, 11, 1>(d, tb, in, out, ntiles, smem, stream)
+        || try_shapes<F, 11, 0>(d, tb, in, out, ntiles, smem, stream)
+        || try_shapes<F, 10, 1>(d, tb, in, out, ntiles, smem, stream)
+        || try_shapes<F, 10, 0>(d, tb, in, out, ntiles, smem, stream);
 }
 
 template bool launch_static<gl64>(const Pass&, const Tables<gl64>&, const uint64_t*, uint64_t*, uint32_t, size_t, cudaStream_t);

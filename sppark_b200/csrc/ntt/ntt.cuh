@@ -32,26 +32,31 @@ pass_kernel(const Pass d, const Tables<F> tb, const typename F::T* in, typename 
 // the same pass with its shape fixed at compile time (see KStat in ntt_core.cuh)
 template<class F, class K>
 __global__ void __launch_bounds__(1024)
-pass_kernel_static(const Pass d, const Tables<F> tb, const typename F::T* in, typename F::T* out)
+pass_kernel_static(const Pass d, const Tables<F> tb, const typename F::T* in, typename F::T* out, uint32_t ntiles)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename F::T* smem = reinterpret_cast<typename F::T*>(smem_raw);
-    const uint32_t tid = threadIdx.x, t = blockIdx.x;
+    const uint32_t tid = threadIdx.x;
     constexpr uint32_t R = K::lg_r();
     constexpr uint32_t nthreads = (R >= LG_EPT ? (1u << (R - LG_EPT)) : 1u) << K::lg_w();
     const K k(d);
 
+    // persistent CTAs: the sub-NTT twiddles are staged into shared memory once per CTA, not
+    // once per tile (they are a quarter of a tile's bytes)
     phase_twiddles<F>(k, tb, smem, tid, nthreads);
-    phase_load<F>(k, d, tb, in, smem, t, tid, nthreads);
-    __syncthreads();
+    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        phase_load<F>(k, d, tb, in, smem, t, tid, nthreads);
+        __syncthreads();
 #pragma unroll
-    for (uint32_t s = 0; s < step_count(R); s++) {
-        constexpr uint32_t full = R / LG_EPT;
-        if (s < full) phase_step<F, K, LG_EPT>(k, smem, s * LG_EPT, tid);
-        else phase_step_dyn<F>(k, smem, s * LG_EPT, R - full * LG_EPT, tid);
+        for (uint32_t s = 0; s < step_count(R); s++) {
+            constexpr uint32_t full = R / LG_EPT;
+            if (s < full) phase_step<F, K, LG_EPT>(k, smem, s * LG_EPT, tid);
+            else phase_step_dyn<F>(k, smem, s * LG_EPT, R - full * LG_EPT, tid);
+            __syncthreads();
+        }
+        phase_store<F>(k, d, tb, out, smem, t, tid, nthreads);
         __syncthreads();
     }
-    phase_store<F>(k, d, tb, out, smem, t, tid, nthreads);
 }
 
 // launcher table for the statically shaped passes; returns false if (d) has no static twin
@@ -199,7 +204,12 @@ public:
             coset_scale(gpu, d_inout, lg_n, in_rev, false, stream);
 
         const Tables<F>& tb = tables(gpu, lg_n, inverse, stream);
-        Plan plan = make_plan(lg_n, (int)order, inverse, FieldId<F>::lg_tile);
+        // 2^14-element tiles fill one SM's shared memory; below 2^22 elements shrink the tile so
+        // that there are still >= 256 of them for the 148 SMs
+        uint32_t lg_tile = FieldId<F>::lg_tile;
+        if (lg_n < lg_tile + 8) lg_tile = lg_n > 18 ? lg_n - 8 : 10;
+        if (const char* env = getenv("SPPARK_B200_NTT_LG_TILE")) lg_tile = (uint32_t)atoi(env);
+        Plan plan = make_plan(lg_n, (int)order, inverse, lg_tile);
 
         T* scratch = nullptr;
         if (plan.needs_scratch)

@@ -3,7 +3,7 @@
 // An N = 2^n point NTT is executed as P <= 3 "passes".  A pass is one kernel launch in
 // which every CTA owns a tile of W independent columns x 2^R rows, pulls it from HBM into
 // shared memory, runs a complete 2^R-point sub-NTT on each column there (radix-2 DIT
-// butterflies, 16 elements per thread in registers between shared-memory exchanges),
+// butterflies, 16 elements per thread in registers between shared-memory exchanges, XOR-swizzled rows),
 // applies the inter-pass twiddle w_N^(row*col) and writes the tile back.  Every element
 // is therefore read and written exactly once per pass: algorithmic traffic per pass is
 // 2*N*sizeof(T) and a 2^24 transform needs two passes (the reference needs three
@@ -81,8 +81,17 @@ struct KStat {
     static HD constexpr uint32_t tw_mode() { return TW; }
 };
 
-HD uint32_t pad(uint32_t i) { return i + (i >> 4); }
-HD uint32_t col_stride(uint32_t lg_r) { return pad(1u << lg_r) + 1; }
+// Shared-memory placement of row `i` of column `c`: an XOR swizzle of the low four index bits
+// with bits 4-7, bits 8-11 and the column, so that a half-warp (sixteen 8-byte words = all 32
+// banks) is conflict-free for every access pattern of a pass: sixteen consecutive rows
+// (register steps with stride >= 16, natural-order tile I/O), sixteen rows 16 apart (the
+// stride-1 register step), sixteen rows 2^(R-4) apart (bit-reversed tile I/O), and rows x
+// columns mixes (strided tile I/O).  No padding: a column is exactly 2^R words.
+HD uint32_t swz(uint32_t i, uint32_t c, uint32_t lg_r)
+{
+    return i ^ (((i >> 4) ^ (i >> 8) ^ c) & (lg_r >= 4 ? 15u : (1u << lg_r) - 1));
+}
+HD uint32_t col_stride(uint32_t lg_r) { return 1u << lg_r; }
 HD uint32_t tile_threads(const Pass& d)
 {
     return (d.lg_r >= LG_EPT ? (1u << (d.lg_r - LG_EPT)) : 1u) << d.lg_w;
@@ -150,7 +159,7 @@ HD void phase_load(const K k, const Pass& d, const Tables<F>& tb, const typename
                 uint32_t colv = tw_column_value(d, base + ((uint64_t)c << d.in_lg_sc));
                 x = F::mul(x, twiddle<F>(tb, (nat * colv) << d.tw_lsh));
             }
-            smem[c * cs + pad(brev32(nat, R))] = x;               // DIT wants bit-reversed rows
+            smem[c * cs + swz(brev32(nat, R), c, R)] = x;            // DIT wants bit-reversed rows
         }
     }
 }
@@ -176,7 +185,7 @@ HD void phase_step(const K k, typename F::T* smem, uint32_t b, uint32_t tid)
         T x[E];
 #pragma unroll
         for (uint32_t m = 0; m < E; m++)
-            x[m] = col[pad(p0 + (m << b))];
+            x[m] = col[swz(p0 + (m << b), c, R)];
 #pragma unroll
         for (uint32_t t = 0; t < LOG_E; t++) {
             const uint32_t h = 1u << (b + t);
@@ -197,7 +206,7 @@ HD void phase_step(const K k, typename F::T* smem, uint32_t b, uint32_t tid)
         }
 #pragma unroll
         for (uint32_t m = 0; m < E; m++)
-            col[pad(p0 + (m << b))] = x[m];
+            col[swz(p0 + (m << b), c, R)] = x[m];
     }
 }
 
@@ -237,7 +246,7 @@ HD void phase_store(const K k, const Pass& d, const Tables<F>& tb, typename F::T
             uint32_t v = row_fast ? (e & ((1u << R) - 1)) : (e >> LW);
             uint32_t c = row_fast ? (e >> R) : (e & ((1u << LW) - 1));
             uint32_t ka = k.out_rev() ? brev32(v, R) : v;          // natural output row
-            T x = smem[c * cs + pad(ka)];
+            T x = smem[c * cs + swz(ka, c, R)];
             if (k.tw_mode() == TW_STORE) {
                 uint32_t colv = tw_column_value(d, ibase + ((uint64_t)c << d.in_lg_sc));
                 x = F::mul(x, twiddle<F>(tb, (ka * colv) << d.tw_lsh));

@@ -39,17 +39,17 @@ def main():
         rng = np.random.default_rng(lg)
         host = rng.integers(0, GL_P, size=n, dtype=np.uint64)
         bytes_alg = 2 * n * 8
-        for split in (None, "8,8,8" if lg == 24 else "10,10", "12,12" if lg == 24 else "7,7,6"):
+        for split in (None, "13", "12"):
             if split:
-                os.environ["SPPARK_B200_NTT_SPLIT"] = split
+                os.environ["SPPARK_B200_NTT_LG_TILE"] = split
             else:
-                os.environ.pop("SPPARK_B200_NTT_SPLIT", None)
+                os.environ.pop("SPPARK_B200_NTT_LG_TILE", None)
             for order, name in ((ntt.NN, "NN"), (ntt.NR, "NR"), (ntt.RN, "RN")):
                 d = torch.from_numpy(host.view(np.int64)).cuda()
                 med, best = time_fn(lambda: ntt.ntt_dev(d, order), cur)
                 print(f"ours  gl64 2^{lg} {name} split={split}: median {med*1e3:.1f} us  min {best*1e3:.1f} us  "
                       f"-> {bytes_alg/ (med*1e-3) / 1e9:.0f} GB/s algorithmic")
-        os.environ.pop("SPPARK_B200_NTT_SPLIT", None)
+        os.environ.pop("SPPARK_B200_NTT_LG_TILE", None)
         # reference kernels, same box, data resident
         p = os.path.join(ROOT, "oracle", "_ref", "libref_ntt_gl64_gpu.so")
         if os.path.exists(p):
