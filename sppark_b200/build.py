@@ -12,7 +12,10 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("SPPARK_B200_LIB") or os.path.join(HERE, "libsppark_b200.so")   # override: experiments only
 
 SOURCES = ["api.cu", "util/gpu.cu", "ntt/ntt.cu", "msm/msm.cu", "msm/msm_bls12_381.cu", "msm/msm_pasta.cu"]
-NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+# the wide-product variants of the hot-loop multiplications (dedicated squaring, single-reduction
+# a*b - c*d, Karatsuba; ff/mont.cuh) measured SLOWER than the fused ladder on B200 (round 1:
+# accumulate 2^24: fused 111 ms, +msub 115, +sqr 126, +both 130), so they are compiled out
+NVCC_FLAGS = ["-std=c++17", "-O3", "-DSPPARK_B200_NO_WIDE_SQR", "-DSPPARK_B200_NO_WIDE_MSUB", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--threads", "4"]
 
 

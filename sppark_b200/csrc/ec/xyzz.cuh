@@ -73,11 +73,11 @@ template<class F> struct xyzz_t {
             else set_inf();
             return;
         }
-        F PP = F::mul_shared(P, P);
+        F PP = F::sqr_shared(P);
         F PPP = F::mul_shared(P, PP);
         F Q = F::mul_shared(X, PP);
-        F X3 = F::mul_shared(R, R) - PPP - Q - Q;
-        Y = F::mul_shared(R, Q - X3) - F::mul_shared(Y, PPP);
+        F X3 = F::sqr_shared(R) - PPP - Q - Q;
+        Y = F::msub_shared(R, Q - X3, Y, PPP);      // R*(Q-X3) - Y1*PPP, one reduction
         X = X3;
         ZZ = F::mul_shared(ZZ, PP);
         ZZZ = F::mul_shared(ZZZ, PPP);

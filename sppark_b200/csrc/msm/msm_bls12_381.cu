@@ -20,7 +20,7 @@ extern "C" RustError mult_pippenger_inf(void* out, const void* points, size_t np
 {   return msm_host_bls12_381(out, points, npoints, scalars, ffi_affine_sz, true);   }
 
 // ---- device self-test hook: element-wise field ops through the PTX arithmetic -------------
-// op 0 mul, 1 add, 2 sub, 3 sqr.  Host arrays of n 48-byte elements.  Used by the GPU KAT tests.
+// op 0 mul, 1 add, 2 sub, 3 sqr, 4 mul_shared, 5 sqr_shared, 6 msub_shared(x,y,y,x^2).  Host arrays of n 48-byte elements.  Used by the GPU KAT tests.
 template<class F>
 __global__ void selftest_kernel(int op, size_t n, uint32_t* r, const uint32_t* a, const uint32_t* b)
 {
@@ -28,7 +28,15 @@ __global__ void selftest_kernel(int op, size_t n, uint32_t* r, const uint32_t* a
     if (i >= n) return;
     F x, y, z;
     for (int k = 0; k < F::N; k++) { x.l[k] = a[i * F::N + k]; y.l[k] = b[i * F::N + k]; }
-    z = op == 0 ? x * y : op == 1 ? x + y : op == 2 ? x - y : x.sqr();
+    switch (op) {
+    case 0: z = x * y; break;
+    case 1: z = x + y; break;
+    case 2: z = x - y; break;
+    case 3: z = x.sqr(); break;
+    case 4: z = F::mul_shared(x, y); break;            // Karatsuba wide product + separate reduction
+    case 5: z = F::sqr_shared(x); break;               // dedicated squaring
+    default: z = F::msub_shared(x, y, y, x.sqr()); break;   // x*y - y*x^2, one reduction
+    }
     for (int k = 0; k < F::N; k++) r[i * F::N + k] = z.l[k];
 }
 

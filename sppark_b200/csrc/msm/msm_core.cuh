@@ -201,6 +201,8 @@ HD void accumulate_body(const Config& cfg, const uint32_t* points, const uint32_
         if (!live) return;
 #endif
         if (live) acc.madd(load_point<F>(points, run[k++]));
+        // (an explicit prefetch.global.L2 of the next point was measured: no gain at 2^24,
+        //  6 % slower at 2^26 -- the 12 resident warps per SM already cover the gather latency)
     }
 }
 

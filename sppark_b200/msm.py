@@ -97,7 +97,7 @@ def selftest_field(field, op, a, b):
     a = np.ascontiguousarray(a, dtype=np.uint64)
     b = np.ascontiguousarray(b, dtype=np.uint64)
     r = np.zeros_like(a)
-    err = _lib.lib().sppark_b200_selftest_field(field, {"mul": 0, "add": 1, "sub": 2, "sqr": 3}[op],
+    err = _lib.lib().sppark_b200_selftest_field(field, {"mul": 0, "add": 1, "sub": 2, "sqr": 3, "mul_shared": 4, "sqr_shared": 5, "msub_shared": 6}[op],
                                                 a.shape[0], r.ctypes.data, a.ctypes.data, b.ctypes.data)
     _lib.check(err)
     return r

@@ -32,7 +32,9 @@ def test_field_kat_ptx(oracle, name, fid, nl):
     b = np.array([_limbs(v, nl) for v in reversed(vals)], dtype=np.uint64)
     Rinv = pow(R, -1, p)
     for op, fn in (("mul", lambda x, y: x * y * Rinv % p), ("add", lambda x, y: (x + y) % p),
-                   ("sub", lambda x, y: (x - y) % p), ("sqr", lambda x, y: x * x * Rinv % p)):
+                   ("sub", lambda x, y: (x - y) % p), ("sqr", lambda x, y: x * x * Rinv % p),
+                   ("mul_shared", lambda x, y: x * y * Rinv % p), ("sqr_shared", lambda x, y: x * x * Rinv % p),
+                   ("msub_shared", lambda x, y: (x * y - y * (x * x * Rinv % p)) * Rinv % p)):
         r = msm.selftest_field(fid, op, a, b)
         for i in range(len(vals)):
             assert _int(r[i]) == fn(vals[i], vals[len(vals) - 1 - i]), (name, op, i)
@@ -197,3 +199,25 @@ def test_host_pipeline_slices(oracle, monkeypatch, nslices):
     want = oracle.msm("bls12_381", clean, sc, "pippenger", ncpus=8)
     assert _same_point(oracle, "bls12_381", msm.multi_scalar_mult_arkworks(pts, sc), want)
     assert _same_point(oracle, "bls12_381", msm.multi_scalar_mult(clean, sc), want)
+
+
+def test_pallas_msm_2pow21_folded(oracle):
+    """BASELINE config 4 shape (Pallas, 2^21 points per GPU): folded check against the oracle."""
+    from sppark_b200 import msm
+    n, m = 1 << 21, 1 << 9
+    r = oracle.ff_consts("vesta_fp")["p"]
+    base = oracle.gen_points("pallas", m)
+    pts = np.tile(base, (n // m, 1))
+    rng = np.random.default_rng(4)
+    sc = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
+    sc[:, 3] >>= np.uint64(3)                         # < 2^253 < r
+    got = msm.msm(1, pts, sc)
+    ints = [0] * m
+    scl = sc.reshape(n // m, m, 4)
+    for limb in range(4):
+        col = scl[:, :, limb].astype(object).sum(axis=0)
+        for j in range(m):
+            ints[j] += int(col[j]) << (64 * limb)
+    folded = np.array([_limbs(v % r, 4) for v in ints], dtype=np.uint64)
+    want = oracle.msm("pallas", base, folded, "pippenger", ncpus=8)
+    assert _same_point(oracle, "pallas", got, want)

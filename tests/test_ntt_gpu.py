@@ -136,3 +136,27 @@ def test_bb_extension_order(oracle, field):
             y = x.copy()
             (ntt.iNTT if inverse else ntt.NTT)(0, y, ntt.BB)
             assert np.array_equal(y, ofn(x, oracle.BB, inverse, nthreads=8))
+
+
+def test_babybear_2pow27_field_maximum():
+    """BASELINE config 5 asks for a 2^28 BabyBear NTT; p - 1 = 15 * 2^27, so 2^27 is the largest
+    domain the field (and the reference: MAX_LG_DOMAIN_SIZE 27, ntt/parameters.cuh:14-15) has.
+    Full-size checks without the oracle: round trip through NR/RN, linearity, delta -> ones."""
+    from sppark_b200 import ntt
+    lg = 27
+    n = 1 << lg
+    a = _rand("bb31", n, 3)
+    v = a.copy()
+    ntt.NTT(0, v, ntt.NR)
+    ntt.iNTT(0, v, ntt.RN)
+    assert np.array_equal(v, a)
+    d = np.zeros(n, dtype=np.uint32)
+    d[0] = 0x0ffffffe                                   # Montgomery one
+    ntt.NTT(0, d, ntt.NN)
+    assert (d == 0x0ffffffe).all()
+    err = None
+    from sppark_b200 import _lib
+    e = _lib.lib().sppark_b200_ntt(1, 0, a.ctypes.data, 28, 0, 0, 0)     # 2^28 does not exist
+    assert e.code != 0
+    if e.message:
+        _lib.lib().drop_error_message(e.message)
