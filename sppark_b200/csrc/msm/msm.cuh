@@ -6,7 +6,13 @@
 
 namespace msm {
 
-constexpr uint32_t ACC_THREADS = 128;       // accumulate CTA size
+#ifndef SPPARK_B200_ACC_THREADS
+# define SPPARK_B200_ACC_THREADS 128
+#endif
+#ifndef SPPARK_B200_ACC_MIN_BLOCKS
+# define SPPARK_B200_ACC_MIN_BLOCKS 3
+#endif
+constexpr uint32_t ACC_THREADS = SPPARK_B200_ACC_THREADS;       // accumulate CTA size
 constexpr uint32_t HEAVY_THREADS = 128;
 
 static __global__ void count_kernel(const Config cfg, const uint32_t* scalars, uint32_t* counts)
@@ -64,7 +70,7 @@ static __global__ void scatter_kernel(const Config cfg, const uint32_t* scalars,
 }
 
 template<class F>
-__global__ void __launch_bounds__(ACC_THREADS, 3)
+__global__ void __launch_bounds__(ACC_THREADS, SPPARK_B200_ACC_MIN_BLOCKS)
 accumulate_kernel(const Config cfg, const uint32_t* points, const uint32_t* sorted,
                   const uint32_t* offsets, const uint32_t* counts, uint32_t* buckets,
                   uint32_t* task_counter)

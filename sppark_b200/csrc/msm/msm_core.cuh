@@ -176,6 +176,7 @@ HD void accumulate_body(const Config& cfg, const uint32_t* points, const uint32_
             for (;;) {
                 t = atomic_inc(task_counter);
                 if (t >= total) { live = false; break; }
+                t = total - 1 - t;          // top window first: its few, long buckets must not be the tail
                 cnt = counts[t];
                 if (cnt == 0) {
                     if (!cfg.merge) {
@@ -289,7 +290,7 @@ inline Config make_config(size_t npoints)
     cfg.nwins = (256 + cfg.wbits - 1) / cfg.wbits;
     cfg.lg_nb = cfg.wbits - 1;
     cfg.npoints = (uint32_t)npoints;
-    cfg.heavy = 4096;
+    cfg.heavy = 16384;
     cfg.merge = 0;
     if (const char* env = getenv("SPPARK_B200_MSM_HEAVY")) cfg.heavy = (uint32_t)atoi(env);
     return cfg;
