@@ -79,7 +79,11 @@ void drop_error_message(char *msg);
 
 /* ================================ extended surface ================================ */
 
-enum { SPPARK_FIELD_GL64 = 0, SPPARK_FIELD_BB31 = 1 };
+enum { SPPARK_FIELD_GL64 = 0, SPPARK_FIELD_BB31 = 1,
+       /* 256-bit Montgomery scalar fields, 8 x uint32 limbs per element (the reference's "wide"
+        * NTT kernels, ntt/kernels/{ct,gs}_mixed_radix_wide.cu): fr of FEATURE_BLS12_381,
+        * FEATURE_PALLAS (= Vesta's base field) and FEATURE_VESTA (= Pallas' base field) */
+       SPPARK_FIELD_BLS12_381_FR = 2, SPPARK_FIELD_PALLAS_FR = 3, SPPARK_FIELD_VESTA_FR = 4 };
 enum { SPPARK_CURVE_BLS12_381_G1 = 0, SPPARK_CURVE_PALLAS = 1, SPPARK_CURVE_VESTA = 2 };
 
 /* compute_ntt for any single-word field (the reference builds one .so per FEATURE_*) */

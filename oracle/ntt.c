@@ -228,3 +228,147 @@ NTT_IMPL(oracle_ntt_gl64, uint64_t, gl_add, gl_sub, gl_mul, gl_pow, oracle_gl64_
          GL_P - 2, 32, GL_REDUCE)
 NTT_IMPL(oracle_ntt_bb31, uint32_t, bb_add, bb_sub, bb_mul, bb_pow, oracle_bb31_root, 3,
          BB_P - 2, 27, BB_REDUCE)
+
+/* ---- 256-bit Montgomery fields (BLS12-381 fr, Pallas/Vesta base fields) -------------------
+ * Same definition as above over ff.h arithmetic; memory words are Montgomery residues as in the
+ * reference's fr_t.  group_gen = 7 (BLS12-381 fr) / 5 (Pasta), S = 32, w_(2^32) = gen^((p-1)/2^32)
+ * -- ntt/parameters/bls12_381.h:11-16, pallas.h:11-16, vesta.h:11-16 (tables checked by
+ * tests/test_params_pin.py). */
+#include "ff.h"
+
+static const ff_ctx *ntt_field(int id, uint64_t *gen)
+{
+    switch (id) {
+    case 1: *gen = 7; return ff_bls12_381_fr();
+    case 2: *gen = 5; return ff_pallas_fp();
+    default: *gen = 5; return ff_vesta_fp();
+    }
+}
+
+static void ffx_pow(const ff_ctx *c, ff_t *r, const ff_t *b, const uint64_t *e, int nlimbs)
+{
+    ff_t acc, base = *b;
+    ff_set_one(c, &acc);
+    for (int i = nlimbs * 64; i--;) {
+        ff_sqr(c, &acc, &acc);
+        if ((e[i / 64] >> (i % 64)) & 1)
+            ff_mul(c, &acc, &acc, &base);
+    }
+    *r = acc;
+}
+
+static void ffx_small(const ff_ctx *c, ff_t *r, uint64_t v)
+{
+    ff_t t;
+    ff_set_zero(&t);
+    t.l[0] = v;
+    ff_to_mont(c, r, &t);
+}
+
+static void ffx_root(const ff_ctx *c, uint64_t gen, unsigned lg, int inverse, ff_t *w)
+{
+    uint64_t e[FF_MAX_LIMBS] = {0};              /* (p - 1) >> 32 */
+    for (int i = 0; i < c->n; i++) {
+        uint64_t lo = c->p[i] >> 32, hi = i + 1 < c->n ? c->p[i + 1] << 32 : 0;
+        e[i] = lo | hi;
+    }
+    ff_t g;
+    ffx_small(c, &g, gen);
+    ffx_pow(c, w, &g, e, c->n);
+    for (unsigned i = 32; i > lg; i--)
+        ff_sqr(c, w, w);
+    if (inverse)
+        ff_inv(c, w, w);
+}
+
+int oracle_ntt_ff(int field_id, uint64_t *data, unsigned lg, int order, int direction, int type, int algo)
+{
+    if (lg == 0)
+        return 0;
+    if (lg > 26)
+        return -1;
+    uint64_t gen;
+    const ff_ctx *c = ntt_field(field_id, &gen);
+    const int nl = c->n;
+    size_t n = (size_t)1 << lg;
+    ff_t *a = malloc(n * sizeof(ff_t)), *tmp = malloc(n * sizeof(ff_t));
+    for (size_t i = 0; i < n; i++) {
+        ff_set_zero(&a[i]);
+        memcpy(a[i].l, data + i * nl, 8 * nl);
+    }
+    int in_rev = order == ORACLE_RN || order == ORACLE_BB;
+    int out_rev = order == ORACLE_NR || order == ORACLE_BB;
+    int quirk = order == ORACLE_RR;
+    if (in_rev) {
+        for (size_t i = 0; i < n; i++) tmp[bitrev(i, lg)] = a[i];
+        memcpy(a, tmp, n * sizeof(ff_t));
+    }
+    ff_t g, pw;
+    if (!direction && type) {
+        ffx_small(c, &g, gen);
+        ff_set_one(c, &pw);
+        for (size_t i = 0; i < n; i++) {
+            size_t k = quirk ? bitrev(i, lg) : i;
+            ff_mul(c, &a[k], &a[k], &pw);
+            ff_mul(c, &pw, &pw, &g);
+        }
+    }
+    ff_t w;
+    ffx_root(c, gen, lg, direction, &w);
+    ff_t *pwr = malloc(n * sizeof(ff_t));
+    ff_set_one(c, &pwr[0]);
+    for (size_t i = 1; i < n; i++) ff_mul(c, &pwr[i], &pwr[i - 1], &w);
+    if (algo == 1) {                              /* definition */
+        for (size_t k = 0; k < n; k++) {
+            ff_t acc, t;
+            ff_set_zero(&acc);
+            for (size_t j = 0; j < n; j++) {
+                ff_mul(c, &t, &a[j], &pwr[(j * k) & (n - 1)]);
+                ff_add(c, &acc, &acc, &t);
+            }
+            tmp[k] = acc;
+        }
+        memcpy(a, tmp, n * sizeof(ff_t));
+    } else {                                      /* radix-2 DIT */
+        for (size_t i = 0; i < n; i++) tmp[bitrev(i, lg)] = a[i];
+        memcpy(a, tmp, n * sizeof(ff_t));
+        for (size_t half = 1; half < n; half <<= 1) {
+            size_t step = n / (2 * half);
+            for (size_t blk = 0; blk < n; blk += 2 * half)
+                for (size_t k = 0; k < half; k++) {
+                    ff_t u = a[blk + k], v;
+                    ff_mul(c, &v, &a[blk + k + half], &pwr[k * step]);
+                    ff_add(c, &a[blk + k], &u, &v);
+                    ff_sub(c, &a[blk + k + half], &u, &v);
+                }
+        }
+    }
+    if (direction) {
+        ff_t two, half_, ninv;
+        ffx_small(c, &two, 2);
+        ff_inv(c, &half_, &two);
+        ff_set_one(c, &ninv);
+        for (unsigned i = 0; i < lg; i++) ff_mul(c, &ninv, &ninv, &half_);
+        for (size_t i = 0; i < n; i++) ff_mul(c, &a[i], &a[i], &ninv);
+        if (type) {
+            ffx_small(c, &g, gen);
+            ff_inv(c, &g, &g);
+            ff_set_one(c, &pw);
+            for (size_t i = 0; i < n; i++) {
+                size_t k = quirk ? bitrev(i, lg) : i;
+                ff_mul(c, &a[k], &a[k], &pw);
+                ff_mul(c, &pw, &pw, &g);
+            }
+        }
+    }
+    if (out_rev) {
+        for (size_t i = 0; i < n; i++) tmp[bitrev(i, lg)] = a[i];
+        memcpy(a, tmp, n * sizeof(ff_t));
+    }
+    for (size_t i = 0; i < n; i++)
+        memcpy(data + i * nl, a[i].l, 8 * nl);
+    free(pwr);
+    free(tmp);
+    free(a);
+    return 0;
+}

@@ -42,6 +42,10 @@ int oracle_ntt_gl64(uint64_t *inout, unsigned lg_n, int order, int direction, in
 int oracle_ntt_bb31(uint32_t *inout, unsigned lg_n, int order, int direction, int type,
                     int algo, int nthreads);
 
+/* 256-bit Montgomery fields: field_id 1 = BLS12-381 fr, 2 = Pallas base field, 3 = Vesta base
+ * field; data = n x 4 64-bit limbs, Montgomery residues; in place */
+int oracle_ntt_ff(int field_id, uint64_t *data, unsigned lg_n, int order, int direction, int type, int algo);
+
 uint64_t oracle_gl64_root(unsigned lg_n, int inverse);
 uint32_t oracle_bb31_root(unsigned lg_n, int inverse);   /* true value, not Montgomery */
 uint64_t oracle_gl64_mul(uint64_t a, uint64_t b);

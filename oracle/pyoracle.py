@@ -52,6 +52,7 @@ def lib():
         _lib.oracle_ff_consts.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.oracle_ntt_gl64.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         _lib.oracle_ntt_bb31.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        _lib.oracle_ntt_ff.argtypes = [C.c_int, C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int]
         _lib.oracle_gl64_root.restype = C.c_uint64
         _lib.oracle_gl64_root.argtypes = [C.c_uint, C.c_int]
         _lib.oracle_bb31_root.restype = C.c_uint32
@@ -146,6 +147,17 @@ def ntt_bb31(a, order=NN, inverse=False, coset=False, algo="fast", nthreads=1):
     lg = int(a.size).bit_length() - 1
     assert a.size == 1 << lg
     rc = lib().oracle_ntt_bb31(_ptr(a), lg, order, int(inverse), int(coset), int(algo == "dft"), nthreads)
+    assert rc == 0
+    return a
+
+
+def ntt_ff(field, a, order=NN, inverse=False, coset=False, algo="fast"):
+    """256-bit fields: field in {'bls12_381_fr', 'pallas_fp', 'vesta_fp'}; a: (n, 4) uint64
+    Montgomery residues."""
+    a = np.array(a, dtype=np.uint64, copy=True).reshape(-1, 4)
+    lg = int(a.shape[0]).bit_length() - 1
+    assert a.shape[0] == 1 << lg
+    rc = lib().oracle_ntt_ff(FIELDS[field], _ptr(a), lg, order, int(inverse), int(coset), int(algo == "dft"))
     assert rc == 0
     return a
 

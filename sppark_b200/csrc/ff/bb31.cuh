@@ -12,6 +12,9 @@ struct bb31 {
     static constexpr uint32_t RR = 0x45dddde3u;      // 2^64 mod p
     static constexpr uint32_t ONE = 0x0ffffffeu;     // 2^32 mod p
     static constexpr int MAX_LG = 27;
+    static constexpr uint32_t NTT_MAX_LG_R = 12;
+    static constexpr uint32_t NTT_MAX_THREADS = 1024;
+    static constexpr uint32_t LG_EPT = 4;          // NTT: elements per thread per register step
     static constexpr int LG_BYTES = 2;
 
     static HD T canon(T a) { return a; }

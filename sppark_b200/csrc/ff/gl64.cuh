@@ -14,6 +14,9 @@ struct gl64 {
     static constexpr uint64_t P = 0xffffffff00000001ULL;
     static constexpr uint64_t EPS = 0xffffffffULL;
     static constexpr int MAX_LG = 32;
+    static constexpr uint32_t NTT_MAX_LG_R = 12;   // largest sub-NTT per tile
+    static constexpr uint32_t NTT_MAX_THREADS = 1024;
+    static constexpr uint32_t LG_EPT = 4;          // NTT: elements per thread per register step
     static constexpr int LG_BYTES = 3;
 
     static HD T canon(T a) { return a >= P ? a - P : a; }

@@ -1,12 +1,17 @@
 // NTT instantiations and their C-ABI entry points (include/sppark_b200.h).
 #include "../ff/gl64.cuh"
 #include "../ff/bb31.cuh"
+#include "../ff/mont_ntt.cuh"
 #include "ntt.cuh"
 
 namespace ntt {
 // lg_tile: log2(elements) of one CTA's shared-memory tile: 128 KiB of data for either field
 template<> struct FieldId<gl64> { static constexpr uint32_t id = 1, lg_tile = 14; };
 template<> struct FieldId<bb31> { static constexpr uint32_t id = 2, lg_tile = 14; };
+// 256-bit Montgomery scalar fields: 2^11-element tiles (64 KiB) + 64 KiB of sub-NTT twiddles
+template<> struct FieldId<ff::bls12_381_fr_ntt> { static constexpr uint32_t id = 3, lg_tile = 11; };
+template<> struct FieldId<ff::pallas_fr_ntt> { static constexpr uint32_t id = 4, lg_tile = 11; };
+template<> struct FieldId<ff::vesta_fr_ntt> { static constexpr uint32_t id = 5, lg_tile = 11; };
 // ---- statically shaped twins of the passes the planner emits for the common sizes ----------
 // key = (lg_r, lg_w, in row-fast, out row-fast, in_rev, out_rev, tw_mode)
 template<class F, uint32_t R, uint32_t W, bool IRF, bool ORF, bool IREV, bool OREV, uint32_t TW>
@@ -27,7 +32,7 @@ static bool try_static(const Pass& d, const Tables<F>& tb, const typename F::T* 
     if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     uint32_t per_sm = smem <= 48 * 1024 ? 4 : smem <= 100 * 1024 ? 2 : 1;
     uint32_t grid = ntiles < (uint32_t)sms * per_sm ? ntiles : (uint32_t)sms * per_sm;
-    pass_kernel_static<F, K><<<grid, tile_threads(d), smem, stream>>>(d, tb, in, out, ntiles);
+    pass_kernel_static<F, K><<<grid, tile_threads<F>(d), smem, stream>>>(d, tb, in, out, ntiles);
     return true;
 }
 
@@ -49,7 +54,8 @@ template<class F> bool launch_static(const Pass& d, const Tables<F>& tb, const t
                                      typename F::T* out, uint32_t ntiles, size_t smem, cudaStream_t stream)
 {
     if (getenv("SPPARK_B200_NTT_GENERIC")) return false;
-    return try_shapes<F, 12, 2>(d, tb, in, out, ntiles, smem, stream)
+    if constexpr (F::LG_EPT != 4) return false;       // 256-bit fields run the run-time shaped kernel
+    else return try_shapes<F, 12, 2>(d, tb, in, out, ntiles, smem, stream)
         || try_shapes<F, 11, 3>(d, tb, in, out, ntiles, smem, stream)
         || try_shapes<F, 10, 4>(d, tb, in, out, ntiles, smem, stream)
         || try_shapes<F, 12, 1>(d, tb, in, out, ntiles, smem, stream)
@@ -65,8 +71,15 @@ template<class F> bool launch_static(const Pass& d, const Tables<F>& tb, const t
 template bool launch_static<gl64>(const Pass&, const Tables<gl64>&, const uint64_t*, uint64_t*, uint32_t, size_t, cudaStream_t);
 template bool launch_static<bb31>(const Pass&, const Tables<bb31>&, const uint32_t*, uint32_t*, uint32_t, size_t, cudaStream_t);
 
+template bool launch_static<ff::bls12_381_fr_ntt>(const Pass&, const Tables<ff::bls12_381_fr_ntt>&, const ff::bls12_381_fr_ntt::T*, ff::bls12_381_fr_ntt::T*, uint32_t, size_t, cudaStream_t);
+template bool launch_static<ff::pallas_fr_ntt>(const Pass&, const Tables<ff::pallas_fr_ntt>&, const ff::pallas_fr_ntt::T*, ff::pallas_fr_ntt::T*, uint32_t, size_t, cudaStream_t);
+template bool launch_static<ff::vesta_fr_ntt>(const Pass&, const Tables<ff::vesta_fr_ntt>&, const ff::vesta_fr_ntt::T*, ff::vesta_fr_ntt::T*, uint32_t, size_t, cudaStream_t);
+
 template class NTT<gl64>;
 template class NTT<bb31>;
+template class NTT<ff::bls12_381_fr_ntt>;
+template class NTT<ff::pallas_fr_ntt>;
+template class NTT<ff::vesta_fr_ntt>;
 }  // namespace ntt
 
 template<class F>
@@ -115,6 +128,9 @@ extern "C" RustError sppark_b200_ntt(int field, size_t device_id, void* inout, u
     switch (field) {
     case SPPARK_FIELD_GL64: return ntt_host<gl64>(device_id, inout, lg, order, direction, type);
     case SPPARK_FIELD_BB31: return ntt_host<bb31>(device_id, inout, lg, order, direction, type);
+    case SPPARK_FIELD_BLS12_381_FR: return ntt_host<ff::bls12_381_fr_ntt>(device_id, inout, lg, order, direction, type);
+    case SPPARK_FIELD_PALLAS_FR: return ntt_host<ff::pallas_fr_ntt>(device_id, inout, lg, order, direction, type);
+    case SPPARK_FIELD_VESTA_FR: return ntt_host<ff::vesta_fr_ntt>(device_id, inout, lg, order, direction, type);
     default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_ntt: unknown field");
     }
 }
@@ -125,6 +141,9 @@ extern "C" RustError sppark_b200_ntt_dev(int field, void* d_inout, uint32_t lg, 
     switch (field) {
     case SPPARK_FIELD_GL64: return ntt_dev<gl64>(d_inout, lg, order, direction, type, stream);
     case SPPARK_FIELD_BB31: return ntt_dev<bb31>(d_inout, lg, order, direction, type, stream);
+    case SPPARK_FIELD_BLS12_381_FR: return ntt_dev<ff::bls12_381_fr_ntt>(d_inout, lg, order, direction, type, stream);
+    case SPPARK_FIELD_PALLAS_FR: return ntt_dev<ff::pallas_fr_ntt>(d_inout, lg, order, direction, type, stream);
+    case SPPARK_FIELD_VESTA_FR: return ntt_dev<ff::vesta_fr_ntt>(d_inout, lg, order, direction, type, stream);
     default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_ntt_dev: unknown field");
     }
 }

@@ -10,7 +10,7 @@
 namespace ntt {
 
 template<class F>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(F::NTT_MAX_THREADS)
 pass_kernel(const Pass d, const Tables<F> tb, const typename F::T* in, typename F::T* out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -21,9 +21,9 @@ pass_kernel(const Pass d, const Tables<F> tb, const typename F::T* in, typename 
     phase_twiddles<F>(k, tb, smem, tid, nthreads);
     phase_load<F>(k, d, tb, in, smem, t, tid, nthreads);
     __syncthreads();
-    const uint32_t nsteps = step_count(d.lg_r);
+    const uint32_t nsteps = step_count<F>(d.lg_r);
     for (uint32_t s = 0; s < nsteps; s++) {
-        phase_step_dyn<F>(k, smem, s * LG_EPT, step_log_e(d.lg_r, s), tid);
+        phase_step_dyn<F>(k, smem, s * F::LG_EPT, step_log_e<F>(d.lg_r, s), tid);
         __syncthreads();
     }
     phase_store<F>(k, d, tb, out, smem, t, tid, nthreads);
@@ -31,13 +31,14 @@ pass_kernel(const Pass d, const Tables<F> tb, const typename F::T* in, typename 
 
 // the same pass with its shape fixed at compile time (see KStat in ntt_core.cuh)
 template<class F, class K>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(F::NTT_MAX_THREADS)
 pass_kernel_static(const Pass d, const Tables<F> tb, const typename F::T* in, typename F::T* out, uint32_t ntiles)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename F::T* smem = reinterpret_cast<typename F::T*>(smem_raw);
     const uint32_t tid = threadIdx.x;
     constexpr uint32_t R = K::lg_r();
+    constexpr uint32_t LG_EPT = F::LG_EPT;
     constexpr uint32_t nthreads = (R >= LG_EPT ? (1u << (R - LG_EPT)) : 1u) << K::lg_w();
     const K k(d);
 
@@ -48,7 +49,7 @@ pass_kernel_static(const Pass d, const Tables<F> tb, const typename F::T* in, ty
         phase_load<F>(k, d, tb, in, smem, t, tid, nthreads);
         __syncthreads();
 #pragma unroll
-        for (uint32_t s = 0; s < step_count(R); s++) {
+        for (uint32_t s = 0; s < step_count<F>(R); s++) {
             constexpr uint32_t full = R / LG_EPT;
             if (s < full) phase_step<F, K, LG_EPT>(k, smem, s * LG_EPT, tid);
             else phase_step_dyn<F>(k, smem, s * LG_EPT, R - full * LG_EPT, tid);
@@ -209,7 +210,8 @@ public:
         uint32_t lg_tile = FieldId<F>::lg_tile;
         if (lg_n < lg_tile + 8) lg_tile = lg_n > 18 ? lg_n - 8 : 10;
         if (const char* env = getenv("SPPARK_B200_NTT_LG_TILE")) lg_tile = (uint32_t)atoi(env);
-        Plan plan = make_plan(lg_n, (int)order, inverse, lg_tile);
+        if (lg_tile > FieldId<F>::lg_tile) lg_tile = FieldId<F>::lg_tile;
+        Plan plan = make_plan(lg_n, (int)order, inverse, lg_tile, 6, F::NTT_MAX_LG_R);
 
         T* scratch = nullptr;
         if (plan.needs_scratch)
@@ -228,7 +230,7 @@ public:
             uint32_t ntiles = 1u << (lg_n - d.lg_r - d.lg_w);
             size_t smem = smem_elems(d) * sizeof(T);
             if (!launch_static<F>(d, tb, buf[d.src], buf[d.dst], ntiles, smem, stream))
-                pass_kernel<F><<<ntiles, tile_threads(d), smem, stream>>>(d, tb, buf[d.src], buf[d.dst]);
+                pass_kernel<F><<<ntiles, tile_threads<F>(d), smem, stream>>>(d, tb, buf[d.src], buf[d.dst]);
             COUNT_LAUNCH();
             CUDA_OK(cudaGetLastError());
         }

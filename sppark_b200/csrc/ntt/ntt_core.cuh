@@ -26,8 +26,8 @@
 namespace ntt {
 
 constexpr uint32_t LG_DENSE = 12;        // largest sub-NTT: 2^12 rows
-constexpr uint32_t EPT = 16;             // elements per thread per register step
-constexpr uint32_t LG_EPT = 4;
+// elements per thread per register step = 2^F::LG_EPT: 16 for the one-word fields (32 live
+// registers of data), 4 for the 256-bit Montgomery fields (8 words each)
 constexpr uint32_t LG_TLO = 12;          // low half of the two-level w_N^e table
 
 enum TwMode : uint32_t { TW_NONE = 0, TW_LOAD = 1, TW_STORE = 2 };
@@ -92,9 +92,9 @@ HD uint32_t swz(uint32_t i, uint32_t c, uint32_t lg_r)
     return i ^ (((i >> 4) ^ (i >> 8) ^ c) & (lg_r >= 4 ? 15u : (1u << lg_r) - 1));
 }
 HD uint32_t col_stride(uint32_t lg_r) { return 1u << lg_r; }
-HD uint32_t tile_threads(const Pass& d)
+template<class F> HD uint32_t tile_threads(const Pass& d)
 {
-    return (d.lg_r >= LG_EPT ? (1u << (d.lg_r - LG_EPT)) : 1u) << d.lg_w;
+    return (d.lg_r >= F::LG_EPT ? (1u << (d.lg_r - F::LG_EPT)) : 1u) << d.lg_w;
 }
 HD uint32_t smem_elems(const Pass& d) { return (col_stride(d.lg_r) << d.lg_w) + (1u << d.lg_r); }
 
@@ -137,6 +137,7 @@ HD void phase_load(const K k, const Pass& d, const Tables<F>& tb, const typename
     const uint32_t R = k.lg_r(), LW = k.lg_w(), n_el = (1u << R) << LW, cs = col_stride(R);
     const uint64_t base = tile_base(t, d.in_lg_tlo, d.in_tl, d.in_th);
     const bool row_fast = k.in_row_fast();      // consecutive threads walk rows, else columns
+    constexpr uint32_t EPT = 1u << F::LG_EPT;
     T v[EPT];
 #pragma unroll
     for (uint32_t l = 0; l < EPT; l++) {
@@ -173,7 +174,7 @@ HD void phase_step(const K k, typename F::T* smem, uint32_t b, uint32_t tid)
     typedef typename F::T T;
     constexpr uint32_t E = 1u << LOG_E;
     const uint32_t R = k.lg_r(), cs = col_stride(R);
-    const uint32_t lg_tpc = R >= LG_EPT ? R - LG_EPT : 0;       // threads per column
+    const uint32_t lg_tpc = R >= F::LG_EPT ? R - F::LG_EPT : 0;       // threads per column
     const uint32_t c = tid >> lg_tpc, tau = tid & ((1u << lg_tpc) - 1);
     T* col = smem + c * cs;
     const T* tw = smem + (cs << k.lg_w());
@@ -213,20 +214,25 @@ HD void phase_step(const K k, typename F::T* smem, uint32_t b, uint32_t tid)
 template<class F, class K>
 HD void phase_step_dyn(const K k, typename F::T* smem, uint32_t b, uint32_t log_e, uint32_t tid)
 {
-    switch (log_e) {
-    case 1: phase_step<F, K, 1>(k, smem, b, tid); break;
-    case 2: phase_step<F, K, 2>(k, smem, b, tid); break;
-    case 3: phase_step<F, K, 3>(k, smem, b, tid); break;
-    default: phase_step<F, K, 4>(k, smem, b, tid); break;
+    if constexpr (F::LG_EPT >= 4) {
+        switch (log_e) {
+        case 1: phase_step<F, K, 1>(k, smem, b, tid); break;
+        case 2: phase_step<F, K, 2>(k, smem, b, tid); break;
+        case 3: phase_step<F, K, 3>(k, smem, b, tid); break;
+        default: phase_step<F, K, 4>(k, smem, b, tid); break;
+        }
+    } else {
+        if (log_e == 1) phase_step<F, K, 1>(k, smem, b, tid);
+        else phase_step<F, K, 2>(k, smem, b, tid);
     }
 }
 
 // stage schedule for a 2^R sub-NTT: full 4-stage steps first, remainder last
-HD uint32_t step_count(uint32_t R) { return (R + LG_EPT - 1) / LG_EPT; }
-HD uint32_t step_log_e(uint32_t R, uint32_t s)
+template<class F> HD constexpr uint32_t step_count(uint32_t R) { return (R + F::LG_EPT - 1) / F::LG_EPT; }
+template<class F> HD uint32_t step_log_e(uint32_t R, uint32_t s)
 {
-    uint32_t done = s * LG_EPT;
-    return R - done >= LG_EPT ? LG_EPT : R - done;
+    uint32_t done = s * F::LG_EPT;
+    return R - done >= F::LG_EPT ? F::LG_EPT : R - done;
 }
 
 // ---- phase 3: shared memory -> HBM -------------------------------------------------
@@ -239,6 +245,7 @@ HD void phase_store(const K k, const Pass& d, const Tables<F>& tb, typename F::T
     const uint64_t ibase = tile_base(t, d.in_lg_tlo, d.in_tl, d.in_th);
     const uint64_t obase = tile_base(t, d.out_lg_tlo, d.out_tl, d.out_th);
     const bool row_fast = k.out_row_fast();
+    constexpr uint32_t EPT = 1u << F::LG_EPT;
 #pragma unroll
     for (uint32_t l = 0; l < EPT; l++) {
         uint32_t e = l * nthreads + tid;

@@ -52,11 +52,11 @@ inline std::vector<uint32_t> split_digits(uint32_t lg_n, uint32_t max_lg_r = LG_
 }
 
 inline Plan make_plan(uint32_t lg_n, int order, bool inverse, uint32_t lg_tile,
-                      uint32_t max_lg_w = 6)
+                      uint32_t max_lg_w = 6, uint32_t max_lg_r = LG_DENSE)
 {
     Plan plan;
     plan.lg_n = lg_n;
-    const std::vector<uint32_t> s = split_digits(lg_n);
+    const std::vector<uint32_t> s = split_digits(lg_n, max_lg_r);
     const uint32_t P = (uint32_t)s.size();
     std::vector<uint32_t> A(P), B(P);
     for (uint32_t p = 0, acc = 0; p < P; p++) { A[p] = acc; acc += s[p]; }

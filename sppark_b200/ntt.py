@@ -11,6 +11,7 @@ BB = 4                                 # extension: bit-reversed in and out (RR 
 FORWARD, INVERSE = 0, 1                # sppark::NTTDirection
 STANDARD, COSET = 0, 1                 # sppark::NTTType
 GL64, BB31 = 0, 1
+BLS12_381_FR, PALLAS_FR, VESTA_FR = 2, 3, 4      # (n, 4) uint64 arrays of Montgomery residues
 
 
 def _field_of(a):
@@ -21,16 +22,16 @@ def _field_of(a):
     raise TypeError("inout must be uint64 (Goldilocks) or uint32 (BabyBear)")
 
 
-def _run(device_id, inout, order, direction, typ):
+def _run(device_id, inout, order, direction, typ, field=None):
     if not isinstance(inout, np.ndarray) or not inout.flags["C_CONTIGUOUS"] or not inout.flags["WRITEABLE"]:
         raise TypeError("inout must be a writable C-contiguous numpy array")
-    n = inout.size
+    n = inout.size if field in (None, GL64, BB31) else inout.shape[0]
     if n & (n - 1):
         raise ValueError("inout.len() is not power of 2")     # same panic text as the crate
     lg = n.bit_length() - 1 if n else 0
     if n == 0:
         return
-    field = _field_of(inout)
+    field = _field_of(inout) if field is None else field
     l = _lib.lib()
     if field == GL64:
         err = l.compute_ntt(device_id, inout.ctypes.data, lg, order, direction, typ)
@@ -39,20 +40,20 @@ def _run(device_id, inout, order, direction, typ):
     _lib.check(err)
 
 
-def NTT(device_id, inout, order=NN):
-    _run(device_id, inout, order, FORWARD, STANDARD)
+def NTT(device_id, inout, order=NN, field=None):
+    _run(device_id, inout, order, FORWARD, STANDARD, field)
 
 
-def iNTT(device_id, inout, order=NN):
-    _run(device_id, inout, order, INVERSE, STANDARD)
+def iNTT(device_id, inout, order=NN, field=None):
+    _run(device_id, inout, order, INVERSE, STANDARD, field)
 
 
-def coset_NTT(device_id, inout, order=NN):
-    _run(device_id, inout, order, FORWARD, COSET)
+def coset_NTT(device_id, inout, order=NN, field=None):
+    _run(device_id, inout, order, FORWARD, COSET, field)
 
 
-def coset_iNTT(device_id, inout, order=NN):
-    _run(device_id, inout, order, INVERSE, COSET)
+def coset_iNTT(device_id, inout, order=NN, field=None):
+    _run(device_id, inout, order, INVERSE, COSET, field)
 
 
 def ntt_dev(tensor, order=NN, direction=FORWARD, typ=STANDARD, field=None, stream=None):

@@ -9,6 +9,7 @@
 #include <vector>
 #include "../../sppark_b200/csrc/ff/gl64.cuh"
 #include "../../sppark_b200/csrc/ff/bb31.cuh"
+#include "../../sppark_b200/csrc/ff/mont_ntt.cuh"
 #include "../../sppark_b200/csrc/ntt/ntt_plan.hpp"
 
 using namespace ntt;
@@ -54,11 +55,11 @@ static int emu_run(typename F::T* data, uint32_t lg_n, int order, int inverse, u
     typedef typename F::T T;
     if (lg_n == 0) return 0;
     HostTables<F> tb(lg_n, inverse != 0);
-    Plan plan = make_plan(lg_n, order, inverse != 0, lg_tile);
+    Plan plan = make_plan(lg_n, order, inverse != 0, lg_tile, 6, F::NTT_MAX_LG_R);
     std::vector<T> scratch(plan.needs_scratch ? (size_t)1 << lg_n : 0);
     T* buf[2] = {data, scratch.data()};
     for (const Pass& d : plan.passes) {
-        uint32_t nthreads = tile_threads(d);
+        uint32_t nthreads = tile_threads<F>(d);
         uint32_t ntiles = 1u << (lg_n - d.lg_r - d.lg_w);
         std::vector<T> smem(smem_elems(d));
         // out-of-place passes read src while other tiles write dst: they never alias.
@@ -67,9 +68,9 @@ static int emu_run(typename F::T* data, uint32_t lg_n, int order, int inverse, u
             const KDyn k{d};
             for (uint32_t tid = 0; tid < nthreads; tid++) phase_twiddles<F>(k, tb.view, smem.data(), tid, nthreads);
             for (uint32_t tid = 0; tid < nthreads; tid++) phase_load<F>(k, d, tb.view, buf[d.src], smem.data(), t, tid, nthreads);
-            for (uint32_t s = 0; s < step_count(d.lg_r); s++)
+            for (uint32_t s = 0; s < step_count<F>(d.lg_r); s++)
                 for (uint32_t tid = 0; tid < nthreads; tid++)
-                    phase_step_dyn<F>(k, smem.data(), s * LG_EPT, step_log_e(d.lg_r, s), tid);
+                    phase_step_dyn<F>(k, smem.data(), s * F::LG_EPT, step_log_e<F>(d.lg_r, s), tid);
             for (uint32_t tid = 0; tid < nthreads; tid++) phase_store<F>(k, d, tb.view, buf[d.dst], smem.data(), t, tid, nthreads);
         }
     }
@@ -80,3 +81,11 @@ extern "C" int emu_ntt_gl64(uint64_t* data, uint32_t lg_n, int order, int invers
 {   return emu_run<gl64>(data, lg_n, order, inverse, lg_tile);   }
 extern "C" int emu_ntt_bb31(uint32_t* data, uint32_t lg_n, int order, int inverse, uint32_t lg_tile)
 {   return emu_run<bb31>(data, lg_n, order, inverse, lg_tile);   }
+extern "C" int emu_ntt_256(int field, uint32_t* data, uint32_t lg_n, int order, int inverse, uint32_t lg_tile)
+{
+    switch (field) {
+    case 2: return emu_run<ff::bls12_381_fr_ntt>((ff::bls12_381_fr_ntt::T*)data, lg_n, order, inverse, lg_tile);
+    case 3: return emu_run<ff::pallas_fr_ntt>((ff::pallas_fr_ntt::T*)data, lg_n, order, inverse, lg_tile);
+    default: return emu_run<ff::vesta_fr_ntt>((ff::vesta_fr_ntt::T*)data, lg_n, order, inverse, lg_tile);
+    }
+}

@@ -83,6 +83,27 @@ def gen_gpu(outdir):
     np.savez_compressed(os.path.join(outdir, "ntt_ref_gpu.npz"), **out)
     print("wrote ntt_ref_gpu.npz")
 
+    # 256-bit "wide" NTT: BLS12-381 scalar field, Montgomery residues
+    lib = C.CDLL(o.ref_path("libref_ntt_bls12_381_gpu.so"))
+    lib.compute_ntt.restype = RE
+    lib.compute_ntt.argtypes = [C.c_size_t, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int]
+    import random
+    rnd = random.Random(11)
+    R = 1 << 256
+    out = {}
+    for lg in range(1, 9):
+        x = np.array([o.int_to_limbs(rnd.randrange(R_BLS), 4) for _ in range(1 << lg)], dtype=np.uint64)
+        out[f"in_{lg}"] = x
+        for order in range(4):
+            for direction in range(2):
+                for typ in range(2):
+                    y = x.copy()
+                    e = lib.compute_ntt(0, y.ctypes.data, lg, order, direction, typ)
+                    assert e.code == 0
+                    out[f"out_{lg}_{order}{direction}{typ}"] = y
+    np.savez_compressed(os.path.join(outdir, "ntt256_ref_gpu.npz"), **out)
+    print("wrote ntt256_ref_gpu.npz")
+
     lib = C.CDLL(o.ref_path("libref_msm_gpu.so"))
     lib.mult_pippenger.restype = RE
     lib.mult_pippenger.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]

@@ -28,6 +28,7 @@ def ntt_emu():
     l = _build("ntt_emu")
     l.emu_ntt_gl64.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_uint]
     l.emu_ntt_bb31.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_uint]
+    l.emu_ntt_256.argtypes = [C.c_int, C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_uint]
     return l
 
 
@@ -64,6 +65,21 @@ def test_ntt_plan_and_schedule(oracle, ntt_emu, lg, split, monkeypatch):
             yb = xb.copy()
             ntt_emu.emu_ntt_bb31(yb.ctypes.data, lg, order, inv, 14)
             assert np.array_equal(yb, oracle.ntt_bb31(xb, order, bool(inv))), (order, inv)
+
+
+@pytest.mark.parametrize("fid,name", [(2, "bls12_381_fr"), (3, "vesta_fp"), (4, "pallas_fp")])
+def test_ntt_256bit_fields(oracle, ntt_emu, fid, name):
+    """the same pass kernel with 4 elements per thread over the 256-bit Montgomery fields
+    (field ids as in include/sppark_b200.h: the Pallas feature's fr is Vesta's base field)"""
+    rnd = random.Random(fid)
+    p = oracle.ff_consts(name)["p"]
+    for lg in (1, 2, 5, 8, 11, 12):
+        x = np.array([oracle.int_to_limbs(rnd.randrange(p), 4) for _ in range(1 << lg)], dtype=np.uint64)
+        for order in range(5):
+            for inv in (0, 1):
+                y = x.copy()
+                ntt_emu.emu_ntt_256(fid, y.ctypes.data, lg, order, inv, 11 if lg != 8 else 5)
+                assert np.array_equal(y, oracle.ntt_ff(name, x, order, bool(inv))), (lg, order, inv)
 
 
 def _scalars(vals):

@@ -160,3 +160,54 @@ def test_babybear_2pow27_field_maximum():
     assert e.code != 0
     if e.message:
         _lib.lib().drop_error_message(e.message)
+
+
+@pytest.mark.parametrize("fid,name", [(2, "bls12_381_fr"), (3, "vesta_fp"), (4, "pallas_fp")])
+def test_ntt_256bit_fields_match_oracle(oracle, fid, name):
+    """256-bit Montgomery scalar fields (the reference's "wide" kernels)."""
+    import random
+    from sppark_b200 import ntt
+    rnd = random.Random(fid)
+    p = oracle.ff_consts(name)["p"]
+    for lg in (1, 2, 3, 7, 11, 12, 14):
+        x = np.array([oracle.int_to_limbs(rnd.randrange(p), 4) for _ in range(1 << lg)], dtype=np.uint64)
+        for order in (ntt.NN, ntt.NR, ntt.RN, ntt.RR, ntt.BB):
+            for inverse in (False, True):
+                y = x.copy()
+                (ntt.iNTT if inverse else ntt.NTT)(0, y, order, field=fid)
+                assert np.array_equal(y, oracle.ntt_ff(name, x, order, inverse)), (name, lg, order, inverse)
+        if lg in (3, 12):
+            for order in (ntt.NN, ntt.NR, ntt.RN, ntt.RR):
+                y = x.copy(); ntt.coset_NTT(0, y, order, field=fid)
+                assert np.array_equal(y, oracle.ntt_ff(name, x, order, False, True))
+                y = x.copy(); ntt.coset_iNTT(0, y, order, field=fid)
+                assert np.array_equal(y, oracle.ntt_ff(name, x, order, True, True))
+
+
+def test_ntt_256bit_matches_reference_gpu_golden():
+    import os
+    from sppark_b200 import ntt
+    path = os.path.join(os.path.dirname(__file__), "golden", "ntt256_ref_gpu.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden not recorded yet")
+    g = np.load(path)
+    for lg in range(1, 9):
+        x = g[f"in_{lg}"]
+        for order in range(4):
+            for d in range(2):
+                for t in range(2):
+                    y = x.copy()
+                    ntt._run(0, y, order, d, t, field=ntt.BLS12_381_FR)
+                    assert np.array_equal(y, g[f"out_{lg}_{order}{d}{t}"]), (lg, order, d, t)
+
+
+def test_ntt_256bit_2pow22_roundtrip():
+    import random
+    from sppark_b200 import ntt
+    lg = 22
+    rng = np.random.default_rng(9)
+    x = rng.integers(0, 2**62, size=(1 << lg, 4), dtype=np.uint64)      # < 2^254: valid residues
+    y = x.copy()
+    ntt.NTT(0, y, ntt.NR, field=ntt.BLS12_381_FR)
+    ntt.iNTT(0, y, ntt.RN, field=ntt.BLS12_381_FR)
+    assert np.array_equal(x, y)

@@ -144,3 +144,32 @@ def test_oracle_matches_reference_gpu_golden_ntt(oracle):
                     for t in range(2):
                         assert np.array_equal(fn(x, order, bool(d), bool(t)), g[f"{field}_out_{lg}_{order}{d}{t}"]), \
                             (field, lg, order, d, t)
+
+
+def test_oracle_matches_reference_gpu_golden_ntt256(oracle):
+    """BLS12-381 scalar-field NTT (the reference's 256-bit "wide" kernels) recorded on a B200."""
+    path = os.path.join(GOLD, "ntt256_ref_gpu.npz")
+    if not os.path.exists(path):
+        pytest.skip("reference-GPU golden not recorded yet")
+    g = np.load(path)
+    for lg in range(1, 9):
+        x = g[f"in_{lg}"]
+        for order in range(4):
+            for d in range(2):
+                for t in range(2):
+                    assert np.array_equal(oracle.ntt_ff("bls12_381_fr", x, order, bool(d), bool(t)),
+                                          g[f"out_{lg}_{order}{d}{t}"]), (lg, order, d, t)
+
+
+@pytest.mark.parametrize("field", ["bls12_381_fr", "pallas_fp", "vesta_fp"])
+def test_ntt256_fast_equals_definition(oracle, field):
+    rnd = random.Random(3)
+    p = oracle.ff_consts(field)["p"]
+    for lg in range(1, 7):
+        x = np.array([oracle.int_to_limbs(rnd.randrange(p), 4) for _ in range(1 << lg)], dtype=np.uint64)
+        for order in range(5):
+            for inv in (False, True):
+                for coset in (False, True):
+                    assert np.array_equal(oracle.ntt_ff(field, x, order, inv, coset, "dft"),
+                                          oracle.ntt_ff(field, x, order, inv, coset, "fast"))
+        assert np.array_equal(oracle.ntt_ff(field, oracle.ntt_ff(field, x, oracle.NR), oracle.RN, True), x)

@@ -77,3 +77,31 @@ def test_msm_field_constants():
     assert ours("vesta_fp", "P") == theirs(q, "Vesta_P")
     assert ours("vesta_fp", "ONE") == theirs(q, "Vesta_one")
     assert "M0 = 0xfffcfffdu" in gen.split("struct bls12_381_fp_params")[1].split("typedef")[0]
+
+
+def test_256bit_ntt_roots():
+    """group_gen / 2^32-th roots of unity of the 256-bit NTT fields: derived (tools/gen_fields.py,
+    oracle/ntt.c) vs ntt/parameters/{bls12_381,pallas,vesta}.h."""
+    def table(path):
+        s = open(path).read()
+        out = {}
+        for m in re.finditer(r"const fr_t (\w+)\[S \+ 1\] = \{(.*?)\};", s, re.S):
+            vals = []
+            for mm in re.finditer(r"FR_T\(vec256,(.*?)\)", m.group(2)):
+                l = [int(x.strip().rstrip("u"), 16) for x in mm.group(1).split(",")]
+                vals.append(sum(v << (64 * i) for i, v in enumerate(l)))
+            out[m.group(1)] = vals
+        m = re.search(r"const fr_t group_gen = FR_T\(vec256,(.*?)\)", s)
+        l = [int(x.strip().rstrip("u"), 16) for x in m.group(1).split(",")]
+        out["group_gen"] = sum(v << (64 * i) for i, v in enumerate(l))
+        return out
+    R = 1 << 256
+    for name, p, g in (("bls12_381", 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001, 7),
+                       ("vesta", 0x40000000000000000000000000000000224698fc0994a8dd8c46eb2100000001, 5),
+                       ("pallas", 0x40000000000000000000000000000000224698fc094cf91b992d30ed00000001, 5)):
+        t = table(f"{REF}/ntt/parameters/{name}.h")
+        assert t["group_gen"] == g * R % p
+        w = pow(g, (p - 1) >> 32, p)
+        for lg in range(33):
+            assert t["forward_roots_of_unity"][lg] == pow(w, 1 << (32 - lg), p) * R % p
+            assert t["domain_size_inverse"][lg] == pow(2, -lg, p) * R % p
