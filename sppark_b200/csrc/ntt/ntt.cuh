@@ -250,6 +250,8 @@ public:
                           Direction direction, Type type)
     {
         if (lg_n == 0) return rust_ok();
+        if (lg_n > (uint32_t)F::MAX_LG || lg_n > 30)          // before touching the caller's buffer
+            return rust_err(-(int)cudaErrorInvalidValue, "NTT: lg_domain_size out of range for this field");
         try {
             gpu.select();
             const stream_t& s = gpu[0];
