@@ -339,10 +339,12 @@ def _jac_equal(a, b, msm):
 
 def bench_ntt(args, torch, ntt, _lib, peak, peak_src, barrier, max_over_ranks, world):
     """Goldilocks 2^lg NTT, NN order, device-resident (NTT::Base_dev_ptr path) and e2e
-    (compute_ntt with a pinned host buffer).  N ranks run N independent transforms (replicas);
-    the slab-sharded single transform is exercised by tests, see DESIGN.md."""
+    (compute_ntt with a pinned host buffer).  With N > 1 ranks ONE transform is slab-sharded over
+    the ranks (column slabs, one NCCL all-to-all between the two local passes; strong scaling)."""
     lg = args.lg_ntt
     n = 1 << lg
+    if world > 1:
+        return bench_ntt_sharded(args, torch, _lib, peak, peak_src, barrier, max_over_ranks, world)
     rng = np.random.default_rng(7)
     host_t = torch.empty(n, dtype=torch.int64, pin_memory=True)
     host = host_t.numpy().view(np.uint64)
@@ -388,6 +390,40 @@ def bench_ntt(args, torch, ntt, _lib, peak, peak_src, barrier, max_over_ranks, w
     res["e2e"] = {"value": 1.0 / dt, "unit": "NTT/s", "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
                   "api": "compute_ntt (host pointer, pinned)"}
     return res
+
+
+def bench_ntt_sharded(args, torch, _lib, peak, peak_src, barrier, max_over_ranks, world):
+    import torch.distributed as dist
+    from sppark_b200 import parallel
+    lg, rank = args.lg_ntt, dist.get_rank()
+    lg_g = world.bit_length() - 1
+    n_local = (1 << lg) // world
+    rng = np.random.default_rng(7 + rank)
+    local = torch.from_numpy(rng.integers(0, GL_P, size=n_local, dtype=np.uint64).view(np.int64)).cuda()
+    pass_fn = parallel.gpu_slab_pass(0, lg, lg_g, rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    iters = max(10, args.steps * 5)
+    for _ in range(max(3, args.warmup)):
+        parallel.ntt_slab(local, lg, 0, pass_fn)
+    barrier()
+    tot = 0.0
+    for _ in range(iters):
+        flush.zero_()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        parallel.ntt_slab(local, lg, 0, pass_fn)
+        e1.record()
+        e1.synchronize()
+        tot += max_over_ranks(e0.elapsed_time(e1))
+    ms = tot / iters
+    alg = 2 * (1 << lg) * 8
+    return {"metric": f"Goldilocks NTT/s @2^{lg} (NN, forward)", "value": 1e3 / ms, "unit": "NTT/s",
+            "ms_per_ntt": ms, "scaling": "strong", "iters": iters,
+            "sharding": f"column slabs x{world}, one all-to-all of {n_local * 8 * (world - 1) // world} B per rank",
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src},
+            "e2e": None}
 
 
 if __name__ == "__main__":

@@ -94,6 +94,18 @@ RustError sppark_b200_ntt(int field, size_t device_id, void *inout, uint32_t lg_
 RustError sppark_b200_ntt_dev(int field, void *d_inout, uint32_t lg_domain_size,
                               int ntt_order, int ntt_direction, int ntt_type, void *stream);
 
+/* Slab-sharded NTT over G = 2^lg_g GPUs with ONE all-to-all (new; the reference has no multi-GPU
+ * path).  N = N1 x N2, N1 = 2^ceil(lg/2).  Rank r owns input columns x[j1*N2 + j2],
+ * j2 in [r*N2/G, (r+1)*N2/G), as a row-major [N1][N2/G] device array, and ends with the output
+ * coefficients X[k1 + N1*k2], k1 in [r*N1/G, (r+1)*N1/G), as a row-major [N2][N1/G] array.
+ *   which = 1: d_in = local input, d_out = staging buffer (N/G elements) laid out [G][N2/G][N1/G];
+ *              then exchange block q with rank q (NCCL all-to-all, torch.distributed, ...)
+ *   which = 2: d_in == d_out = the received buffer, transformed in place.
+ * Both calls enqueue on `stream`.  sppark_b200/parallel.py: ntt_slab(). */
+RustError sppark_b200_ntt_slab_pass(int field, int which, const void *d_in, void *d_out,
+                                    uint32_t lg_domain_size, uint32_t lg_g, uint32_t rank,
+                                    int ntt_direction, void *stream);
+
 /* MSM on any supported curve with host pointers (mult_pippenger's signature + curve id;
  * the reference has no PoC boundary for Pasta). */
 RustError sppark_b200_msm(int curve, void *out_jacobian, const void *points_affine,

@@ -241,6 +241,41 @@ public:
             coset_scale(gpu, d_inout, lg_n, out_rev, true, stream);
     }
 
+    // one local pass of the slab-sharded transform (ntt_plan.hpp: make_slab_plan); which = 1:
+    // d_in [N1][N2/G] -> d_out = all-to-all staging [G][N2/G][N1/G]; which = 2: d_in == d_out,
+    // the received [N2][N1/G] matrix, in place.  Enqueued on `stream`.
+    static void slab_pass(const gpu_t& gpu, int which, const T* d_in, T* d_out, uint32_t lg_n,
+                          uint32_t lg_g, uint32_t rank, Direction direction, cudaStream_t stream)
+    {
+        const bool inverse = direction == Direction::inverse;
+        if (lg_n > (uint32_t)F::MAX_LG || lg_n > 30 || rank >= (1u << lg_g))
+            throw cuda_error(-(int)cudaErrorInvalidValue, "NTT slab: bad lg_domain_size / rank");
+        uint32_t lg_local = lg_n - lg_g, lg_tile = FieldId<F>::lg_tile;
+        if (lg_local < lg_tile + 8) lg_tile = lg_local > 18 ? lg_local - 8 : 10;
+        if (lg_tile > FieldId<F>::lg_tile) lg_tile = FieldId<F>::lg_tile;
+        SlabPlan sp;
+        if (!make_slab_plan(sp, lg_n, lg_g, rank, inverse, lg_tile, F::NTT_MAX_LG_R))
+            throw cuda_error(-(int)cudaErrorInvalidValue,
+                             "NTT slab: lg_domain_size must split into two digits of at most NTT_MAX_LG_R bits, each >= lg_g");
+        const Tables<F>& tb = tables(gpu, lg_n, inverse, stream);
+        static bool attr_done[64];
+        if (!attr_done[gpu.cid() & 63]) {
+            CUDA_OK(cudaFuncSetAttribute(pass_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)gpu.props().sharedMemPerBlockOptin));
+            attr_done[gpu.cid() & 63] = true;
+        }
+        const Pass& d = which == 1 ? sp.pass1 : sp.pass2;
+        uint32_t ntiles = 1u << (lg_local - d.lg_r - d.lg_w);
+        size_t smem = smem_elems(d) * sizeof(T);
+        g_profile.reset();
+        g_profile.mark("pass", stream);
+        if (!launch_static<F>(d, tb, d_in, d_out, ntiles, smem, stream))
+            pass_kernel<F><<<ntiles, tile_threads<F>(d), smem, stream>>>(d, tb, d_in, d_out);
+        COUNT_LAUNCH();
+        g_profile.mark("end", stream);
+        CUDA_OK(cudaGetLastError());
+    }
+
     static void Base_dev_ptr(const gpu_t& gpu, cudaStream_t stream, T* d_inout, uint32_t lg_n,
                              InputOutputOrder order, Direction direction, Type type)
     {   NTT_internal(gpu, d_inout, lg_n, order, direction, type, stream);   }

@@ -45,6 +45,11 @@ struct Pass {
     uint32_t tw_mode, tw_rsh, tw_bits, tw_brev, tw_lsh;
     uint32_t scale;                      // multiply by n^-1 at store (last pass of an inverse)
     uint32_t src, dst;                   // 0 = caller's buffer, 1 = scratch
+    // slab-sharded transforms only (zero otherwise): the output row index is split, its top
+    // bits select the destination rank's block of the all-to-all staging buffer; and the
+    // twiddle column is offset by the first column this rank owns
+    uint32_t out_split_bits, out_split_shift;
+    uint32_t tw_col_offset;
 };
 
 template<class F> struct Tables {
@@ -115,7 +120,7 @@ template<class F> HD typename F::T twiddle(const Tables<F>& tb, uint32_t e)
 HD uint32_t tw_column_value(const Pass& d, uint64_t pos0)
 {
     uint32_t v = (uint32_t)(pos0 >> d.tw_rsh) & (d.tw_bits >= 32 ? ~0u : ((1u << d.tw_bits) - 1));
-    return d.tw_brev ? brev32(v, d.tw_bits) : v;
+    return (d.tw_brev ? brev32(v, d.tw_bits) : v) + d.tw_col_offset;
 }
 
 // ---- phase 0: per-CTA copy of the sub-NTT twiddles into shared memory -------------
@@ -260,7 +265,11 @@ HD void phase_store(const K k, const Pass& d, const Tables<F>& tb, typename F::T
             }
             if (d.scale)
                 x = F::mul(x, tb.ninv);
-            out[obase + ((uint64_t)v << d.out_lg_sa) + ((uint64_t)c << d.out_lg_sc)] = F::canon(x);
+            uint64_t row_off = (uint64_t)v << d.out_lg_sa;
+            if (d.out_split_bits)
+                row_off = ((uint64_t)(v >> d.out_split_bits) << d.out_split_shift) +
+                          ((uint64_t)(v & ((1u << d.out_split_bits) - 1)) << d.out_lg_sa);
+            out[obase + row_off + ((uint64_t)c << d.out_lg_sc)] = F::canon(x);
         }
     }
 }

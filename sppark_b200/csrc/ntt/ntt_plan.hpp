@@ -147,4 +147,69 @@ inline Plan make_plan(uint32_t lg_n, int order, bool inverse, uint32_t lg_tile,
     return plan;
 }
 
+// ---- slab-sharded transform over G = 2^lg_g ranks, ONE all-to-all ---------------------------
+// N = N1 x N2 (N1 = 2^s1 rows, N2 = 2^s2 columns, x[j1*N2 + j2]).  Rank r owns the columns
+// j2 in [r*N2/G, (r+1)*N2/G) of the input, stored locally as a row-major [N1][N2/G] matrix, and
+// ends up owning the output coefficients X[k1 + N1*k2] with k1 in [r*N1/G, (r+1)*N1/G), stored
+// as a row-major [N2][N1/G] matrix (natural order in both cases, "column slab" distribution).
+//   pass 1 (local): N1-point NTT down every local column, twiddle w_N^(k1*j2) with the GLOBAL
+//           column j2, written straight into the all-to-all staging layout [G][N2/G][N1/G]
+//   exchange:       block q of the staging buffer goes to rank q (N*(G-1)/G^2 elements per rank)
+//   pass 2 (local): the received [N2][N1/G] matrix, N2-point NTT down every column, in place
+// The reference has no multi-GPU path; this is SURVEY.md section 8(e).
+struct SlabPlan {
+    uint32_t s1, s2;
+    Pass pass1, pass2;
+};
+
+inline bool make_slab_plan(SlabPlan& sp, uint32_t lg_n, uint32_t lg_g, uint32_t rank, bool inverse,
+                           uint32_t lg_tile, uint32_t max_lg_r = LG_DENSE, uint32_t max_lg_w = 6)
+{
+    const uint32_t s1 = (lg_n + 1) / 2, s2 = lg_n - s1;
+    if (s1 > max_lg_r || s2 > max_lg_r || s1 < lg_g || s2 < lg_g) return false;
+    sp.s1 = s1;
+    sp.s2 = s2;
+    const uint32_t lc = s2 - lg_g;                        // log2(local columns of the input)
+    const uint32_t ld = s1 - lg_g;                        // log2(local columns of the output)
+
+    Pass d;
+    memset(&d, 0, sizeof(d));
+    d.lg_r = s1;
+    uint32_t lg_w = lg_tile > s1 ? lg_tile - s1 : 0;
+    if (lg_w > max_lg_w) lg_w = max_lg_w;
+    if (lg_w > lc) lg_w = lc;
+    d.lg_w = lg_w;
+    d.in_lg_tlo = 32; d.in_tl = 1ull << lg_w; d.in_th = 0;
+    d.in_lg_sa = lc; d.in_lg_sc = 0;
+    d.out_lg_tlo = 32; d.out_tl = (1ull << lg_w) << ld; d.out_th = 0;
+    d.out_lg_sa = 0; d.out_lg_sc = ld;
+    if (lg_g) { d.out_split_bits = ld; d.out_split_shift = lc + ld; }
+    d.in_rev = 0; d.out_rev = 0;
+    d.tw_mode = TW_STORE; d.tw_rsh = 0; d.tw_bits = lc; d.tw_brev = 0; d.tw_lsh = 0;
+    d.tw_col_offset = rank << lc;
+    if (ld == 0 && lg_g) {                                // one output row per destination rank
+        d.out_split_bits = 0;
+        d.out_lg_sa = lc;                                 // row v == destination block v
+        d.out_lg_sc = 0;
+        d.out_tl = 1ull << lg_w;
+    }
+    d.src = 0; d.dst = 1;
+    sp.pass1 = d;
+
+    memset(&d, 0, sizeof(d));
+    d.lg_r = s2;
+    lg_w = lg_tile > s2 ? lg_tile - s2 : 0;
+    if (lg_w > max_lg_w) lg_w = max_lg_w;
+    if (lg_w > ld) lg_w = ld;
+    d.lg_w = lg_w;
+    d.in_lg_tlo = 32; d.in_tl = 1ull << lg_w; d.in_th = 0;
+    d.in_lg_sa = ld; d.in_lg_sc = 0;
+    d.out_lg_tlo = 32; d.out_tl = d.in_tl; d.out_th = 0;
+    d.out_lg_sa = ld; d.out_lg_sc = 0;
+    d.tw_mode = TW_NONE;
+    d.scale = inverse;
+    sp.pass2 = d;
+    return true;
+}
+
 }  // namespace ntt

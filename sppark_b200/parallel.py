@@ -38,3 +38,80 @@ def msm_sharded(local_msm, combine, partial_words, device=None):
     part = np.asarray(local_msm(), dtype=np.uint64)
     assert part.shape == (partial_words,)
     return combine(all_gather_partials(part, device))
+
+
+# ---------------------------------------------------------------------------------- NTT
+def slab_shapes(lg_n, lg_g):
+    """(N1, N2, local input shape [N1][N2/G], local output shape [N2][N1/G]) of the slab-sharded
+    transform: x[j1*N2 + j2] lives on the rank owning column j2, X[k1 + N1*k2] on the rank owning k1."""
+    s1 = (lg_n + 1) // 2
+    s2 = lg_n - s1
+    n1, n2, g = 1 << s1, 1 << s2, 1 << lg_g
+    return n1, n2, (n1, n2 // g), (n2, n1 // g)
+
+
+def scatter_columns(x, lg_n, lg_g, rank):
+    """This rank's slab of a full natural-order array (test/bench helper)."""
+    n1, n2, (_, c), _ = slab_shapes(lg_n, lg_g)
+    return np.ascontiguousarray(x.reshape(n1, n2)[:, rank * c:(rank + 1) * c])
+
+
+def gather_columns(parts, lg_n, lg_g):
+    """Inverse of the output distribution: parts[r] = [N2][N1/G] -> natural-order array."""
+    n1, n2, _, (_, d) = slab_shapes(lg_n, lg_g)
+    out = np.empty((n2, n1), dtype=parts[0].dtype)
+    for r, p in enumerate(parts):
+        out[:, r * d:(r + 1) * d] = p.reshape(n2, d)
+    return out.reshape(-1)
+
+
+def exchange(staging, world, all_to_all):
+    """The one collective of the sharded NTT: block q of `staging` ([G][...]) goes to rank q.
+    `all_to_all(recv, send)` is torch.distributed.all_to_all_single on NCCL; gloo (CPU tests) has
+    no all-to-all, so there the blocks travel as point-to-point messages."""
+    import torch
+    import torch.distributed as dist
+    recv = torch.empty_like(staging)
+    if world == 1:
+        recv.copy_(staging)
+    elif all_to_all:
+        dist.all_to_all_single(recv, staging)
+    else:
+        rank = dist.get_rank()
+        sb, rb = staging.view(world, -1), recv.view(world, -1)
+        rb[rank].copy_(sb[rank])
+        reqs = []
+        for q in range(world):
+            if q != rank:
+                reqs.append(dist.isend(sb[q].contiguous(), q))
+                reqs.append(dist.irecv(rb[q], q))
+        for r in reqs:
+            r.wait()
+    return recv
+
+
+def ntt_slab(local, lg_n, field, pass_fn, inverse=False, all_to_all=True):
+    """Slab-sharded NTT of 2^lg_n points over the default process group.  `local` is this rank's
+    [N1][N2/G] slab (torch tensor, flat); returns its [N2][N1/G] slab of the result.
+    pass_fn(which, src, dst) runs one local pass (sppark_b200_ntt_slab_pass on a GPU)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    staging = torch.empty_like(local)
+    pass_fn(1, local, staging)
+    recv = exchange(staging, world, all_to_all)
+    pass_fn(2, recv, recv)
+    return recv
+
+
+def gpu_slab_pass(field, lg_n, lg_g, rank, inverse=False):
+    """pass_fn for ntt_slab() on CUDA tensors, on torch's current stream."""
+    import torch
+    from . import _lib
+
+    def run(which, src, dst):
+        with torch.cuda.device(src.device):
+            err = _lib.lib().sppark_b200_ntt_slab_pass(field, which, src.data_ptr(), dst.data_ptr(), lg_n, lg_g,
+                                                       rank, int(inverse), torch.cuda.current_stream().cuda_stream)
+        _lib.check(err)
+    return run

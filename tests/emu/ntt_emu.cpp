@@ -77,6 +77,36 @@ static int emu_run(typename F::T* data, uint32_t lg_n, int order, int inverse, u
     return (int)plan.passes.size();
 }
 
+// one local pass of the slab-sharded transform on a "rank"'s buffers (see make_slab_plan)
+template<class F>
+static int emu_slab_pass(int which, const typename F::T* in, typename F::T* out, uint32_t lg_n, uint32_t lg_g,
+                         uint32_t rank, int inverse, uint32_t lg_tile)
+{
+    typedef typename F::T T;
+    HostTables<F> tb(lg_n, inverse != 0);
+    SlabPlan sp;
+    if (!make_slab_plan(sp, lg_n, lg_g, rank, inverse != 0, lg_tile, F::NTT_MAX_LG_R)) return -1;
+    const Pass& d = which == 1 ? sp.pass1 : sp.pass2;
+    uint32_t nthreads = tile_threads<F>(d), ntiles = 1u << (lg_n - lg_g - d.lg_r - d.lg_w);
+    std::vector<T> smem(smem_elems(d));
+    const KDyn k{d};
+    for (uint32_t t = 0; t < ntiles; t++) {
+        for (uint32_t tid = 0; tid < nthreads; tid++) phase_twiddles<F>(k, tb.view, smem.data(), tid, nthreads);
+        for (uint32_t tid = 0; tid < nthreads; tid++) phase_load<F>(k, d, tb.view, in, smem.data(), t, tid, nthreads);
+        for (uint32_t s = 0; s < step_count<F>(d.lg_r); s++)
+            for (uint32_t tid = 0; tid < nthreads; tid++)
+                phase_step_dyn<F>(k, smem.data(), s * F::LG_EPT, step_log_e<F>(d.lg_r, s), tid);
+        for (uint32_t tid = 0; tid < nthreads; tid++) phase_store<F>(k, d, tb.view, out, smem.data(), t, tid, nthreads);
+    }
+    return 0;
+}
+extern "C" int emu_ntt_slab_gl64(int which, const uint64_t* in, uint64_t* out, uint32_t lg_n, uint32_t lg_g,
+                                 uint32_t rank, int inverse, uint32_t lg_tile)
+{   return emu_slab_pass<gl64>(which, in, out, lg_n, lg_g, rank, inverse, lg_tile);   }
+extern "C" int emu_ntt_slab_bb31(int which, const uint32_t* in, uint32_t* out, uint32_t lg_n, uint32_t lg_g,
+                                 uint32_t rank, int inverse, uint32_t lg_tile)
+{   return emu_slab_pass<bb31>(which, in, out, lg_n, lg_g, rank, inverse, lg_tile);   }
+
 extern "C" int emu_ntt_gl64(uint64_t* data, uint32_t lg_n, int order, int inverse, uint32_t lg_tile)
 {   return emu_run<gl64>(data, lg_n, order, inverse, lg_tile);   }
 extern "C" int emu_ntt_bb31(uint32_t* data, uint32_t lg_n, int order, int inverse, uint32_t lg_tile)

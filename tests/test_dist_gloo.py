@@ -72,3 +72,49 @@ def test_shard_range_properties():
             assert r[0][0] == 0 and r[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
             assert max(h - l for l, h in r) - min(h - l for l, h in r) <= 1
+
+
+def _ntt_worker(rank, world, port, lg, q):
+    sys.path.insert(0, ROOT)
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from oracle import pyoracle as o
+    from sppark_b200 import parallel
+    emu = C.CDLL(os.path.join(ROOT, "tests", "emu", "libntt_emu.so"))
+    emu.emu_ntt_slab_gl64.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_uint]
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lg_g = world.bit_length() - 1
+    rng = np.random.default_rng(77)                      # same full input on every rank
+    x = rng.integers(0, 2**64 - 2**32 + 1, size=1 << lg, dtype=np.uint64)
+    local = torch.from_numpy(parallel.scatter_columns(x, lg, lg_g, rank).reshape(-1).view(np.int64).copy())
+
+    def pass_fn(which, src, dst):                        # CPU single-stepper stands in for the CUDA pass
+        assert emu.emu_ntt_slab_gl64(which, src.data_ptr(), dst.data_ptr(), lg, lg_g, rank, 0, 14) == 0
+
+    mine = parallel.ntt_slab(local, lg, 0, pass_fn, all_to_all=False).numpy().view(np.uint64)
+    gathered = [torch.empty_like(torch.from_numpy(mine.view(np.int64))) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(mine.view(np.int64).copy()))
+    full = parallel.gather_columns([g.numpy().view(np.uint64) for g in gathered], lg, lg_g)
+    q.put((rank, bool(np.array_equal(full, o.ntt_gl64(x, o.NN)))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,lg", [(2, 10), (4, 12)])
+def test_slab_sharded_ntt_over_gloo(world, lg):
+    import subprocess
+    import torch.multiprocessing as mp
+    so = os.path.join(ROOT, "tests", "emu", "libntt_emu.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", so,
+                               os.path.join(ROOT, "tests", "emu", "ntt_emu.cpp")])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ntt_worker, args=(r, world, port, lg, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res)

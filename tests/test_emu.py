@@ -29,6 +29,8 @@ def ntt_emu():
     l.emu_ntt_gl64.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_uint]
     l.emu_ntt_bb31.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_uint]
     l.emu_ntt_256.argtypes = [C.c_int, C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_uint]
+    l.emu_ntt_slab_gl64.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_uint]
+    l.emu_ntt_slab_bb31.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_uint]
     return l
 
 
@@ -80,6 +82,32 @@ def test_ntt_256bit_fields(oracle, ntt_emu, fid, name):
                 y = x.copy()
                 ntt_emu.emu_ntt_256(fid, y.ctypes.data, lg, order, inv, 11 if lg != 8 else 5)
                 assert np.array_equal(y, oracle.ntt_ff(name, x, order, bool(inv))), (lg, order, inv)
+
+
+@pytest.mark.parametrize("lg,lg_g,lg_tile", [(4, 1, 14), (6, 2, 14), (8, 3, 6), (10, 3, 14), (12, 2, 8),
+                                             (14, 3, 14), (7, 1, 5), (6, 3, 14), (2, 1, 14)])
+def test_ntt_slab_sharded(oracle, ntt_emu, lg, lg_g, lg_tile):
+    """G ranks simulated in one process: local pass 1 -> all-to-all (array slicing) -> local pass 2
+    must equal the single-array NN transform."""
+    from sppark_b200 import parallel
+    G = 1 << lg_g
+    rng = np.random.default_rng(lg * 8 + lg_g)
+    for field, fn, ofn, dt, p in (("gl64", ntt_emu.emu_ntt_slab_gl64, oracle.ntt_gl64, np.uint64, 2**64 - 2**32 + 1),
+                                  ("bb31", ntt_emu.emu_ntt_slab_bb31, oracle.ntt_bb31, np.uint32, 0x78000001)):
+        x = rng.integers(0, p, size=1 << lg, dtype=dt)
+        for inv in (0, 1):
+            stag = []
+            for r in range(G):
+                loc = parallel.scatter_columns(x, lg, lg_g, r).reshape(-1).copy()
+                st = np.zeros_like(loc)
+                assert fn(1, loc.ctypes.data, st.ctypes.data, lg, lg_g, r, inv, lg_tile) == 0
+                stag.append(st.reshape(G, -1))
+            outs = []
+            for r in range(G):
+                recv = np.concatenate([stag[q][r] for q in range(G)]).copy()
+                fn(2, recv.ctypes.data, recv.ctypes.data, lg, lg_g, r, inv, lg_tile)
+                outs.append(recv)
+            assert np.array_equal(parallel.gather_columns(outs, lg, lg_g), ofn(x, 0, bool(inv))), (field, inv)
 
 
 def _scalars(vals):

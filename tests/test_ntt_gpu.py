@@ -208,3 +208,30 @@ def test_ntt_256bit_2pow22_roundtrip():
     ntt.NTT(0, y, ntt.NR, field=ntt.BLS12_381_FR)
     ntt.iNTT(0, y, ntt.RN, field=ntt.BLS12_381_FR)
     assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("field,lg,lg_g", [("gl64", 16, 1), ("gl64", 20, 3), ("bb31", 18, 2), ("gl64", 24, 3)])
+def test_slab_sharded_transform_on_one_gpu(oracle, field, lg, lg_g):
+    """The multi-GPU NTT with its G ranks run one after another on this GPU (the exchange is a
+    tensor shuffle): both CUDA passes + layouts against the oracle's single-array transform."""
+    import torch
+    from sppark_b200 import ntt, parallel
+    G = 1 << lg_g
+    fid = 0 if field == "gl64" else 1
+    x = _rand(field, 1 << lg, lg + lg_g)
+    tdt = torch.int64 if field == "gl64" else torch.int32
+    sdt = np.int64 if field == "gl64" else np.int32
+    staged = []
+    for r in range(G):
+        loc = torch.from_numpy(parallel.scatter_columns(x, lg, lg_g, r).reshape(-1).view(sdt).copy()).cuda()
+        st = torch.empty_like(loc)
+        parallel.gpu_slab_pass(fid, lg, lg_g, r)(1, loc, st)
+        staged.append(st.view(G, -1))
+    outs = []
+    for r in range(G):
+        recv = torch.cat([staged[q][r] for q in range(G)]).contiguous()
+        parallel.gpu_slab_pass(fid, lg, lg_g, r)(2, recv, recv)
+        outs.append(recv.cpu().numpy().view(x.dtype))
+    got = parallel.gather_columns(outs, lg, lg_g)
+    ofn = oracle.ntt_gl64 if field == "gl64" else oracle.ntt_bb31
+    assert np.array_equal(got, ofn(x, oracle.NN, nthreads=8))
