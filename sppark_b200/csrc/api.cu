@@ -47,11 +47,12 @@ struct gpu_ptr_inner {
     std::atomic<size_t> ref_cnt;
     int real_id;
 };
-struct gpu_ptr_handle { gpu_ptr_inner* inner; };
+static gpu_ptr_inner* inner_of(const gpu_ptr_t* ref)
+{   return ref ? static_cast<gpu_ptr_inner*>(ref->inner) : nullptr;   }
 
-extern "C" void drop_gpu_ptr_t(gpu_ptr_handle* ref)
+extern "C" void drop_gpu_ptr_t(gpu_ptr_t* ref)
 {
-    gpu_ptr_inner* in = ref ? ref->inner : nullptr;
+    gpu_ptr_inner* in = inner_of(ref);
     if (in && in->ref_cnt.fetch_sub(1, std::memory_order_seq_cst) == 1) {
         int cur = 0;
         (void)cudaGetDevice(&cur);
@@ -63,27 +64,31 @@ extern "C" void drop_gpu_ptr_t(gpu_ptr_handle* ref)
     if (ref) ref->inner = nullptr;
 }
 
-extern "C" gpu_ptr_handle clone_gpu_ptr_t(const gpu_ptr_handle* ref)
+extern "C" gpu_ptr_t clone_gpu_ptr_t(const gpu_ptr_t* ref)
 {
-    if (ref && ref->inner) ref->inner->ref_cnt.fetch_add(1, std::memory_order_relaxed);
-    return gpu_ptr_handle{ref ? ref->inner : nullptr};
+    gpu_ptr_inner* in = inner_of(ref);
+    if (in) in->ref_cnt.fetch_add(1, std::memory_order_relaxed);
+    return gpu_ptr_t{in};
 }
 
 // allocate `bytes` on the current device; {NULL} on failure
-extern "C" gpu_ptr_handle sppark_b200_gpu_ptr_alloc(size_t bytes)
+extern "C" gpu_ptr_t sppark_b200_gpu_ptr_alloc(size_t bytes)
 {
     void* p = nullptr;
     if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
         (void)cudaGetLastError();
-        return gpu_ptr_handle{nullptr};
+        return gpu_ptr_t{nullptr};
     }
-    auto* in = new gpu_ptr_inner{p, {1}, 0};
+    auto* in = new gpu_ptr_inner;
+    in->ptr = p;
+    in->ref_cnt.store(1);
+    in->real_id = 0;
     (void)cudaGetDevice(&in->real_id);
-    return gpu_ptr_handle{in};
+    return gpu_ptr_t{in};
 }
 
-extern "C" void* sppark_b200_gpu_ptr_get(const gpu_ptr_handle* ref)
-{   return ref && ref->inner ? ref->inner->ptr : nullptr;   }
+extern "C" void* sppark_b200_gpu_ptr_get(const gpu_ptr_t* ref)
+{   gpu_ptr_inner* in = inner_of(ref); return in ? in->ptr : nullptr;   }
 
-extern "C" size_t sppark_b200_gpu_ptr_refs(const gpu_ptr_handle* ref)
-{   return ref && ref->inner ? ref->inner->ref_cnt.load() : 0;   }
+extern "C" size_t sppark_b200_gpu_ptr_refs(const gpu_ptr_t* ref)
+{   gpu_ptr_inner* in = inner_of(ref); return in ? in->ref_cnt.load() : 0;   }
