@@ -124,6 +124,50 @@ template<class F> struct xyzz_t {
         ZZZ = ZZZ * p2.ZZZ * PPP;
     }
 
+
+    // ---- variants for the bucket-reduction kernels: the same formulae with every product going
+    // through the ONE shared copy of the Montgomery ladder (F::mul_shared) and the point routine
+    // itself inlined, exactly like madd().  The plain add()/dbl() above inline fourteen ladders
+    // (~100 KB of code): fine for cold code, but the running-sum kernels then stall on
+    // instruction fetch (they ran at 40 % of the accumulate kernel's per-product rate).
+    HD void dbl_hot()
+    {
+        if (is_inf()) return;
+        F U = Y.dbl();
+        F V = F::mul_shared(U, U);
+        F W = F::mul_shared(U, V);
+        F S = F::mul_shared(X, V);
+        F M = F::mul_shared(X, X);
+        M = M.dbl() + M;
+        F X3 = F::mul_shared(M, M) - S - S;
+        Y = F::mul_shared(M, S - X3) - F::mul_shared(W, Y);
+        X = X3;
+        ZZ = F::mul_shared(ZZ, V);
+        ZZZ = F::mul_shared(ZZZ, W);
+    }
+    HD void add_hot(const xyzz_t& p2)
+    {
+        if (p2.is_inf()) return;
+        if (is_inf()) { *this = p2; return; }
+        F U1 = F::mul_shared(X, p2.ZZ);
+        F S1 = F::mul_shared(Y, p2.ZZZ);
+        F P = F::mul_shared(p2.X, ZZ) - U1;
+        F R = F::mul_shared(p2.Y, ZZZ) - S1;
+        if (P.is_zero()) {
+            if (R.is_zero()) dbl_hot();
+            else set_inf();
+            return;
+        }
+        F PP = F::mul_shared(P, P);
+        F PPP = F::mul_shared(P, PP);
+        F Q = F::mul_shared(U1, PP);
+        F X3 = F::mul_shared(R, R) - PPP - Q - Q;
+        Y = F::mul_shared(R, Q - X3) - F::mul_shared(S1, PPP);
+        X = X3;
+        ZZ = F::mul_shared(F::mul_shared(ZZ, p2.ZZ), PP);
+        ZZZ = F::mul_shared(F::mul_shared(ZZZ, p2.ZZZ), PPP);
+    }
+
     // (X*ZZ, Y*ZZZ, ZZ): Z := ZZ  (ec/xyzz_t.hpp:87-90)
     HD jacobian_t<F> to_jacobian() const
     {

@@ -86,7 +86,7 @@ DEV void block_sum(ec::xyzz_t<F>& acc, uint32_t* tree)
     __syncthreads();
     for (uint32_t d = blockDim.x / 2; d > 0; d >>= 1) {
         if (threadIdx.x < d) {
-            acc.add(load_bucket<F>(tree, threadIdx.x + d));
+            acc.add_hot(load_bucket<F>(tree, threadIdx.x + d));
             store_bucket<F>(tree, threadIdx.x, acc);
         }
         __syncthreads();
@@ -130,10 +130,10 @@ heavy_fold_kernel(const Config cfg, const uint32_t* ctrl, const uint32_t* heavy_
         ec::xyzz_t<F> acc;
         acc.set_inf();
         for (uint32_t k = threadIdx.x; k < nch; k += blockDim.x)
-            acc.add(load_bucket<F>(partials, first + k));
+            acc.add_hot(load_bucket<F>(partials, first + k));
         block_sum<F>(acc, tree);
         if (threadIdx.x == 0) {
-            if (cfg.merge) acc.add(load_bucket<F>(buckets, t));
+            if (cfg.merge) acc.add_hot(load_bucket<F>(buckets, t));
             store_bucket<F>(buckets, t, acc);
         }
         __syncthreads();

@@ -219,8 +219,8 @@ HD void reduce1_body(const Config& cfg, const uint32_t* buckets, uint32_t lg_l,
     acc.set_inf();
     res.set_inf();
     for (uint32_t k = 1u << lg_l; k-- > 0;) {
-        acc.add(load_bucket<F>(buckets, first + k));
-        res.add(acc);
+        acc.add_hot(load_bucket<F>(buckets, first + k));
+        res.add_hot(acc);
     }
     store_bucket<F>(outR, item, res);
     store_bucket<F>(outS, item, acc);
@@ -238,12 +238,12 @@ HD void combine_body(const uint32_t* inR, const uint32_t* inS, uint32_t G, uint3
     weighted.set_inf();
     rsum.set_inf();
     for (uint32_t i = G; i-- > 0;) {
-        rsum.add(load_bucket<F>(inR, first + i));
-        acc.add(load_bucket<F>(inS, first + i));
-        if (i) weighted.add(acc);                    // sum_{i>=1} i*S_i
+        rsum.add_hot(load_bucket<F>(inR, first + i));
+        acc.add_hot(load_bucket<F>(inS, first + i));
+        if (i) weighted.add_hot(acc);                    // sum_{i>=1} i*S_i
     }
-    for (uint32_t d = 0; d < lg_span; d++) weighted.dbl();
-    rsum.add(weighted);
+    for (uint32_t d = 0; d < lg_span; d++) weighted.dbl_hot();
+    rsum.add_hot(weighted);
     store_bucket<F>(outR, item, rsum);
     store_bucket<F>(outS, item, acc);
 }
@@ -254,8 +254,8 @@ HD void finish_body(const Config& cfg, const uint32_t* winR, uint32_t* out_jacob
 {
     ec::xyzz_t<F> acc = load_bucket<F>(winR, cfg.nwins - 1);
     for (uint32_t w = cfg.nwins - 1; w-- > 0;) {
-        for (uint32_t d = 0; d < cfg.wbits; d++) acc.dbl();
-        acc.add(load_bucket<F>(winR, w));
+        for (uint32_t d = 0; d < cfg.wbits; d++) acc.dbl_hot();
+        acc.add_hot(load_bucket<F>(winR, w));
     }
     ec::jacobian_t<F> j = acc.to_jacobian();
 #pragma unroll
