@@ -63,10 +63,11 @@ scan_kernel(const Config cfg, const uint32_t* counts, uint32_t* offsets, uint32_
     }
 }
 
-static __global__ void scatter_kernel(const Config cfg, const uint32_t* scalars, uint32_t* cursor, uint32_t* sorted)
+static __global__ void scatter_kernel(const Config cfg, const uint32_t* scalars, uint32_t* cursor, uint32_t* sorted,
+                                      uint32_t w0, uint32_t w1)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cfg.npoints; i += gridDim.x * blockDim.x)
-        scatter_body(cfg, scalars, cursor, sorted, i);
+        scatter_body(cfg, scalars, cursor, sorted, i, w0, w1);
 }
 
 template<class F>
@@ -246,8 +247,23 @@ public:
         COUNT_LAUNCH();
         scan_kernel<<<cfg.nwins, 1024, 0, stream>>>(cfg, j.counts, j.offsets, j.cursor, j.ctrl, j.heavy_list, j.chunk_map);
         COUNT_LAUNCH();
-        scatter_kernel<<<nblk, 256, 0, stream>>>(cfg, d_scalars, j.cursor, j.sorted);
-        COUNT_LAUNCH();
+        // The scatter writes 4 random bytes per (point, window): with all windows in flight the
+        // write set (4*n bytes per window) thrashes L2 and every store costs a 32-byte sector
+        // read + write-back in DRAM (ncu: 68 B of DRAM traffic per entry, profiles/msm_sort_r01.md).
+        // One launch per window confines the write set to one window's slots (4*n bytes, resident
+        // in the 126 MB L2 up to n = 2^24) at the price of re-reading the scalars per window:
+        // 11.4 -> 7.1 ms at 2^24, 44 -> 25 ms at 2^26.
+        bool per_window = n >= (1u << 18);
+        if (const char* env = getenv("SPPARK_B200_MSM_SCATTER")) per_window = atoi(env) != 0;
+        if (per_window) {
+            for (uint32_t w = 0; w < cfg.nwins; w++) {
+                scatter_kernel<<<nblk, 256, 0, stream>>>(cfg, d_scalars, j.cursor, j.sorted, w, w + 1);
+                COUNT_LAUNCH();
+            }
+        } else {
+            scatter_kernel<<<nblk, 256, 0, stream>>>(cfg, d_scalars, j.cursor, j.sorted, 0, cfg.nwins);
+            COUNT_LAUNCH();
+        }
         CUDA_OK(cudaGetLastError());
 
         g_profile.mark("accumulate", stream);

@@ -89,13 +89,14 @@ HD void count_body(const Config& cfg, const uint32_t* scalars, uint32_t* counts,
     }
 }
 
+// windows [w0, w1) only: digits below w0 are still walked for their carry
 HD void scatter_body(const Config& cfg, const uint32_t* scalars, uint32_t* cursor,
-                     uint32_t* sorted, uint32_t i)
+                     uint32_t* sorted, uint32_t i, uint32_t w0, uint32_t w1)
 {
     Digits d(scalars + 8 * (size_t)i);
-    for (uint32_t w = 0; w < cfg.nwins; w++) {
+    for (uint32_t w = 0; w < w1; w++) {
         uint32_t b, neg;
-        if (d.next(w, cfg.wbits, b, neg)) {
+        if (d.next(w, cfg.wbits, b, neg) && w >= w0) {
             uint32_t pos = atomic_inc(&cursor[((size_t)w << cfg.lg_nb) + b]);
             sorted[(size_t)w * cfg.npoints + pos] = i | (neg << 31);
         }

@@ -45,7 +45,7 @@ static void emu_msm(uint32_t* out, const uint32_t* points_all, size_t npoints_al
             run += counts[t];
         }
     }
-    for (uint32_t i = 0; i < npoints; i++) scatter_body(cfg, scalars, cursor.data(), sorted.data(), i);
+    for (uint32_t i = 0; i < npoints; i++) scatter_body(cfg, scalars, cursor.data(), sorted.data(), i, 0, cfg.nwins);
     uint32_t task_counter = 0;
     accumulate_body<F>(cfg, points, sorted.data(), offsets.data(), counts.data(), buckets.data(), &task_counter);
     const uint32_t HT = 8;                                        // heavy_kernel with 8 "threads"
