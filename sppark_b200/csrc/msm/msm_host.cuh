@@ -29,12 +29,28 @@ RustError msm_host(void* out, const void* points, size_t npoints, const void* sc
         const stream_t &compute = gpu[0], &copy = gpu[1];
         const bool packed = stride == PB && !has_flag;
 
-        size_t nslices = npoints >= (1u << 24) ? 4 : npoints >= (1u << 22) ? 2 : 1;
-        if (const char* env = getenv("SPPARK_B200_MSM_SLICES")) nslices = std::max(1, atoi(env));
-        size_t slice_n = (npoints + nslices - 1) / nslices;
-        slice_n = (slice_n + 31) & ~(size_t)31;
-        nslices = (npoints + slice_n - 1) / slice_n;
-        const size_t nbuf = nslices > 1 ? 2 : 1;
+        // slice schedule: short first slices (the GPU idles while slice 0 crosses PCIe), then
+        // longer ones (fewer bucket reloads); slice k+1 is copied while slice k is computed
+        std::vector<size_t> sched;
+        if (const char* env = getenv("SPPARK_B200_MSM_SLICES")) {
+            size_t k = std::max(1, atoi(env)), each = ((npoints + k - 1) / k + 31) & ~(size_t)31;
+            for (size_t done = 0; done < npoints; done += each) sched.push_back(std::min(each, npoints - done));
+        } else if (npoints >= (1u << 22)) {
+            const size_t e = (npoints / 8 + 31) & ~(size_t)31;
+            for (size_t part : {e, e, 2 * e}) sched.push_back(part);
+            sched.push_back(npoints - 4 * e);
+        } else {
+            sched.push_back(npoints);
+        }
+        const size_t nslices = sched.size(), nbuf = nslices > 1 ? 2 : 1;
+        const size_t slice_n = *std::max_element(sched.begin(), sched.end());
+        const bool pageable = stager_t::is_pageable(points) || stager_t::is_pageable(scalars);
+        std::unique_lock<std::mutex> stage_lock(gpu.stage_mtx, std::defer_lock);
+        if (pageable) stage_lock.lock();
+        auto upload = [&](void* dst, const void* src, size_t bytes) {
+            if (pageable) gpu.stager().HtoD(copy, dst, src, bytes);
+            else copy.HtoD(dst, src, bytes);
+        };
 
         dev_ptr_t<uint32_t> d_out(JB / 4, compute);
         dev_ptr_t<uint32_t> d_points(nbuf * slice_n * (PB / 4), compute), d_scalars(nbuf * slice_n * 8, compute);
@@ -47,17 +63,18 @@ RustError msm_host(void* out, const void* points, size_t npoints, const void* sc
 
         msm::msm_t<F> m(gpu);
         auto job = m.begin(npoints, slice_n, compute);
-        for (size_t k = 0; k < nslices; k++) {
-            const size_t b = k & (nbuf - 1), first = k * slice_n, n = std::min(slice_n, npoints - first);
+        size_t first = 0;
+        for (size_t k = 0; k < nslices; first += sched[k], k++) {
+            const size_t b = k & (nbuf - 1), n = sched[k];
             uint32_t* dp = d_points + b * slice_n * (PB / 4);
             uint32_t* ds = d_scalars + b * slice_n * 8;
             if (k >= nbuf) CUDA_OK(cudaStreamWaitEvent(copy, consumed[b], 0));   // buffer free again
-            copy.HtoD(ds, (const uint8_t*)scalars + first * 32, n * 32);
+            upload(ds, (const uint8_t*)scalars + first * 32, n * 32);
             if (packed) {
-                copy.HtoD(dp, (const uint8_t*)points + first * PB, n * PB);
+                upload(dp, (const uint8_t*)points + first * PB, n * PB);
             } else {
                 uint8_t* dr = d_raw + b * slice_n * stride;
-                copy.HtoD(dr, (const uint8_t*)points + first * stride, n * stride);
+                upload(dr, (const uint8_t*)points + first * stride, n * stride);
                 uint32_t blocks = (uint32_t)std::min<size_t>((n + 255) / 256, (size_t)gpu.sm_count() * 8);
                 msm::pack_points_kernel<<<blocks, 256, 0, copy>>>(dr, stride, PB / 4, has_flag, dp, (uint32_t)n);
                 COUNT_LAUNCH();

@@ -13,7 +13,10 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -85,6 +88,100 @@ public:
     void sync() const { CUDA_OK(cudaStreamSynchronize(s)); }
 };
 
+// ---- pageable host memory -> device, at pinned-memory speed ---------------------------------
+// cudaMemcpyAsync from pageable memory is staged by the driver through a small bounce buffer on
+// the calling thread (~10 GB/s).  The reference's callers (Rust Vec, Go slices) hand over
+// pageable memory, so the host-pointer entry points stage it themselves: worker threads copy
+// 32 MiB chunks into a ring of pinned buffers while earlier chunks are in flight on the copy
+// engine.  Reference counterpart: the host thread pool of gpu_t (util/gpu_t.cuh:176-186,
+// util/thread_pool_t.hpp), used there for the post-processing of results.
+class stager_t {
+    static constexpr size_t CHUNK = (size_t)32 << 20;
+    static constexpr int NBUF = 4, NTHREADS = 8;
+    uint8_t* buf[NBUF] = {};
+    cudaEvent_t ev[NBUF] = {};
+    int next = 0;
+    std::vector<std::thread> workers;
+    std::mutex mtx;
+    std::condition_variable cv_work, cv_done;
+    struct job_t { uint8_t* dst; const uint8_t* src; size_t len; };
+    std::vector<job_t> jobs;
+    size_t pending = 0;
+    bool quit = false;
+
+    void worker()
+    {
+        for (;;) {
+            job_t j;
+            {
+                std::unique_lock<std::mutex> lk(mtx);
+                cv_work.wait(lk, [&] { return quit || !jobs.empty(); });
+                if (quit && jobs.empty()) return;
+                j = jobs.back();
+                jobs.pop_back();
+            }
+            memcpy(j.dst, j.src, j.len);
+            {
+                std::lock_guard<std::mutex> lk(mtx);
+                if (--pending == 0) cv_done.notify_all();
+            }
+        }
+    }
+    void parallel_copy(uint8_t* dst, const uint8_t* src, size_t len)
+    {
+        const size_t piece = (len + NTHREADS - 1) / NTHREADS;
+        {
+            std::lock_guard<std::mutex> lk(mtx);
+            for (size_t off = 0; off < len; off += piece) {
+                jobs.push_back({dst + off, src + off, std::min(piece, len - off)});
+                pending++;
+            }
+        }
+        cv_work.notify_all();
+        std::unique_lock<std::mutex> lk(mtx);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+
+public:
+    stager_t()
+    {
+        for (int i = 0; i < NBUF; i++) {
+            CUDA_OK(cudaHostAlloc((void**)&buf[i], CHUNK, cudaHostAllocDefault));
+            CUDA_OK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+        for (int i = 0; i < NTHREADS; i++) workers.emplace_back([this] { worker(); });
+    }
+    ~stager_t()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mtx);
+            quit = true;
+        }
+        cv_work.notify_all();
+        for (auto& t : workers) t.join();
+        for (int i = 0; i < NBUF; i++) { cudaFreeHost(buf[i]); cudaEventDestroy(ev[i]); }
+    }
+    static bool is_pageable(const void* p)
+    {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return true; }
+        return a.type == cudaMemoryTypeUnregistered;
+    }
+    // dst (device) <- src (pageable host), enqueued on `s`; returns once the LAST chunk has been
+    // handed to the copy engine (the source may not be modified until the stream is synchronised)
+    void HtoD(cudaStream_t s, void* dst, const void* src, size_t bytes)
+    {
+        for (size_t off = 0; off < bytes; off += CHUNK) {
+            const int b = next++ % NBUF;
+            const size_t len = std::min(CHUNK, bytes - off);
+            CUDA_OK(cudaEventSynchronize(ev[b]));            // this ring slot has left the host
+            parallel_copy(buf[b], (const uint8_t*)src + off, len);
+            CUDA_OK(cudaMemcpyAsync((uint8_t*)dst + off, buf[b], len, cudaMemcpyHostToDevice, s));
+            CUDA_OK(cudaEventRecord(ev[b], s));
+        }
+    }
+};
+
 // stream-ordered scratch buffer
 template<typename T> class dev_ptr_t {
     T* p;
@@ -104,6 +201,13 @@ class gpu_t {
 public:
     std::mutex cache_mtx;                                   // guards per-device table caches
     std::map<uint64_t, void*> cache;
+    mutable std::mutex stage_mtx;                           // one pageable upload at a time
+    mutable std::unique_ptr<stager_t> stage;
+    stager_t& stager() const
+    {
+        if (!stage) stage.reset(new stager_t());
+        return *stage;
+    }
 
     gpu_t(int id, int cid) : gpu_id(id), cuda_id(cid)
     {
