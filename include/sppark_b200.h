@@ -105,6 +105,13 @@ RustError sppark_b200_ntt(int field, size_t device_id, void *inout, uint32_t lg_
 RustError sppark_b200_ntt_dev(int field, void *d_inout, uint32_t lg_domain_size,
                               int ntt_order, int ntt_direction, int ntt_type, void *stream);
 
+/* Low-degree extension, NTT::LDE / NTT::LDE_aux (ntt/ntt.cuh:247-340):
+ * inout holds 2^lg evaluations and has room for 2^(lg + lg_blowup) elements; it returns the
+ * evaluations of the same polynomial on the coset group_gen*<w_(2^(lg+lg_blowup))>, natural order.
+ * aux_out (NULL or 2^lg elements) receives the coefficients in natural order. */
+RustError sppark_b200_lde(int field, size_t device_id, void *inout, uint32_t lg_domain_size,
+                          uint32_t lg_blowup, void *aux_out);
+
 /* Slab-sharded NTT over G = 2^lg_g GPUs with ONE all-to-all (new; the reference has no multi-GPU
  * path).  N = N1 x N2, N1 = 2^ceil(lg/2).  Rank r owns input columns x[j1*N2 + j2],
  * j2 in [r*N2/G, (r+1)*N2/G), as a row-major [N1][N2/G] device array, and ends with the output

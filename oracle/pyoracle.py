@@ -162,6 +162,16 @@ def ntt_ff(field, a, order=NN, inverse=False, coset=False, algo="fast"):
     return a
 
 
+def lde(field, evals, lg_blowup):
+    """Definition of NTT::LDE (ntt/ntt.cuh:247-340): coefficients c = iNTT(evals); the extended
+    array is the coset NTT, over the 2^(lg+lg_blowup) domain, of c padded with zeros."""
+    fn = {"gl64": ntt_gl64, "bb31": ntt_bb31}.get(field) or (lambda a, *k, **kw: ntt_ff(field, a, *k, **kw))
+    c = fn(evals, NN, True)
+    ext = np.zeros((c.shape[0] << lg_blowup,) + c.shape[1:], dtype=c.dtype)
+    ext[:c.shape[0]] = c
+    return fn(ext, NN, False, True), c
+
+
 # ---------------------------------------------------------------- reference builds (_ref)
 def ref_path(name):
     p = os.path.join(REF_DIR, name)

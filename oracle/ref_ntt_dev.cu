@@ -37,3 +37,11 @@ extern "C" int ref_ntt_dev_async(void* d_inout, uint32_t lg, int order, int dire
         return e.code();
     }
 }
+
+/* the reference's own low-degree extension (ntt/ntt.cuh:336-338), host buffer of 2^(lg+lb) elements */
+extern "C" int ref_lde(void* inout, uint32_t lg, uint32_t lg_blowup)
+{
+    RustError e = NTT::LDE(select_gpu(0), (fr_t*)inout, lg, lg_blowup);
+    if (e.message) free(e.message);
+    return e.code;
+}

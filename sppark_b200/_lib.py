@@ -31,6 +31,7 @@ _SIGS = {
     "compute_ntt": [C.c_size_t, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int],
     "sppark_b200_ntt": [C.c_int, C.c_size_t, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int],
     "sppark_b200_ntt_dev": [C.c_int, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p],
+    "sppark_b200_lde": [C.c_int, C.c_size_t, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p],
     "sppark_b200_ntt_slab_pass": [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                   C.c_int, C.c_void_p],
     "sppark_b200_msm": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t],

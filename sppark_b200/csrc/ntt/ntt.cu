@@ -136,6 +136,30 @@ static RustError ntt_slab(int which, const void* d_in, void* d_out, uint32_t lg,
     }
 }
 
+template<class F>
+static RustError lde_host(size_t device_id, void* inout, uint32_t lg, uint32_t lg_blowup, void* aux)
+{
+    try {
+        return ntt::NTT<F>::LDE(select_gpu((int)device_id), (typename F::T*)inout, lg, lg_blowup, (typename F::T*)aux);
+    } catch (const cuda_error& e) {
+        return rust_err(e.code(), e.what());
+    } catch (const std::exception& e) {
+        return rust_err(-1, e.what());
+    }
+}
+
+extern "C" RustError sppark_b200_lde(int field, size_t device_id, void* inout, uint32_t lg, uint32_t lg_blowup, void* aux_out)
+{
+    switch (field) {
+    case SPPARK_FIELD_GL64: return lde_host<gl64>(device_id, inout, lg, lg_blowup, aux_out);
+    case SPPARK_FIELD_BB31: return lde_host<bb31>(device_id, inout, lg, lg_blowup, aux_out);
+    case SPPARK_FIELD_BLS12_381_FR: return lde_host<ff::bls12_381_fr_ntt>(device_id, inout, lg, lg_blowup, aux_out);
+    case SPPARK_FIELD_PALLAS_FR: return lde_host<ff::pallas_fr_ntt>(device_id, inout, lg, lg_blowup, aux_out);
+    case SPPARK_FIELD_VESTA_FR: return lde_host<ff::vesta_fr_ntt>(device_id, inout, lg, lg_blowup, aux_out);
+    default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_lde: unknown field");
+    }
+}
+
 extern "C" RustError sppark_b200_ntt_slab_pass(int field, int which, const void* d_in, void* d_out,
                                                uint32_t lg, uint32_t lg_g, uint32_t rank, int direction, void* stream)
 {

@@ -116,6 +116,32 @@ __global__ void coset_kernel(typename F::T* data, uint32_t lg_n, bool bitrev,
     }
 }
 
+// LDE: zero-stuffing blow-up fused with the coset shift (reference:
+// LDE_spread_distribute_powers, ntt/kernels.cu:155-237).  `in` holds the n coefficients in
+// bit-reversed order (the output of an NR inverse transform); out[i << lg_blowup] = in[i] *
+// g^bitrev(i), every other slot of the (n << lg_blowup)-element array is zero -- i.e. the
+// coefficients of P(g*x) in the bit-reversed order of the extended domain.
+template<class F>
+__global__ void lde_spread_kernel(typename F::T* out, const typename F::T* in, uint32_t lg_n, uint32_t lg_blowup,
+                                  const typename F::T* g0, const typename F::T* g1, const typename F::T* g2)
+{
+    typedef typename F::T T;
+    const size_t n_ext = (size_t)1 << (lg_n + lg_blowup);
+    const uint32_t mask = (1u << lg_blowup) - 1;
+    T zero = F::sub(F::one(), F::one());
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_ext; i += (size_t)gridDim.x * blockDim.x) {
+        T x = zero;
+        if ((i & mask) == 0) {
+            uint32_t src = (uint32_t)(i >> lg_blowup), e = brev32(src, lg_n);
+            x = F::mul(F::load(in[src]), g0[e & 4095]);
+            if (e >> 12) x = F::mul(x, g1[(e >> 12) & 4095]);
+            if (e >> 24) x = F::mul(x, g2[e >> 24]);
+            x = F::canon(x);
+        }
+        out[i] = x;
+    }
+}
+
 template<class F> struct FieldId;     // specialised in ntt.cu: cache key + shared-memory tile
 
 template<class F>
@@ -276,6 +302,47 @@ public:
         CUDA_OK(cudaGetLastError());
     }
 
+    // Low-degree extension (reference: NTT::LDE / LDE_aux, ntt/ntt.cuh:247-340): `inout` holds
+    // 2^lg_n evaluations on the size-2^lg_n domain and has room for 2^(lg_n+lg_blowup) elements;
+    // on return it holds the evaluations of the same polynomial on the coset g*<w_ext> of the
+    // extended domain, natural order.  aux_out (optional, 2^lg_n elements) receives the
+    // polynomial's coefficients in natural order, as LDE_aux does.
+    static RustError LDE(const gpu_t& gpu, T* inout, uint32_t lg_n, uint32_t lg_blowup, T* aux_out = nullptr)
+    {
+        const uint32_t lg_ext = lg_n + lg_blowup;
+        if (lg_n == 0 || lg_ext > (uint32_t)F::MAX_LG || lg_ext > 30)
+            return rust_err(-(int)cudaErrorInvalidValue, "LDE: lg_domain_size + lg_blowup out of range for this field");
+        try {
+            gpu.select();
+            const stream_t& s = gpu[0];
+            const size_t n = (size_t)1 << lg_n, n_ext = (size_t)1 << lg_ext;
+            dev_ptr_t<T> d_in(n, s), d_ext(n_ext, s);
+            s.HtoD(d_in, inout, n * sizeof(T));
+            NTT_internal(gpu, d_in, lg_n, InputOutputOrder::NR, Direction::inverse, Type::standard, s);
+            if (aux_out) {                                 // natural-order coefficients
+                dev_ptr_t<T> d_aux(n, s);
+                CUDA_OK(cudaMemcpyAsync(d_aux, d_in, n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+                // bit-reversed -> natural = an RN round trip is overkill; redo the inverse as NN
+                s.HtoD(d_aux, inout, n * sizeof(T));
+                NTT_internal(gpu, d_aux, lg_n, InputOutputOrder::NN, Direction::inverse, Type::standard, s);
+                s.DtoH(aux_out, d_aux, n * sizeof(T));
+                s.sync();
+            }
+            const CosetTables& ct = coset_tables(gpu, false, s);
+            uint32_t blocks = (uint32_t)std::min<size_t>((n_ext + 255) / 256, (size_t)gpu.sm_count() * 16);
+            lde_spread_kernel<F><<<blocks, 256, 0, s>>>(d_ext, d_in, lg_n, lg_blowup, ct.g0, ct.g1, ct.g2);
+            COUNT_LAUNCH();
+            CUDA_OK(cudaGetLastError());
+            NTT_internal(gpu, d_ext, lg_ext, InputOutputOrder::RN, Direction::forward, Type::standard, s);
+            s.DtoH(inout, d_ext, n_ext * sizeof(T));
+            s.sync();
+        } catch (const cuda_error& e) {
+            try { gpu.sync(); } catch (...) {}
+            return rust_err(e.code(), e.what());
+        }
+        return rust_ok();
+    }
+
     static void Base_dev_ptr(const gpu_t& gpu, cudaStream_t stream, T* d_inout, uint32_t lg_n,
                              InputOutputOrder order, Direction direction, Type type)
     {   NTT_internal(gpu, d_inout, lg_n, order, direction, type, stream);   }
@@ -292,9 +359,19 @@ public:
             const stream_t& s = gpu[0];
             size_t n = (size_t)1 << lg_n;
             dev_ptr_t<T> d_inout(n, s);
-            s.HtoD(d_inout, inout, n * sizeof(T));
+            // pageable buffers (what the reference's Rust / Go callers pass) are staged through
+            // pinned memory by worker threads; registered buffers go straight to the copy engine
+            const bool pageable = n * sizeof(T) >= ((size_t)8 << 20) && stager_t::is_pageable(inout);
+            std::unique_lock<std::mutex> stage_lock(gpu.stage_mtx, std::defer_lock);
+            if (pageable) {
+                stage_lock.lock();
+                gpu.stager().HtoD(s, d_inout, inout, n * sizeof(T));
+            } else {
+                s.HtoD(d_inout, inout, n * sizeof(T));
+            }
             NTT_internal(gpu, d_inout, lg_n, order, direction, type, s);
-            s.DtoH(inout, d_inout, n * sizeof(T));
+            if (pageable) gpu.stager().DtoH(s, inout, d_inout, n * sizeof(T));
+            else s.DtoH(inout, d_inout, n * sizeof(T));
             s.sync();
         } catch (const cuda_error& e) {
             try { gpu.sync(); } catch (...) {}

@@ -180,6 +180,34 @@ public:
             CUDA_OK(cudaEventRecord(ev[b], s));
         }
     }
+    // dst (pageable host) <- src (device): chunks land in the pinned ring and are copied out by
+    // the workers while the next chunk is on the wire.  Returns when dst is complete.
+    void DtoH(cudaStream_t s, void* dst, const void* src, size_t bytes)
+    {
+        size_t issued = 0, drained = 0;
+        int slot_of[NBUF];
+        size_t off_of[NBUF], len_of[NBUF];
+        int head = 0, tail = 0, inflight = 0;
+        while (drained < bytes) {
+            while (inflight < NBUF && issued < bytes) {
+                const int b = next++ % NBUF;
+                const size_t len = std::min(CHUNK, bytes - issued);
+                CUDA_OK(cudaEventSynchronize(ev[b]));
+                CUDA_OK(cudaMemcpyAsync(buf[b], (const uint8_t*)src + issued, len, cudaMemcpyDeviceToHost, s));
+                CUDA_OK(cudaEventRecord(ev[b], s));
+                slot_of[head] = b; off_of[head] = issued; len_of[head] = len;
+                head = (head + 1) % NBUF;
+                issued += len;
+                inflight++;
+            }
+            const int b = slot_of[tail];
+            CUDA_OK(cudaEventSynchronize(ev[b]));
+            parallel_copy((uint8_t*)dst + off_of[tail], buf[b], len_of[tail]);
+            drained += len_of[tail];
+            tail = (tail + 1) % NBUF;
+            inflight--;
+        }
+    }
 };
 
 // stream-ordered scratch buffer

@@ -56,6 +56,25 @@ def coset_iNTT(device_id, inout, order=NN, field=None):
     _run(device_id, inout, order, INVERSE, COSET, field)
 
 
+def LDE(device_id, evals, lg_blowup, field=None, want_coefficients=False):
+    """NTT::LDE (ntt/ntt.cuh:336-338): evaluations on the 2^lg domain -> evaluations on the coset
+    of the 2^(lg+lg_blowup) domain (natural order).  Returns the extended array (and the natural
+    -order coefficients if asked, as LDE_aux does)."""
+    field = _field_of(evals) if field is None else field
+    n = evals.size if field in (GL64, BB31) else evals.shape[0]
+    if n & (n - 1):
+        raise ValueError("inout.len() is not power of 2")
+    lg = n.bit_length() - 1
+    shape = (n << lg_blowup,) + tuple(evals.shape[1:])
+    ext = np.zeros(shape, dtype=evals.dtype)
+    ext[:n] = evals
+    aux = np.zeros_like(evals) if want_coefficients else None
+    err = _lib.lib().sppark_b200_lde(field, device_id, ext.ctypes.data, lg, lg_blowup,
+                                     aux.ctypes.data if aux is not None else None)
+    _lib.check(err)
+    return (ext, aux) if want_coefficients else ext
+
+
 def ntt_dev(tensor, order=NN, direction=FORWARD, typ=STANDARD, field=None, stream=None):
     """NTT::Base_dev_ptr (ntt/ntt.cuh:344-350): in place on a CUDA torch tensor, enqueued on
     torch's current stream (or `stream`), not synchronised."""

@@ -83,6 +83,21 @@ def gen_gpu(outdir):
     np.savez_compressed(os.path.join(outdir, "ntt_ref_gpu.npz"), **out)
     print("wrote ntt_ref_gpu.npz")
 
+    # low-degree extension, Goldilocks (NTT::LDE)
+    lib = C.CDLL(o.ref_path("libref_ntt_gl64_gpu.so"))
+    lib.ref_lde.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    rng = np.random.default_rng(21)
+    out = {}
+    for lg, lb in ((1, 1), (3, 1), (6, 2), (10, 1), (12, 3)):
+        x = rng.integers(0, GL_P, size=1 << lg, dtype=np.uint64)
+        buf = np.zeros(1 << (lg + lb), dtype=np.uint64)
+        buf[: 1 << lg] = x
+        assert lib.ref_lde(buf.ctypes.data, lg, lb) == 0
+        out[f"in_{lg}_{lb}"] = x
+        out[f"out_{lg}_{lb}"] = buf
+    np.savez_compressed(os.path.join(outdir, "lde_ref_gpu.npz"), **out)
+    print("wrote lde_ref_gpu.npz")
+
     # 256-bit "wide" NTT: BLS12-381 scalar field, Montgomery residues
     lib = C.CDLL(o.ref_path("libref_ntt_bls12_381_gpu.so"))
     lib.compute_ntt.restype = RE

@@ -257,3 +257,34 @@ def test_gpu_ptr_handles():
     _lib.check(l.sppark_b200_ntt_dev(0, dptr, 10, 0, 0, 0, None)) if False else None
     l.drop_gpu_ptr_t(C.byref(h2))
     assert not h2.inner
+
+
+@pytest.mark.parametrize("field,fid", [("gl64", 0), ("bb31", 1), ("bls12_381_fr", 2)])
+def test_lde_matches_definition(oracle, field, fid):
+    """NTT::LDE / LDE_aux (SURVEY section 8f row 1): extended coset evaluations + coefficients."""
+    import random
+    from sppark_b200 import ntt
+    rnd = random.Random(fid)
+    for lg, lb in ((1, 1), (5, 1), (8, 3), (12, 2), (13, 1), (16, 2)):
+        if field in ("gl64", "bb31"):
+            x = _rand(field, 1 << lg, lg * 7 + lb)
+        else:
+            p = oracle.ff_consts(field)["p"]
+            if lg > 12:
+                continue
+            x = np.array([oracle.int_to_limbs(rnd.randrange(p), 4) for _ in range(1 << lg)], dtype=np.uint64)
+        ext, coeffs = ntt.LDE(0, x, lb, field=fid, want_coefficients=True)
+        want_ext, want_c = oracle.lde(field, x, lb)
+        assert np.array_equal(coeffs, want_c), (field, lg, lb)
+        assert np.array_equal(ext, want_ext), (field, lg, lb)
+
+
+def test_lde_matches_reference_gpu_golden():
+    import os
+    from sppark_b200 import ntt
+    path = os.path.join(os.path.dirname(__file__), "golden", "lde_ref_gpu.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden not recorded yet")
+    g = np.load(path)
+    for lg, lb in ((1, 1), (3, 1), (6, 2), (10, 1), (12, 3)):
+        assert np.array_equal(ntt.LDE(0, g[f"in_{lg}_{lb}"], lb), g[f"out_{lg}_{lb}"]), (lg, lb)

@@ -176,3 +176,14 @@ def test_ntt256_fast_equals_definition(oracle, field):
                     assert np.array_equal(oracle.ntt_ff(field, x, order, inv, coset, "dft"),
                                           oracle.ntt_ff(field, x, order, inv, coset, "fast"))
         assert np.array_equal(oracle.ntt_ff(field, oracle.ntt_ff(field, x, oracle.NR), oracle.RN, True), x)
+
+
+def test_oracle_lde_matches_reference_gpu_golden(oracle):
+    """NTT::LDE of the reference (Goldilocks) recorded on a B200 vs the oracle's definition."""
+    path = os.path.join(GOLD, "lde_ref_gpu.npz")
+    if not os.path.exists(path):
+        pytest.skip("reference-GPU golden not recorded yet")
+    g = np.load(path)
+    for lg, lb in ((1, 1), (3, 1), (6, 2), (10, 1), (12, 3)):
+        ext, _ = oracle.lde("gl64", g[f"in_{lg}_{lb}"], lb)
+        assert np.array_equal(ext, g[f"out_{lg}_{lb}"]), (lg, lb)
