@@ -21,7 +21,6 @@ static __global__ void count_kernel(const Config cfg, const uint32_t* scalars, u
         count_body(cfg, scalars, counts, i);
 }
 
-constexpr uint32_t HEAVY_CHUNK = 16384;     // entries of a heavy bucket folded by one CTA
 
 // control block: [0] task counter, [1] #heavy buckets, [2] #chunks
 // heavy bucket h: heavy_list[3h] = slot, [3h+1] = first chunk, [3h+2] = #chunks; chunk_map[c] = h
@@ -52,7 +51,7 @@ scan_kernel(const Config cfg, const uint32_t* counts, uint32_t* offsets, uint32_
         offsets[base + b] = run;
         cursor[base + b] = run;
         if (c > cfg.heavy) {
-            uint32_t h = atomicAdd(&ctrl[1], 1), nch = (c + HEAVY_CHUNK - 1) / HEAVY_CHUNK;
+            uint32_t h = atomicAdd(&ctrl[1], 1), nch = (c + cfg.heavy_chunk - 1) / cfg.heavy_chunk;
             uint32_t first_chunk = atomicAdd(&ctrl[2], nch);
             heavy_list[3 * h] = (uint32_t)(base + b);
             heavy_list[3 * h + 1] = first_chunk;
@@ -94,7 +93,7 @@ DEV void block_sum(ec::xyzz_t<F>& acc, uint32_t* tree)
     }
 }
 
-// heavy buckets, phase A: one CTA per HEAVY_CHUNK entries -> one partial sum per chunk, so a
+// heavy buckets, phase A: one CTA per cfg.heavy_chunk entries -> one partial sum per chunk, so a
 // bucket holding most of the points is spread over the whole GPU
 template<class F>
 __global__ void __launch_bounds__(HEAVY_THREADS)
@@ -105,8 +104,8 @@ heavy_chunks_kernel(const Config cfg, const uint32_t* points, const uint32_t* so
     extern __shared__ __align__(16) uint32_t tree[];         // HEAVY_THREADS xyzz slots
     const uint32_t nchunks = ctrl[2];
     for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-        const uint32_t h = chunk_map[ch], t = heavy_list[3 * h], k0 = (ch - heavy_list[3 * h + 1]) * HEAVY_CHUNK;
-        const uint32_t cnt = counts[t], k1 = min(k0 + HEAVY_CHUNK, cnt);
+        const uint32_t h = chunk_map[ch], t = heavy_list[3 * h], k0 = (ch - heavy_list[3 * h + 1]) * cfg.heavy_chunk;
+        const uint32_t cnt = counts[t], k1 = min(k0 + cfg.heavy_chunk, cnt);
         const uint32_t* run = sorted + (size_t)(t >> cfg.lg_nb) * cfg.npoints + offsets[t];
         ec::xyzz_t<F> acc;
         acc.set_inf();
@@ -211,7 +210,7 @@ public:
         j.slices_done = 0;
         const size_t entries = (size_t)j.cfg.nwins * slice_cap;
         const size_t heavy_cap = entries / (j.cfg.heavy + 1) + 1;   // most heavy buckets possible
-        const size_t chunk_cap = entries / HEAVY_CHUNK + heavy_cap; // most chunks possible
+        const size_t chunk_cap = entries / j.cfg.heavy_chunk + heavy_cap; // most chunks possible
         size_t off = 0;
         auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
         const size_t o_counts = take(j.nslots * 4), o_offsets = take(j.nslots * 4), o_cursor = take(j.nslots * 4);

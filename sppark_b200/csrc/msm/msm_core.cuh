@@ -18,6 +18,7 @@
 // windows here, Booth there); only the group element is part of the contract
 // (poc/msm-cuda/tests/msm.rs:27-38 compares after affine normalisation).
 #pragma once
+#include <algorithm>
 #include "../ec/xyzz.cuh"
 
 namespace msm {
@@ -28,6 +29,7 @@ struct Config {
     uint32_t lg_nb;        // c - 1: log2(buckets per window)
     uint32_t npoints;
     uint32_t heavy;        // buckets with more entries go to the cooperative kernel
+    uint32_t heavy_chunk;  // entries of a heavy bucket folded by one CTA
     uint32_t merge;        // 0: first slice of points (buckets start empty); 1: add into the buckets
 };
 
@@ -291,7 +293,14 @@ inline Config make_config(size_t npoints)
     cfg.nwins = (256 + cfg.wbits - 1) / cfg.wbits;
     cfg.lg_nb = cfg.wbits - 1;
     cfg.npoints = (uint32_t)npoints;
-    cfg.heavy = 16384;
+    // a bucket is "heavy" when one lane folding it alone would take longer than that lane's fair
+    // share of the whole job (~57k lanes are resident on a B200): such buckets are cut into chunks
+    // and spread over CTAs.  At 2^26 points the share is ~15k entries (nothing is heavy for uniform
+    // scalars, the long top-window buckets are simply queued first); at 2^16 it is ~25, and the
+    // three 16k-entry buckets of the top window must not be left to three single lanes.
+    const uint64_t share = (uint64_t)cfg.nwins * npoints / 57000;
+    cfg.heavy = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(share, 256), 16384);
+    cfg.heavy_chunk = std::min<uint32_t>(std::max<uint32_t>(4 * cfg.heavy, 2048), 16384);
     cfg.merge = 0;
     if (const char* env = getenv("SPPARK_B200_MSM_HEAVY")) cfg.heavy = (uint32_t)atoi(env);
     return cfg;

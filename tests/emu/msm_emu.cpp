@@ -20,7 +20,7 @@ static void emu_msm(uint32_t* out, const uint32_t* points_all, size_t npoints_al
     if (npoints == 0) { memset(out, 0, JW * 4); return; }
     Config cfg = make_config(npoints);
     if (wbits) { cfg.wbits = wbits; cfg.nwins = (256 + wbits - 1) / wbits; cfg.lg_nb = wbits - 1; }
-    if (heavy) cfg.heavy = heavy;
+    if (heavy) { cfg.heavy = heavy; cfg.heavy_chunk = 4 * heavy; }
     const size_t nslots = (size_t)cfg.nwins << cfg.lg_nb;
     std::vector<uint32_t> counts(nslots, 0), offsets(nslots), cursor(nslots), sorted((size_t)cfg.nwins * npoints_all);
     std::vector<uint32_t> buckets(nslots * BW, 0xdeadbeef), heavy_list;
