@@ -221,3 +221,43 @@ def test_pallas_msm_2pow21_folded(oracle):
     folded = np.array([_limbs(v % r, 4) for v in ints], dtype=np.uint64)
     want = oracle.msm("pallas", base, folded, "pippenger", ncpus=8)
     assert _same_point(oracle, "pallas", got, want)
+
+
+@pytest.mark.parametrize("kind", ["uniform_2pow16", "all_same_2pow20", "two_values_2pow20"])
+def test_no_serialised_buckets(oracle, kind):
+    """Guards the load balancing: neither the narrow top window of a small MSM nor a scalar
+    distribution that puts every point into one bucket per window may end up on a single lane
+    (a serial chain of 2^20 mixed adds takes ~10 s; the budget below is two orders above normal)."""
+    import time
+    import torch
+    from sppark_b200 import msm
+    n = 1 << (16 if kind == "uniform_2pow16" else 20)
+    m = 1 << 10
+    base = msm.generate_points_dev(0, m)
+    dp = base.repeat(n // m, 1).contiguous()
+    rng = np.random.default_rng(1)
+    if kind == "uniform_2pow16":
+        sc = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
+        sc[:, 3] >>= np.uint64(2)
+    elif kind == "all_same_2pow20":
+        sc = np.tile(np.array(_limbs(0x0123456789ABCDEF0FEDCBA9876543210123456789ABCDEF0FEDCBA987654321 % R_BLS, 4),
+                              dtype=np.uint64), (n, 1))
+    else:
+        sc = np.tile(np.array([_limbs(R_BLS - 5, 4), _limbs(3, 4)], dtype=np.uint64), (n // 2, 1))
+    ds = torch.from_numpy(sc.view(np.int64)).cuda()
+    msm.msm_dev(0, dp, ds)
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    got = msm.msm_dev(0, dp, ds)
+    dt = time.perf_counter() - t
+    assert dt < 0.5, f"{kind}: {dt * 1e3:.0f} ms"
+    # value check by folding onto the m distinct points
+    ints = [0] * m
+    scl = sc.reshape(n // m, m, 4)
+    for limb in range(4):
+        col = scl[:, :, limb].astype(object).sum(axis=0)
+        for j in range(m):
+            ints[j] += int(col[j]) << (64 * limb)
+    folded = np.array([_limbs(v % R_BLS, 4) for v in ints], dtype=np.uint64)
+    want = oracle.msm("bls12_381", base.cpu().numpy().view(np.uint64), folded, "pippenger", ncpus=8)
+    assert _same_point(oracle, "bls12_381", got, want)
