@@ -262,7 +262,7 @@ def main():
     # DRAM traffic of this kernel at 2^26 / c=20 from the committed `ncu --set full` capture
     # (profiles/msm_accumulate_r01.md: dram__bytes_read.sum + dram__bytes_write.sum per launch);
     # every point is gathered once per window, hence ~19x the algorithmic bytes
-    traffic = 167.3e9 if (args.lg_msm == 26 and world == 1) else None
+    traffic = 174.7e9 if (args.lg_msm == 26 and world == 1) else None
     wide_mults = 2880.0 * phases_entries(n, world)          # 10 products x 288 IMAD.WIDE per mixed add
     imad_peak = 0.94 * 32 * 148 * 1.965e9                   # measured: tools/imad_bench.cu on this B200
     roofline = {"bound": "hbm", "kernel": "msm::accumulate_kernel", "achieved": achieved, "peak": peak,
