@@ -68,6 +68,13 @@ RustError mult_pippenger(void *out_jacobian, const void *points_affine, size_t n
 RustError mult_pippenger_inf(void *out_jacobian, const void *points_affine_inf, size_t npoints,
                              const void *scalars, size_t ffi_affine_sz);
 
+/* poc/msm-cuda/cuda/pippenger_inf.cu:36-47 ; Rust decl poc/msm-cuda/src/lib.rs:84-119.
+ * BLS12-381 G2 (coordinates in Fp2 = two consecutive Fp, blst_fp2 / arkworks Fq2 layout):
+ * out is a 288-byte Jacobian point, points are arkworks G2Affine (x, y, infinity flag) with a
+ * host stride of ffi_affine_sz bytes. */
+RustError mult_pippenger_fp2_inf(void *out_jacobian, const void *points_affine_inf, size_t npoints,
+                                 const void *scalars, size_t ffi_affine_sz);
+
 /* poc/ntt-cuda/cuda/ntt_api.cu:25-36 (FEATURE_GOLDILOCKS build, the one
  * poc/ntt-cuda/go/goldilocks.go:24-40 loads); in place on HOST memory; lg == 0 is a no-op. */
 RustError compute_ntt(size_t device_id, void *inout, uint32_t lg_domain_size,
@@ -95,7 +102,8 @@ enum { SPPARK_FIELD_GL64 = 0, SPPARK_FIELD_BB31 = 1,
         * NTT kernels, ntt/kernels/{ct,gs}_mixed_radix_wide.cu): fr of FEATURE_BLS12_381,
         * FEATURE_PALLAS (= Vesta's base field) and FEATURE_VESTA (= Pallas' base field) */
        SPPARK_FIELD_BLS12_381_FR = 2, SPPARK_FIELD_PALLAS_FR = 3, SPPARK_FIELD_VESTA_FR = 4 };
-enum { SPPARK_CURVE_BLS12_381_G1 = 0, SPPARK_CURVE_PALLAS = 1, SPPARK_CURVE_VESTA = 2 };
+enum { SPPARK_CURVE_BLS12_381_G1 = 0, SPPARK_CURVE_PALLAS = 1, SPPARK_CURVE_VESTA = 2,
+       SPPARK_CURVE_BLS12_381_G2 = 3 };
 
 /* compute_ntt for any single-word field (the reference builds one .so per FEATURE_*) */
 RustError sppark_b200_ntt(int field, size_t device_id, void *inout, uint32_t lg_domain_size,

@@ -1,6 +1,6 @@
 """ctypes binding of the CPU oracle -- TEST INFRASTRUCTURE ONLY.
 
-liboracle.so   = the C restatement (oracle/ff.c ec.c msm.c ntt.c)
+liboracle.so   = the C restatement (oracle/ff.c ec.c ec2.c msm.c ntt.c)
 _ref/*.so      = the reference's own sources compiled where they lie (oracle/Makefile),
                  present only if built in the authoring container.
 All buffers are numpy arrays; field elements are little-endian 64-bit limbs.
@@ -25,7 +25,7 @@ _lib = None
 
 def build(force=False):
     so = os.path.join(HERE, "liboracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("ff.c", "ec.c", "msm.c", "ntt.c", "ff.h", "ec.h", "msm.h", "ntt.h")]
+    srcs = [os.path.join(HERE, f) for f in ("ff.c", "ec.c", "ec2.c", "msm.c", "ntt.c", "ff.h", "ec.h", "ec2.h", "msm.h", "ntt.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", HERE, "liboracle.so"])
     return so
@@ -53,6 +53,11 @@ def lib():
         _lib.oracle_ntt_gl64.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         _lib.oracle_ntt_bb31.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         _lib.oracle_ntt_ff.argtypes = [C.c_int, C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int]
+        _lib.oracle_fp2_op.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.oracle_g2_points.argtypes = [C.c_void_p, C.c_size_t]
+        _lib.oracle_g2_msm.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_size_t, C.c_void_p]
+        _lib.oracle_g2_jac_to_affine.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.oracle_g2_on_curve.argtypes = [C.c_void_p]
         _lib.oracle_gl64_root.restype = C.c_uint64
         _lib.oracle_gl64_root.argtypes = [C.c_uint, C.c_int]
         _lib.oracle_bb31_root.restype = C.c_uint32
@@ -170,6 +175,46 @@ def lde(field, evals, lg_blowup):
     ext = np.zeros((c.shape[0] << lg_blowup,) + c.shape[1:], dtype=c.dtype)
     ext[:c.shape[0]] = c
     return fn(ext, NN, False, True), c
+
+
+# ---------------------------------------------------------------- BLS12-381 G2 (oracle/ec2.c)
+def fp2_op(op, a, b=None):
+    """Element-wise Fp2 op on (n, 12) Montgomery limb arrays: mul, add, sub, sqr, inv."""
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 12)
+    b = a if b is None else np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 12)
+    r = np.zeros_like(a)
+    code = {"mul": 0, "add": 1, "sub": 2, "sqr": 3, "inv": 4}[op]
+    for i in range(a.shape[0]):
+        lib().oracle_fp2_op(code, _ptr(r[i]), _ptr(a[i]), _ptr(b[i]))
+    return r
+
+
+def g2_points(n):
+    """(n, 24) uint64: (i+1)*G2 as affine Montgomery (X.c0, X.c1, Y.c0, Y.c1)."""
+    out = np.zeros((n, 24), dtype=np.uint64)
+    lib().oracle_g2_points(_ptr(out), n)
+    return out
+
+
+def g2_msm(points, scalars, algo="buckets"):
+    """points (n, 24) packed or (n, 25) arkworks G2Affine (flag word last); scalars (n, 4)."""
+    points = np.ascontiguousarray(points, dtype=np.uint64)
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
+    assert points.shape[1] in (24, 25) and scalars.shape == (points.shape[0], 4)
+    out = np.zeros(36, dtype=np.uint64)
+    lib().oracle_g2_msm(int(algo != "naive"), _ptr(out), _ptr(points), points.strides[0],
+                        int(points.shape[1] == 25), points.shape[0], _ptr(scalars))
+    return out
+
+
+def g2_jac_to_affine(jac):
+    out = np.zeros(24, dtype=np.uint64)
+    lib().oracle_g2_jac_to_affine(_ptr(out), _ptr(np.ascontiguousarray(jac, dtype=np.uint64)))
+    return out
+
+
+def g2_on_curve(xy):
+    return bool(lib().oracle_g2_on_curve(_ptr(np.ascontiguousarray(xy, dtype=np.uint64))))
 
 
 # ---------------------------------------------------------------- reference builds (_ref)

@@ -226,3 +226,120 @@ template<size_t NBITS, const limb_t* MOD, limb_t M0, const limb_t* RR, const lim
 using blst_256_t = shim_field_t<NBITS, 4, MOD, M0, RR, ONE>;
 template<size_t NBITS, const limb_t* MOD, limb_t M0, const limb_t* RR, const limb_t* ONE>
 using blst_384_t = shim_field_t<NBITS, 6, MOD, M0, RR, ONE>;
+
+/* ---- blst C-level vector API (blst src/vect.h, consumed by the host half of
+ * ff/bls12-381-fp2.hpp:158-417).  Own portable code, same signatures. ------------------------ */
+typedef vec384 vec384x[2];
+
+static inline void vec_copy(void* d, const void* s, size_t n) { memcpy(d, s, n); }
+static inline void vec_zero(void* d, size_t n) { memset(d, 0, n); }
+static inline bool vec_is_zero(const void* a, size_t n)
+{
+    const unsigned char* p = (const unsigned char*)a;
+    unsigned char acc = 0;
+    for (size_t i = 0; i < n; i++) acc |= p[i];
+    return acc == 0;
+}
+static inline bool vec_is_equal(const void* a, const void* b, size_t n) { return memcmp(a, b, n) == 0; }
+static inline void vec_select(void* d, const void* a, const void* b, size_t n, bool sel_a)
+{   memmove(d, sel_a ? a : b, n);   }
+
+static inline void mul_mont_384(vec384 r, const vec384 a, const vec384 b, const vec384 p, limb_t n0)
+{
+    typedef shim_detail::u128 u128;
+    limb_t t[8] = {0};
+    for (size_t i = 0; i < 6; i++) {
+        limb_t c = 0;
+        for (size_t j = 0; j < 6; j++) {
+            u128 x = (u128)a[j] * b[i] + t[j] + c;
+            t[j] = (limb_t)x; c = (limb_t)(x >> 64);
+        }
+        u128 s = (u128)t[6] + c;
+        t[6] = (limb_t)s; t[7] = (limb_t)(s >> 64);
+        limb_t m = t[0] * n0;
+        u128 x = (u128)m * p[0] + t[0];
+        c = (limb_t)(x >> 64);
+        for (size_t j = 1; j < 6; j++) {
+            x = (u128)m * p[j] + t[j] + c;
+            t[j - 1] = (limb_t)x; c = (limb_t)(x >> 64);
+        }
+        s = (u128)t[6] + c;
+        t[5] = (limb_t)s; t[6] = t[7] + (limb_t)(s >> 64);
+    }
+    if (t[6] || shim_detail::geq<6>(t, p)) shim_detail::sub_n<6>(t, p);
+    memcpy(r, t, sizeof(vec384));
+}
+static inline void from_mont_384(vec384 r, const vec384 a, const vec384 p, limb_t n0)
+{
+    const vec384 one = {1};
+    mul_mont_384(r, a, one, p, n0);
+}
+static inline void add_mod_384(vec384 r, const vec384 a, const vec384 b, const vec384 p)
+{
+    typedef shim_detail::u128 u128;
+    limb_t t[6], c = 0;
+    for (size_t i = 0; i < 6; i++) { u128 x = (u128)a[i] + b[i] + c; t[i] = (limb_t)x; c = (limb_t)(x >> 64); }
+    if (c || shim_detail::geq<6>(t, p)) shim_detail::sub_n<6>(t, p);
+    memcpy(r, t, sizeof(vec384));
+}
+static inline void sub_mod_384(vec384 r, const vec384 a, const vec384 b, const vec384 p)
+{
+    typedef shim_detail::u128 u128;
+    limb_t t[6], br = 0;
+    for (size_t i = 0; i < 6; i++) { u128 x = (u128)a[i] - b[i] - br; t[i] = (limb_t)x; br = (limb_t)(x >> 64) & 1; }
+    if (br) shim_detail::add_n<6>(t, p);
+    memcpy(r, t, sizeof(vec384));
+}
+static inline void cneg_mod_384(vec384 r, const vec384 a, bool flag, const vec384 p)
+{
+    if (flag && !vec_is_zero(a, sizeof(vec384))) {
+        const vec384 zero = {0};
+        sub_mod_384(r, zero, a, p);
+    } else {
+        memmove(r, a, sizeof(vec384));
+    }
+}
+static inline void lshift_mod_384(vec384 r, const vec384 a, size_t n, const vec384 p)
+{
+    vec384 t;
+    memcpy(t, a, sizeof(t));
+    while (n--) add_mod_384(t, t, t, p);
+    memcpy(r, t, sizeof(t));
+}
+static inline void rshift_mod_384(vec384 r, const vec384 a, size_t n, const vec384 p)
+{
+    typedef shim_detail::u128 u128;
+    limb_t t[6];
+    memcpy(t, a, sizeof(t));
+    while (n--) {
+        limb_t c = 0;
+        if (t[0] & 1)
+            for (size_t i = 0; i < 6; i++) { u128 x = (u128)t[i] + p[i] + c; t[i] = (limb_t)x; c = (limb_t)(x >> 64); }
+        for (size_t i = 0; i < 5; i++) t[i] = (t[i] >> 1) | (t[i + 1] << 63);
+        t[5] = (t[5] >> 1) | (c << 63);
+    }
+    memcpy(r, t, sizeof(t));
+}
+static inline void add_mod_384x(vec384x r, const vec384x a, const vec384x b, const vec384 p)
+{   add_mod_384(r[0], a[0], b[0], p); add_mod_384(r[1], a[1], b[1], p);   }
+static inline void sub_mod_384x(vec384x r, const vec384x a, const vec384x b, const vec384 p)
+{   sub_mod_384(r[0], a[0], b[0], p); sub_mod_384(r[1], a[1], b[1], p);   }
+/* Fp2 = Fp[u]/(u^2+1), schoolbook */
+static inline void mul_mont_384x(vec384x r, const vec384x a, const vec384x b, const vec384 p, limb_t n0)
+{
+    vec384 t0, t1, t2, t3;
+    mul_mont_384(t0, a[0], b[0], p, n0);
+    mul_mont_384(t1, a[1], b[1], p, n0);
+    mul_mont_384(t2, a[0], b[1], p, n0);
+    mul_mont_384(t3, a[1], b[0], p, n0);
+    sub_mod_384(r[0], t0, t1, p);
+    add_mod_384(r[1], t2, t3, p);
+}
+static inline void sqr_mont_384x(vec384x r, const vec384x a, const vec384 p, limb_t n0)
+{   mul_mont_384x(r, a, a, p, n0);   }
+
+static inline void be_bytes_from_limbs(unsigned char* out, const limb_t* in, size_t n)
+{
+    for (size_t i = 0; i < n; i++) out[n - 1 - i] = (unsigned char)(in[i / 8] >> (8 * (i % 8)));
+}
+static inline char hex_from_nibble(unsigned char n) { return "0123456789abcdef"[n & 15]; }

@@ -28,6 +28,7 @@ _lib = None
 _SIGS = {
     "mult_pippenger": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
     "mult_pippenger_inf": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t],
+    "mult_pippenger_fp2_inf": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t],
     "compute_ntt": [C.c_size_t, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int],
     "sppark_b200_ntt": [C.c_int, C.c_size_t, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int],
     "sppark_b200_ntt_dev": [C.c_int, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p],

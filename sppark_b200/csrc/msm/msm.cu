@@ -8,6 +8,10 @@ RustError msm_dev_pallas(void*, const void*, size_t, const void*, void*);
 RustError msm_host_vesta(void*, const void*, size_t, const void*, size_t, bool);
 RustError msm_dev_vesta(void*, const void*, size_t, const void*, void*);
 
+RustError msm_host_bls12_381_g2(void*, const void*, size_t, const void*, size_t, bool);
+RustError msm_dev_bls12_381_g2(void*, const void*, size_t, const void*, void*);
+RustError gen_points_bls12_381_g2(void*, size_t, void*);
+RustError combine_bls12_381_g2(void*, const void*, size_t);
 RustError gen_points_bls12_381(void*, size_t, void*);
 RustError gen_points_pallas(void*, size_t, void*);
 RustError gen_points_vesta(void*, size_t, void*);
@@ -22,6 +26,7 @@ extern "C" RustError sppark_b200_generate_points_dev(int curve, void* d_out, siz
     case SPPARK_CURVE_BLS12_381_G1: return gen_points_bls12_381(d_out, n, stream);
     case SPPARK_CURVE_PALLAS: return gen_points_pallas(d_out, n, stream);
     case SPPARK_CURVE_VESTA: return gen_points_vesta(d_out, n, stream);
+    case SPPARK_CURVE_BLS12_381_G2: return gen_points_bls12_381_g2(d_out, n, stream);
     default: return rust_err(-(int)cudaErrorInvalidValue, "generate_points: unknown curve");
     }
 }
@@ -32,6 +37,7 @@ extern "C" RustError sppark_b200_msm_combine(int curve, void* out, const void* p
     case SPPARK_CURVE_BLS12_381_G1: return combine_bls12_381(out, partials, count);
     case SPPARK_CURVE_PALLAS: return combine_pallas(out, partials, count);
     case SPPARK_CURVE_VESTA: return combine_vesta(out, partials, count);
+    case SPPARK_CURVE_BLS12_381_G2: return combine_bls12_381_g2(out, partials, count);
     default: return rust_err(-(int)cudaErrorInvalidValue, "msm_combine: unknown curve");
     }
 }
@@ -46,6 +52,8 @@ extern "C" RustError sppark_b200_msm(int curve, void* out, const void* points, s
         return msm_host_pallas(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 64, ffi_affine_sz > 64);
     case SPPARK_CURVE_VESTA:
         return msm_host_vesta(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 64, ffi_affine_sz > 64);
+    case SPPARK_CURVE_BLS12_381_G2:
+        return msm_host_bls12_381_g2(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 192, ffi_affine_sz > 192);
     default:
         return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_msm: unknown curve");
     }
@@ -58,6 +66,7 @@ extern "C" RustError sppark_b200_msm_dev(int curve, void* out, const void* d_poi
     case SPPARK_CURVE_BLS12_381_G1: return msm_dev_bls12_381(out, d_points, npoints, d_scalars, stream);
     case SPPARK_CURVE_PALLAS: return msm_dev_pallas(out, d_points, npoints, d_scalars, stream);
     case SPPARK_CURVE_VESTA: return msm_dev_vesta(out, d_points, npoints, d_scalars, stream);
+    case SPPARK_CURVE_BLS12_381_G2: return msm_dev_bls12_381_g2(out, d_points, npoints, d_scalars, stream);
     default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_msm_dev: unknown curve");
     }
 }

@@ -70,7 +70,7 @@ static __global__ void scatter_kernel(const Config cfg, const uint32_t* scalars,
 }
 
 template<class F>
-__global__ void __launch_bounds__(ACC_THREADS, SPPARK_B200_ACC_MIN_BLOCKS)
+__global__ void __launch_bounds__(ACC_THREADS, (F::N > 12 ? 2 : SPPARK_B200_ACC_MIN_BLOCKS))
 accumulate_kernel(const Config cfg, const uint32_t* points, const uint32_t* sorted,
                   const uint32_t* offsets, const uint32_t* counts, uint32_t* buckets,
                   uint32_t* task_counter)

@@ -1,0 +1,24 @@
+// BLS12-381 G2 MSM: the third entry point of poc/msm-cuda's default (bls12_381) build,
+//   mult_pippenger_fp2_inf   poc/msm-cuda/cuda/pippenger_inf.cu:36-43
+// Same sort / accumulate / reduce kernels as G1, instantiated over Fp2 (ff/fp2.cuh).
+#include "msm_host.cuh"
+#include "../ff/fp2.cuh"
+
+namespace {
+typedef ff::fp2_t<ff::bls12_381_fp_t> fp2;
+struct g2_gen : ff::bls12_381_g2_gen { typedef fp2 F; };
+}
+
+RustError msm_host_bls12_381_g2(void* out, const void* points, size_t npoints, const void* scalars,
+                                size_t stride, bool has_flag)
+{   return msm_host<fp2>(out, points, npoints, scalars, stride, has_flag);   }
+RustError msm_dev_bls12_381_g2(void* out, const void* d_points, size_t npoints, const void* d_scalars, void* stream)
+{   return msm_dev<fp2>(out, d_points, npoints, d_scalars, stream);   }
+RustError gen_points_bls12_381_g2(void* d_out, size_t n, void* stream)
+{   return gen_points_dev<g2_gen>(d_out, n, stream);   }
+RustError combine_bls12_381_g2(void* out, const void* partials, size_t count)
+{   return combine_host<fp2>(out, partials, count);   }
+
+extern "C" RustError mult_pippenger_fp2_inf(void* out, const void* points, size_t npoints,
+                                            const void* scalars, size_t ffi_affine_sz)
+{   return msm_host_bls12_381_g2(out, points, npoints, scalars, ffi_affine_sz, true);   }

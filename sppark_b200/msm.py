@@ -9,8 +9,8 @@ import numpy as np
 
 from . import _lib
 
-BLS12_381_G1, PALLAS, VESTA = 0, 1, 2
-_LIMBS = {BLS12_381_G1: 6, PALLAS: 4, VESTA: 4}
+BLS12_381_G1, PALLAS, VESTA, BLS12_381_G2 = 0, 1, 2, 3
+_LIMBS = {BLS12_381_G1: 6, PALLAS: 4, VESTA: 4, BLS12_381_G2: 12}    # 64-bit limbs per coordinate
 
 
 def _check(points, scalars):
@@ -40,6 +40,18 @@ def multi_scalar_mult_arkworks(points, scalars):
     out = np.zeros(18, dtype=np.uint64)
     err = _lib.lib().mult_pippenger_inf(out.ctypes.data, points.ctypes.data, points.shape[0],
                                         scalars.ctypes.data, points.strides[0])
+    _lib.check(err)
+    return out
+
+
+def multi_scalar_mult_fp2_arkworks(points, scalars):
+    """ark G2Affine[] (X, Y in Fq2, infinity flag; size_of::<G2Affine>() == 200) x BigInteger256[]
+    -> G2Projective (36 limbs) via mult_pippenger_fp2_inf (poc/msm-cuda/src/lib.rs:84-119)."""
+    _check(points, scalars)
+    assert points.shape[1] == 25
+    out = np.zeros(36, dtype=np.uint64)
+    err = _lib.lib().mult_pippenger_fp2_inf(out.ctypes.data, points.ctypes.data, points.shape[0],
+                                            scalars.ctypes.data, points.strides[0])
     _lib.check(err)
     return out
 

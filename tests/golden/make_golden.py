@@ -5,6 +5,8 @@
                     BabyBear, lg 1..10, every order x direction x type.  Needs a GPU: run as
                     `gpurun -- python tests/golden/make_golden.py gpu` and copy gpurun_out/golden/*.
   msm_ref_gpu.npz   same for the reference's CUDA mult_pippenger (BLS12-381 G1).
+  msm_g2_ref_gpu.npz  the reference's mult_pippenger_fp2_inf (BLS12-381 G2) and mult_pippenger_inf
+                    (G1, arkworks layout with infinity flags): `... make_golden.py g2` on a GPU.
   msm_ref_cpu.npz   the reference's CPU msm/pippenger.hpp (oracle/_ref/libref_msm_cpu.so);
                     runs anywhere: `python tests/golden/make_golden.py cpu`.
 
@@ -134,6 +136,70 @@ def gen_gpu(outdir):
     print("wrote msm_ref_gpu.npz")
 
 
+def g2_inputs():
+    """Small deterministic G2 instances in the arkworks layout (n, 25): X, Y in Fp2 + flag word."""
+    rng = np.random.default_rng(381)
+    base = o.g2_points(64)
+    cases = []
+    for n in (1, 2, 33, 200, 1000):
+        pts = np.zeros((n, 25), dtype=np.uint64)
+        pts[:, :24] = base[rng.integers(0, 64, size=n)]
+        if n > 3:
+            pts[3, 24] = 1                       # flagged infinity
+        sc = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
+        sc[:, 3] >>= np.uint64(2)
+        if n >= 33:
+            sc[5] = 0
+            sc[6] = [1, 0, 0, 0]
+            sc[7] = o.int_to_limbs(R_BLS - 1, 4)
+            pts[9] = pts[8]                      # equal points, equal scalars -> doubling in a bucket
+            sc[9] = sc[8]
+        cases.append((pts, sc))
+    return cases
+
+
+def gen_g2(outdir):
+    """msm_g2_ref_gpu.npz: the reference's mult_pippenger_fp2_inf (and, for the G1 arkworks layout,
+    mult_pippenger_inf) from oracle/_ref/libref_msm_g2_gpu.so, run on a B200."""
+    lib = C.CDLL(o.ref_path("libref_msm_g2_gpu.so"))
+    for f in (lib.mult_pippenger_fp2_inf, lib.mult_pippenger_inf):
+        f.restype = RE
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    packed = C.CDLL(o.ref_path("libref_msm_g2_packed_gpu.so"))
+    packed.ref_mult_pippenger_fp2.restype = RE
+    packed.ref_mult_pippenger_fp2.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    out = {}
+    cases = g2_inputs()
+    for k, (pts, sc) in enumerate(cases):
+        # out{k}: the reference's templates on packed points (flagged rows -> X = Y = 0), the pin.
+        # inf_out{k}: the reference's mult_pippenger_fp2_inf as built -- kept as evidence of its
+        # host/device layout mismatch (oracle/ref_msm_g2.cu), not used as an expectation.
+        flat = np.ascontiguousarray(pts[:, :24])
+        flat[pts[:, 24] != 0] = 0
+        jac = np.zeros(36, dtype=np.uint64)
+        e = packed.ref_mult_pippenger_fp2(jac.ctypes.data, flat.ctypes.data, flat.shape[0], sc.ctypes.data)
+        assert e.code == 0
+        inf = np.zeros(36, dtype=np.uint64)
+        e = lib.mult_pippenger_fp2_inf(inf.ctypes.data, pts.ctypes.data, pts.shape[0], sc.ctypes.data, 200)
+        assert e.code == 0
+        out[f"points{k}"], out[f"scalars{k}"], out[f"out{k}"], out[f"inf_out{k}"] = pts, sc, jac, inf
+    out["ncases"] = np.int64(len(cases))
+    g1 = 0
+    for n, (pts, sc) in msm_inputs().items():
+        ark = np.zeros((n, 13), dtype=np.uint64)
+        ark[:, :12] = pts
+        if n > 10:
+            ark[10, 12] = 1
+        jac = np.zeros(18, dtype=np.uint64)
+        e = lib.mult_pippenger_inf(jac.ctypes.data, ark.ctypes.data, n, sc.ctypes.data, 104)
+        assert e.code == 0
+        out[f"g1_points{g1}"], out[f"g1_scalars{g1}"], out[f"g1_out{g1}"] = ark, sc, jac
+        g1 += 1
+    out["g1_ncases"] = np.int64(g1)
+    np.savez_compressed(os.path.join(outdir, "msm_g2_ref_gpu.npz"), **out)
+    print("wrote msm_g2_ref_gpu.npz")
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "cpu"
     if mode == "cpu":
@@ -141,4 +207,7 @@ if __name__ == "__main__":
     else:
         outdir = os.path.join(ROOT, "gpurun_out", "golden")
         os.makedirs(outdir, exist_ok=True)
-        gen_gpu(outdir)
+        if mode == "g2":
+            gen_g2(outdir)
+        else:
+            gen_gpu(outdir)

@@ -18,7 +18,7 @@ def _declared_symbols():
 
 def test_library_exports_every_declared_symbol(lib):
     names = _declared_symbols()
-    assert {"mult_pippenger", "mult_pippenger_inf", "compute_ntt", "cuda_available",
+    assert {"mult_pippenger", "mult_pippenger_inf", "mult_pippenger_fp2_inf", "compute_ntt", "cuda_available",
             "drop_error_message"} <= set(names)
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/sppark_b200.h but not exported"
