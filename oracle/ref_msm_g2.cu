@@ -31,10 +31,10 @@ typedef jacobian_t<fp2_t> g2_point_t;
 typedef xyzz_t<fp2_t> g2_bucket_t;
 typedef g2_bucket_t::affine_t g2_affine_t;
 
-#ifndef __CUDA_ARCH__
-extern "C" RustError ref_mult_pippenger_fp2(g2_point_t* out, const g2_affine_t points[],
+/* not guarded by __CUDA_ARCH__: the device pass must see the call to instantiate the fp2 kernels
+ * (the reference's explicit instantiations, msm/pippenger.cuh:299-316, cover bucket_t only) */
+extern "C" RustError::by_value ref_mult_pippenger_fp2(g2_point_t* out, const g2_affine_t points[],
                                             size_t npoints, const scalar_t scalars[])
 {
     return mult_pippenger<g2_bucket_t>(out, points, npoints, scalars, false);
 }
-#endif

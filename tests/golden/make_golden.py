@@ -33,6 +33,12 @@ class RE(C.Structure):
     _fields_ = [("code", C.c_int), ("message", C.c_void_p)]
 
 
+def ok(e, what=""):
+    if e.code != 0:
+        msg = C.cast(e.message, C.c_char_p).value if e.message else b""
+        raise RuntimeError(f"{what}: reference returned {e.code}: {msg.decode(errors='replace')}")
+
+
 def msm_inputs():
     """A few small deterministic MSM instances (points = multiples of G, incl. infinity)."""
     rng = np.random.default_rng(2024)
@@ -178,10 +184,10 @@ def gen_g2(outdir):
         flat[pts[:, 24] != 0] = 0
         jac = np.zeros(36, dtype=np.uint64)
         e = packed.ref_mult_pippenger_fp2(jac.ctypes.data, flat.ctypes.data, flat.shape[0], sc.ctypes.data)
-        assert e.code == 0
+        ok(e, f"packed fp2 n={flat.shape[0]}")
         inf = np.zeros(36, dtype=np.uint64)
         e = lib.mult_pippenger_fp2_inf(inf.ctypes.data, pts.ctypes.data, pts.shape[0], sc.ctypes.data, 200)
-        assert e.code == 0
+        ok(e, f"fp2_inf n={pts.shape[0]}")
         out[f"points{k}"], out[f"scalars{k}"], out[f"out{k}"], out[f"inf_out{k}"] = pts, sc, jac, inf
     out["ncases"] = np.int64(len(cases))
     g1 = 0
