@@ -414,37 +414,51 @@ def bench_ntt(args, torch, ntt, _lib, peak, peak_src, barrier, max_over_ranks, w
 
 
 def bench_ntt_sharded(args, torch, _lib, peak, peak_src, barrier, max_over_ranks, world):
+    """ONE transform slab-sharded over the ranks.  Headline: Goldilocks 2^lg.  Also reported
+    (SURVEY.md section 8d config 5): BabyBear 2^27, the largest transform that field admits
+    (p - 1 = 15 * 2^27; "2^28" is not a valid BabyBear domain), 2^9 x 2^18 with a two-pass second
+    stage."""
     import torch.distributed as dist
     from sppark_b200 import parallel
-    lg, rank = args.lg_ntt, dist.get_rank()
+    rank = dist.get_rank()
     lg_g = world.bit_length() - 1
-    n_local = (1 << lg) // world
-    rng = np.random.default_rng(7 + rank)
-    local = torch.from_numpy(rng.integers(0, GL_P, size=n_local, dtype=np.uint64).view(np.int64)).cuda()
-    pass_fn = parallel.gpu_slab_pass(0, lg, lg_g, rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    iters = max(10, args.steps * 5)
-    for _ in range(max(3, args.warmup)):
-        parallel.ntt_slab(local, lg, 0, pass_fn)
-    barrier()
-    tot = 0.0
-    for _ in range(iters):
-        flush.zero_()
+
+    def run(fid, lg, name, esz, iters):
+        n_local = (1 << lg) // world
+        rng = np.random.default_rng(7 + rank)
+        if fid == 0:
+            local = torch.from_numpy(rng.integers(0, GL_P, size=n_local, dtype=np.uint64).view(np.int64)).cuda()
+        else:
+            local = torch.from_numpy(rng.integers(0, 0x78000001, size=n_local, dtype=np.uint32).view(np.int32)).cuda()
+        pass_fn = parallel.gpu_slab_pass(fid, lg, lg_g, rank)
+        for _ in range(max(3, args.warmup)):
+            parallel.ntt_slab(local, lg, fid, pass_fn)
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        parallel.ntt_slab(local, lg, 0, pass_fn)
-        e1.record()
-        e1.synchronize()
-        tot += max_over_ranks(e0.elapsed_time(e1))
-    ms = tot / iters
-    alg = 2 * (1 << lg) * 8
-    return {"metric": f"Goldilocks NTT/s @2^{lg} (NN, forward)", "value": 1e3 / ms, "unit": "NTT/s",
-            "ms_per_ntt": ms, "scaling": "strong", "iters": iters,
-            "sharding": f"column slabs x{world}, one all-to-all of {n_local * 8 * (world - 1) // world} B per rank",
-            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
-                         "frac": alg / (ms * 1e-3) / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src},
-            "e2e": None}
+        tot = 0.0
+        for _ in range(iters):
+            flush.zero_()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            parallel.ntt_slab(local, lg, fid, pass_fn)
+            e1.record()
+            e1.synchronize()
+            tot += max_over_ranks(e0.elapsed_time(e1))
+        ms = tot / iters
+        alg = 2 * (1 << lg) * esz
+        n1 = 1 << parallel.slab_first_digit(lg, fid)
+        return {"metric": f"{name} NTT/s @2^{lg} (NN, forward)", "value": 1e3 / ms, "unit": "NTT/s",
+                "ms_per_ntt": ms, "scaling": "strong", "iters": iters,
+                "sharding": f"column slabs x{world} of a {n1} x {(1 << lg) // n1} matrix, one all-to-all of "
+                            f"{n_local * esz * (world - 1) // world} B per rank",
+                "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                             "frac": alg / (ms * 1e-3) / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src},
+                "e2e": None}
+
+    res = run(0, args.lg_ntt, "Goldilocks", 8, max(10, args.steps * 5))
+    res["babybear_2pow27"] = run(1, 27, "BabyBear", 4, max(5, args.steps * 2))
+    return res
 
 
 if __name__ == "__main__":

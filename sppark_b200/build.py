@@ -33,6 +33,19 @@ def _newest_input():
     return max(newest, os.path.getmtime(inc))
 
 
+def _up_to_date(obj, flags):
+    """Object newer than every file of its nvcc -MD dependency list, built with the same flags."""
+    dep = obj[:-2] + ".d"
+    try:
+        if open(obj + ".flags").read() != " ".join(flags):
+            return False
+        t = os.path.getmtime(obj)
+        words = open(dep).read().replace("\\\n", " ").split()
+        return all(os.path.getmtime(w) <= t for w in words[1:] if not w.endswith(":"))
+    except OSError:
+        return False
+
+
 def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_input():
         return LIB
@@ -43,11 +56,15 @@ def build(force=False, verbose=False):
     os.makedirs(objdir, exist_ok=True)
     for src in _sources():
         obj = os.path.join(objdir, os.path.basename(src).replace(".cu", ".o"))
-        cmd = ["nvcc", *NVCC_FLAGS, *extra, "-c", "-o", obj, src]
+        objs.append(obj)
+        if not force and not verbose and _up_to_date(obj, [*NVCC_FLAGS, *extra]):
+            continue
+        cmd = ["nvcc", *NVCC_FLAGS, *extra, "-MD", "-c", "-o", obj, src]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
+        with open(obj + ".flags", "w") as f:
+            f.write(" ".join([*NVCC_FLAGS, *extra]))
         procs.append((subprocess.Popen(cmd), cmd))
-        objs.append(obj)
     for p, cmd in procs:
         if p.wait() != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))

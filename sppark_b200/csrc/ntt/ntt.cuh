@@ -267,9 +267,11 @@ public:
             coset_scale(gpu, d_inout, lg_n, out_rev, true, stream);
     }
 
-    // one local pass of the slab-sharded transform (ntt_plan.hpp: make_slab_plan); which = 1:
-    // d_in [N1][N2/G] -> d_out = all-to-all staging [G][N2/G][N1/G]; which = 2: d_in == d_out,
-    // the received [N2][N1/G] matrix, in place.  Enqueued on `stream`.
+    // one local stage of the slab-sharded transform (ntt_plan.hpp: make_slab_plan); which = 1:
+    // d_in [N1][N2/G] -> d_out = all-to-all staging [G][N2/G][N1/G]; which = 2: d_in = the received
+    // [N2][N1/G] matrix, transformed down its columns with the result left in d_in; d_out is
+    // scratch of the same size, touched only when N2 needs more than one pass (it may equal d_in
+    // otherwise).  Enqueued on `stream`.
     static void slab_pass(const gpu_t& gpu, int which, const T* d_in, T* d_out, uint32_t lg_n,
                           uint32_t lg_g, uint32_t rank, Direction direction, cudaStream_t stream)
     {
@@ -282,7 +284,9 @@ public:
         SlabPlan sp;
         if (!make_slab_plan(sp, lg_n, lg_g, rank, inverse, lg_tile, F::NTT_MAX_LG_R))
             throw cuda_error(-(int)cudaErrorInvalidValue,
-                             "NTT slab: lg_domain_size must split into two digits of at most NTT_MAX_LG_R bits, each >= lg_g");
+                             "NTT slab: the first digit of lg_domain_size and the rest must both be >= lg_g");
+        if (which == 2 && sp.needs_scratch && d_out == d_in)
+            throw cuda_error(-(int)cudaErrorInvalidValue, "NTT slab: this size needs a scratch buffer distinct from the data");
         const Tables<F>& tb = tables(gpu, lg_n, inverse, stream);
         static bool attr_done[64];
         if (!attr_done[gpu.cid() & 63]) {
@@ -290,16 +294,23 @@ public:
                                          (int)gpu.props().sharedMemPerBlockOptin));
             attr_done[gpu.cid() & 63] = true;
         }
-        const Pass& d = which == 1 ? sp.pass1 : sp.pass2;
-        uint32_t ntiles = 1u << (lg_local - d.lg_r - d.lg_w);
-        size_t smem = smem_elems(d) * sizeof(T);
         g_profile.reset();
-        g_profile.mark("pass", stream);
-        if (!launch_static<F>(d, tb, d_in, d_out, ntiles, smem, stream))
-            pass_kernel<F><<<ntiles, tile_threads<F>(d), smem, stream>>>(d, tb, d_in, d_out);
-        COUNT_LAUNCH();
+        auto run = [&](const Pass& d, const T* src, T* dst) {
+            uint32_t ntiles = 1u << (lg_local - d.lg_r - d.lg_w);
+            size_t smem = smem_elems(d) * sizeof(T);
+            g_profile.mark("pass", stream);
+            if (!launch_static<F>(d, tb, src, dst, ntiles, smem, stream))
+                pass_kernel<F><<<ntiles, tile_threads<F>(d), smem, stream>>>(d, tb, src, dst);
+            COUNT_LAUNCH();
+            CUDA_OK(cudaGetLastError());
+        };
+        if (which == 1) {
+            run(sp.pass1, d_in, d_out);
+        } else {
+            T* buf[2] = {const_cast<T*>(d_in), d_out};
+            for (const Pass& d : sp.after) run(d, buf[d.src], buf[d.dst]);
+        }
         g_profile.mark("end", stream);
-        CUDA_OK(cudaGetLastError());
     }
 
     // Low-degree extension (reference: NTT::LDE / LDE_aux, ntt/ntt.cuh:247-340): `inout` holds

@@ -155,22 +155,40 @@ inline Plan make_plan(uint32_t lg_n, int order, bool inverse, uint32_t lg_tile,
 //   pass 1 (local): N1-point NTT down every local column, twiddle w_N^(k1*j2) with the GLOBAL
 //           column j2, written straight into the all-to-all staging layout [G][N2/G][N1/G]
 //   exchange:       block q of the staging buffer goes to rank q (N*(G-1)/G^2 elements per rank)
-//   pass 2 (local): the received [N2][N1/G] matrix, N2-point NTT down every column, in place
+//   after (local):  the received [N2][N1/G] matrix, N2-point NTT down every column.  N1 is the
+//           first digit of the transform; when N2 exceeds one tile (lg_n > 2*max_lg_r, e.g.
+//           BabyBear 2^27 = 2^9 x 2^18) the column NTT is itself the remaining digits of the
+//           NN plan, run on the local array with the N1/G batch index as the finished low bits:
+//           ping-pong between the received buffer and a scratch buffer, result in the former.
 // The reference has no multi-GPU path; this is SURVEY.md section 8(e).
 struct SlabPlan {
     uint32_t s1, s2;
-    Pass pass1, pass2;
+    Pass pass1;
+    std::vector<Pass> after;             // buffers: 0 = received matrix, 1 = scratch
+    bool needs_scratch;
 };
+
+inline uint32_t slab_first_digit(uint32_t lg_n, uint32_t max_lg_r = LG_DENSE)
+{
+    const std::vector<uint32_t> s = split_digits(lg_n, max_lg_r);
+    return s.size() < 2 ? (lg_n + 1) / 2 : s[0];
+}
 
 inline bool make_slab_plan(SlabPlan& sp, uint32_t lg_n, uint32_t lg_g, uint32_t rank, bool inverse,
                            uint32_t lg_tile, uint32_t max_lg_r = LG_DENSE, uint32_t max_lg_w = 6)
 {
-    const uint32_t s1 = (lg_n + 1) / 2, s2 = lg_n - s1;
-    if (s1 > max_lg_r || s2 > max_lg_r || s1 < lg_g || s2 < lg_g) return false;
+    std::vector<uint32_t> s = split_digits(lg_n, max_lg_r);
+    if (s.size() < 2) { s.assign(2, 0); s[0] = (lg_n + 1) / 2; s[1] = lg_n - s[0]; }
+    const uint32_t P = (uint32_t)s.size();
+    const uint32_t s1 = s[0], s2 = lg_n - s1;
+    if (s1 > max_lg_r || s1 < lg_g || s2 < lg_g) return false;
+    for (uint32_t p = 1; p < P; p++)
+        if (s[p] == 0 || s[p] > max_lg_r) return false;
     sp.s1 = s1;
     sp.s2 = s2;
     const uint32_t lc = s2 - lg_g;                        // log2(local columns of the input)
     const uint32_t ld = s1 - lg_g;                        // log2(local columns of the output)
+    const uint32_t nloc = lg_n - lg_g;
 
     Pass d;
     memset(&d, 0, sizeof(d));
@@ -196,19 +214,41 @@ inline bool make_slab_plan(SlabPlan& sp, uint32_t lg_n, uint32_t lg_g, uint32_t 
     d.src = 0; d.dst = 1;
     sp.pass1 = d;
 
-    memset(&d, 0, sizeof(d));
-    d.lg_r = s2;
-    lg_w = lg_tile > s2 ? lg_tile - s2 : 0;
-    if (lg_w > max_lg_w) lg_w = max_lg_w;
-    if (lg_w > ld) lg_w = ld;
-    d.lg_w = lg_w;
-    d.in_lg_tlo = 32; d.in_tl = 1ull << lg_w; d.in_th = 0;
-    d.in_lg_sa = ld; d.in_lg_sc = 0;
-    d.out_lg_tlo = 32; d.out_tl = d.in_tl; d.out_th = 0;
-    d.out_lg_sa = ld; d.out_lg_sc = 0;
-    d.tw_mode = TW_NONE;
-    d.scale = inverse;
-    sp.pass2 = d;
+    // digits 2..P on the received [N2][N1/G] array: the NN schedule of make_plan with the global
+    // finished-bits count a replaced by its local value a - lg_g wherever it addresses memory
+    sp.after.clear();
+    sp.needs_scratch = P > 2;
+    uint32_t where = 0;
+    for (uint32_t p = 1, a = s1; p < P; a += s[p], p++) {
+        const uint32_t R = s[p], b = lg_n - a - R, al = a - lg_g;
+        memset(&d, 0, sizeof(d));
+        d.lg_r = R;
+        lg_w = lg_tile > R ? lg_tile - R : 0;
+        if (lg_w > max_lg_w) lg_w = max_lg_w;
+        const uint32_t avail = al == 0 ? nloc - R : (al < nloc - R ? al : nloc - R);
+        if (lg_w > avail) lg_w = avail;
+        d.lg_w = lg_w;
+        const uint64_t W = 1ull << lg_w;
+        d.in_lg_tlo = 32; d.in_tl = W; d.in_th = 0;
+        d.in_lg_sa = nloc - R; d.in_lg_sc = 0;
+        if (al == 0) {
+            d.out_lg_tlo = 32; d.out_tl = W << R; d.out_th = 0;
+            d.out_lg_sa = 0; d.out_lg_sc = R;
+        } else {
+            d.out_lg_tlo = al - lg_w; d.out_tl = W; d.out_th = 1ull << (al + R);
+            d.out_lg_sa = al; d.out_lg_sc = 0;
+        }
+        if (b) {
+            d.tw_mode = TW_STORE; d.tw_rsh = al; d.tw_bits = b; d.tw_brev = 0; d.tw_lsh = a;
+        }
+        if (P > 2) {
+            d.src = where;
+            d.dst = p == P - 1 ? 0 : (where ^ 1);
+            where = d.dst;
+        }
+        d.scale = inverse && p == P - 1;
+        sp.after.push_back(d);
+    }
     return true;
 }
 

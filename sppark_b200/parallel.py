@@ -41,28 +41,40 @@ def msm_sharded(local_msm, combine, partial_words, device=None):
 
 
 # ---------------------------------------------------------------------------------- NTT
-def slab_shapes(lg_n, lg_g):
+_MAX_LG_R = {0: 12, 1: 12, 2: 11, 3: 11, 4: 11}       # F::NTT_MAX_LG_R per field id (csrc/ff/*.cuh)
+
+
+def slab_first_digit(lg_n, field=0, s1=None):
+    """log2(N1): the first digit of the planner's split (ntt_plan.hpp: slab_first_digit)."""
+    if s1 is not None:
+        return s1
+    max_r = _MAX_LG_R[field]
+    p = max(1, -(-lg_n // max_r))
+    return (lg_n + 1) // 2 if p < 2 else lg_n // p + (1 if lg_n % p else 0)
+
+
+def slab_shapes(lg_n, lg_g, field=0, s1=None):
     """(N1, N2, local input shape [N1][N2/G], local output shape [N2][N1/G]) of the slab-sharded
-    transform: x[j1*N2 + j2] lives on the rank owning column j2, X[k1 + N1*k2] on the rank owning k1."""
-    s1 = (lg_n + 1) // 2
+    transform: x[j1*N2 + j2] lives on the rank owning column j2, X[k1 + N1*k2] on the rank owning k1.
+    N1 = 2^(first digit): half of lg_n while both halves fit one tile (<= 2^12 rows), otherwise
+    the first of three (or more) digits, e.g. BabyBear 2^27 = 2^9 x 2^18."""
+    s1 = slab_first_digit(lg_n, field, s1)
     s2 = lg_n - s1
     n1, n2, g = 1 << s1, 1 << s2, 1 << lg_g
     return n1, n2, (n1, n2 // g), (n2, n1 // g)
 
 
-def scatter_columns(x, lg_n, lg_g, rank):
+def scatter_columns(x, lg_n, lg_g, rank, field=0, s1=None):
     """This rank's slab of a full natural-order array (test/bench helper)."""
-    n1, n2, (_, c), _ = slab_shapes(lg_n, lg_g)
+    n1, n2, (_, c), _ = slab_shapes(lg_n, lg_g, field, s1)
     return np.ascontiguousarray(x.reshape(n1, n2)[:, rank * c:(rank + 1) * c])
 
 
-def gather_columns(parts, lg_n, lg_g):
+def gather_columns(parts, lg_n, lg_g, field=0, s1=None):
     """Inverse of the output distribution: parts[r] = [N2][N1/G] -> natural-order array."""
-    n1, n2, _, (_, d) = slab_shapes(lg_n, lg_g)
-    out = np.empty((n2, n1), dtype=parts[0].dtype)
-    for r, p in enumerate(parts):
-        out[:, r * d:(r + 1) * d] = p.reshape(n2, d)
-    return out.reshape(-1)
+    n1, n2, _, (_, d) = slab_shapes(lg_n, lg_g, field, s1)
+    full = np.concatenate([np.asarray(p).reshape(n2, d) for p in parts], axis=1)      # [k2][k1]
+    return np.ascontiguousarray(full.reshape(-1))
 
 
 def exchange(staging, world, all_to_all):
@@ -93,14 +105,15 @@ def exchange(staging, world, all_to_all):
 def ntt_slab(local, lg_n, field, pass_fn, inverse=False, all_to_all=True):
     """Slab-sharded NTT of 2^lg_n points over the default process group.  `local` is this rank's
     [N1][N2/G] slab (torch tensor, flat); returns its [N2][N1/G] slab of the result.
-    pass_fn(which, src, dst) runs one local pass (sppark_b200_ntt_slab_pass on a GPU)."""
+    pass_fn(which, src, dst) runs one local stage (sppark_b200_ntt_slab_pass on a GPU): which = 1
+    writes dst, which = 2 transforms src with dst as scratch."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_initialized() else 1
     staging = torch.empty_like(local)
     pass_fn(1, local, staging)
     recv = exchange(staging, world, all_to_all)
-    pass_fn(2, recv, recv)
+    pass_fn(2, recv, staging)            # staging doubles as scratch when N2 takes several passes
     return recv
 
 

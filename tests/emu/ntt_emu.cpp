@@ -77,7 +77,8 @@ static int emu_run(typename F::T* data, uint32_t lg_n, int order, int inverse, u
     return (int)plan.passes.size();
 }
 
-// one local pass of the slab-sharded transform on a "rank"'s buffers (see make_slab_plan)
+// one local stage of the slab-sharded transform on a "rank"'s buffers (see make_slab_plan):
+// which = 1: in -> out (staging); which = 2: `in` transformed with `out` as scratch, result in `in`
 template<class F>
 static int emu_slab_pass(int which, const typename F::T* in, typename F::T* out, uint32_t lg_n, uint32_t lg_g,
                          uint32_t rank, int inverse, uint32_t lg_tile)
@@ -86,20 +87,29 @@ static int emu_slab_pass(int which, const typename F::T* in, typename F::T* out,
     HostTables<F> tb(lg_n, inverse != 0);
     SlabPlan sp;
     if (!make_slab_plan(sp, lg_n, lg_g, rank, inverse != 0, lg_tile, F::NTT_MAX_LG_R)) return -1;
-    const Pass& d = which == 1 ? sp.pass1 : sp.pass2;
-    uint32_t nthreads = tile_threads<F>(d), ntiles = 1u << (lg_n - lg_g - d.lg_r - d.lg_w);
-    std::vector<T> smem(smem_elems(d));
-    const KDyn k{d};
-    for (uint32_t t = 0; t < ntiles; t++) {
-        for (uint32_t tid = 0; tid < nthreads; tid++) phase_twiddles<F>(k, tb.view, smem.data(), tid, nthreads);
-        for (uint32_t tid = 0; tid < nthreads; tid++) phase_load<F>(k, d, tb.view, in, smem.data(), t, tid, nthreads);
-        for (uint32_t s = 0; s < step_count<F>(d.lg_r); s++)
-            for (uint32_t tid = 0; tid < nthreads; tid++)
-                phase_step_dyn<F>(k, smem.data(), s * F::LG_EPT, step_log_e<F>(d.lg_r, s), tid);
-        for (uint32_t tid = 0; tid < nthreads; tid++) phase_store<F>(k, d, tb.view, out, smem.data(), t, tid, nthreads);
+    if (which == 2 && sp.needs_scratch && in == out) return -2;
+    auto run = [&](const Pass& d, const T* src, T* dst) {
+        uint32_t nthreads = tile_threads<F>(d), ntiles = 1u << (lg_n - lg_g - d.lg_r - d.lg_w);
+        std::vector<T> smem(smem_elems(d));
+        const KDyn k{d};
+        for (uint32_t t = 0; t < ntiles; t++) {
+            for (uint32_t tid = 0; tid < nthreads; tid++) phase_twiddles<F>(k, tb.view, smem.data(), tid, nthreads);
+            for (uint32_t tid = 0; tid < nthreads; tid++) phase_load<F>(k, d, tb.view, src, smem.data(), t, tid, nthreads);
+            for (uint32_t s = 0; s < step_count<F>(d.lg_r); s++)
+                for (uint32_t tid = 0; tid < nthreads; tid++)
+                    phase_step_dyn<F>(k, smem.data(), s * F::LG_EPT, step_log_e<F>(d.lg_r, s), tid);
+            for (uint32_t tid = 0; tid < nthreads; tid++) phase_store<F>(k, d, tb.view, dst, smem.data(), t, tid, nthreads);
+        }
+    };
+    if (which == 1) {
+        run(sp.pass1, in, out);
+    } else {
+        T* buf[2] = {const_cast<T*>(in), out};
+        for (const Pass& d : sp.after) run(d, buf[d.src], buf[d.dst]);
     }
     return 0;
 }
+extern "C" int emu_slab_first_digit(uint32_t lg_n, uint32_t max_lg_r) { return (int)slab_first_digit(lg_n, max_lg_r); }
 extern "C" int emu_ntt_slab_gl64(int which, const uint64_t* in, uint64_t* out, uint32_t lg_n, uint32_t lg_g,
                                  uint32_t rank, int inverse, uint32_t lg_tile)
 {   return emu_slab_pass<gl64>(which, in, out, lg_n, lg_g, rank, inverse, lg_tile);   }

@@ -31,6 +31,7 @@ def ntt_emu():
     l.emu_ntt_256.argtypes = [C.c_int, C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_uint]
     l.emu_ntt_slab_gl64.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_uint]
     l.emu_ntt_slab_bb31.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_uint]
+    l.emu_slab_first_digit.argtypes = [C.c_uint, C.c_uint]
     return l
 
 
@@ -108,6 +109,48 @@ def test_ntt_slab_sharded(oracle, ntt_emu, lg, lg_g, lg_tile):
                 fn(2, recv.ctypes.data, recv.ctypes.data, lg, lg_g, r, inv, lg_tile)
                 outs.append(recv)
             assert np.array_equal(parallel.gather_columns(outs, lg, lg_g), ofn(x, 0, bool(inv))), (field, inv)
+
+
+@pytest.mark.parametrize("lg,lg_g,split,lg_tile", [
+    (8, 1, "3,3,2", 14), (8, 3, "3,3,2", 5), (9, 2, "3,3,3", 14), (9, 3, "4,2,3", 6), (10, 2, "4,3,3", 14),
+    (8, 2, "2,2,2,2", 14), (11, 3, "3,4,4", 7), (12, 3, "3,1,8", 14), (14, 3, "5,5,4", 14), (9, 3, "3,3,3", 14)])
+def test_ntt_slab_sharded_multipass(oracle, ntt_emu, lg, lg_g, split, lg_tile, monkeypatch):
+    """Sizes whose second factor N2 does not fit one tile (BabyBear 2^27 = 2^9 x 2^18 on the GPU):
+    after the all-to-all the N2-point column NTTs are the remaining digits of the NN schedule,
+    ping-ponging between the received buffer and a scratch buffer.  Small digits stand in for
+    the 2^12-row tiles here."""
+    from sppark_b200 import parallel
+    monkeypatch.setenv("SPPARK_B200_NTT_SPLIT", split)
+    s1 = int(split.split(",")[0])
+    assert ntt_emu.emu_slab_first_digit(lg, 12) == s1
+    G = 1 << lg_g
+    rng = np.random.default_rng(lg * 16 + lg_g)
+    for field, fn, ofn, dt, p in (("gl64", ntt_emu.emu_ntt_slab_gl64, oracle.ntt_gl64, np.uint64, 2**64 - 2**32 + 1),
+                                  ("bb31", ntt_emu.emu_ntt_slab_bb31, oracle.ntt_bb31, np.uint32, 0x78000001)):
+        x = rng.integers(0, p, size=1 << lg, dtype=dt)
+        for inv in (0, 1):
+            stag = []
+            for r in range(G):
+                loc = parallel.scatter_columns(x, lg, lg_g, r, s1=s1).reshape(-1).copy()
+                st = np.zeros_like(loc)
+                assert fn(1, loc.ctypes.data, st.ctypes.data, lg, lg_g, r, inv, lg_tile) == 0
+                stag.append(st.reshape(G, -1))
+            outs = []
+            for r in range(G):
+                recv = np.concatenate([stag[q][r] for q in range(G)]).copy()
+                scratch = np.zeros_like(recv)
+                assert fn(2, recv.ctypes.data, recv.ctypes.data, lg, lg_g, r, inv, lg_tile) == -2   # needs scratch
+                assert fn(2, recv.ctypes.data, scratch.ctypes.data, lg, lg_g, r, inv, lg_tile) == 0
+                outs.append(recv)
+            assert np.array_equal(parallel.gather_columns(outs, lg, lg_g, s1=s1), ofn(x, 0, bool(inv))), (field, inv)
+
+
+def test_slab_first_digit_matches_planner(ntt_emu, monkeypatch):
+    from sppark_b200 import parallel
+    monkeypatch.delenv("SPPARK_B200_NTT_SPLIT", raising=False)
+    for max_r, field in ((12, 0), (11, 2)):
+        for lg in range(2, 33):
+            assert parallel.slab_first_digit(lg, field) == ntt_emu.emu_slab_first_digit(lg, max_r), (lg, max_r)
 
 
 def _scalars(vals):

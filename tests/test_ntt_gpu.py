@@ -210,10 +210,13 @@ def test_ntt_256bit_2pow22_roundtrip():
     assert np.array_equal(x, y)
 
 
-@pytest.mark.parametrize("field,lg,lg_g", [("gl64", 16, 1), ("gl64", 20, 3), ("bb31", 18, 2), ("gl64", 24, 3)])
+@pytest.mark.parametrize("field,lg,lg_g", [("gl64", 16, 1), ("gl64", 20, 3), ("bb31", 18, 2), ("gl64", 24, 3),
+                                           ("gl64", 25, 1), ("bb31", 26, 2), ("bb31", 27, 3)])
 def test_slab_sharded_transform_on_one_gpu(oracle, field, lg, lg_g):
     """The multi-GPU NTT with its G ranks run one after another on this GPU (the exchange is a
-    tensor shuffle): both CUDA passes + layouts against the oracle's single-array transform."""
+    tensor shuffle): both CUDA stages + layouts against the oracle's single-array transform.
+    Above 2^24 the second stage is two passes (BabyBear 2^27, the field's maximum, is SURVEY.md
+    section 8d config 5: 2^9 x 2^18 over 8 ranks)."""
     import torch
     from sppark_b200 import ntt, parallel
     G = 1 << lg_g
@@ -223,18 +226,18 @@ def test_slab_sharded_transform_on_one_gpu(oracle, field, lg, lg_g):
     sdt = np.int64 if field == "gl64" else np.int32
     staged = []
     for r in range(G):
-        loc = torch.from_numpy(parallel.scatter_columns(x, lg, lg_g, r).reshape(-1).view(sdt).copy()).cuda()
+        loc = torch.from_numpy(parallel.scatter_columns(x, lg, lg_g, r, fid).reshape(-1).view(sdt).copy()).cuda()
         st = torch.empty_like(loc)
         parallel.gpu_slab_pass(fid, lg, lg_g, r)(1, loc, st)
         staged.append(st.view(G, -1))
     outs = []
     for r in range(G):
         recv = torch.cat([staged[q][r] for q in range(G)]).contiguous()
-        parallel.gpu_slab_pass(fid, lg, lg_g, r)(2, recv, recv)
+        parallel.gpu_slab_pass(fid, lg, lg_g, r)(2, recv, torch.empty_like(recv) if lg > 24 else recv)
         outs.append(recv.cpu().numpy().view(x.dtype))
-    got = parallel.gather_columns(outs, lg, lg_g)
+    got = parallel.gather_columns(outs, lg, lg_g, fid)
     ofn = oracle.ntt_gl64 if field == "gl64" else oracle.ntt_bb31
-    assert np.array_equal(got, ofn(x, oracle.NN, nthreads=8))
+    assert np.array_equal(got, ofn(x, oracle.NN, nthreads=16))
 
 
 def test_gpu_ptr_handles():
