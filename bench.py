@@ -42,15 +42,30 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 10 ms from
+    a thread (a short multi-GPU run lasts less than one nvidia-smi start-up); nvidia-smi -lms as
+    the fallback when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.nvml, self.h, self.stop_flag, self.samples, self.mask, self.max = None, None, False, [], 0, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "200"],
@@ -60,11 +75,30 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+                self.mask |= int(fn(self.h))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            sm = sorted(self.samples)
+            busy = [v for v in sm if v > 0.5 * (self.max or 1)] or sm
+            return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": self.max,
+                    "reasons": sorted(nm for bit, nm in self.BITS.items() if self.mask & bit),
+                    "samples": len(sm), "source": "nvml, 10 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -82,7 +116,7 @@ class ClockSampler:
                     reasons.add(nm)
         busy = [v for v in sm if v > 0.5 * (mx[0] if mx else 1)] or sm
         return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx[0] if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 200"}
 
 
 def fold_scalars(sc, m):
@@ -424,6 +458,22 @@ def bench_ntt_sharded(args, torch, _lib, peak, peak_src, barrier, max_over_ranks
     lg_g = world.bit_length() - 1
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
+    def timed(step, iters):
+        for _ in range(max(3, args.warmup)):
+            step()
+        barrier()
+        tot = 0.0
+        for _ in range(iters):
+            flush.zero_()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            e1.synchronize()
+            tot += max_over_ranks(e0.elapsed_time(e1))
+        return tot / iters
+
     def run(fid, lg, name, esz, iters):
         n_local = (1 << lg) // world
         rng = np.random.default_rng(7 + rank)
@@ -432,26 +482,39 @@ def bench_ntt_sharded(args, torch, _lib, peak, peak_src, barrier, max_over_ranks
         else:
             local = torch.from_numpy(rng.integers(0, 0x78000001, size=n_local, dtype=np.uint32).view(np.int32)).cuda()
         pass_fn = parallel.gpu_slab_pass(fid, lg, lg_g, rank)
-        for _ in range(max(3, args.warmup)):
-            parallel.ntt_slab(local, lg, fid, pass_fn)
-        barrier()
-        tot = 0.0
-        for _ in range(iters):
-            flush.zero_()
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            parallel.ntt_slab(local, lg, fid, pass_fn)
-            e1.record()
-            e1.synchronize()
-            tot += max_over_ranks(e0.elapsed_time(e1))
-        ms = tot / iters
+        # baseline exchange: staging buffer + NCCL all-to-all between the two local stages
+        ms_nccl = timed(lambda: parallel.ntt_slab(local, lg, fid, pass_fn), iters)
+        # fused exchange: stage 1 stores straight into the receivers over NVLink peer memory
+        exchange, ms, why = "NCCL all_to_all_single", ms_nccl, None
+        if os.environ.get("SPPARK_B200_NTT_EXCHANGE", "p2p") == "p2p":
+            ok = torch.ones(1, dtype=torch.int32, device="cuda")
+            peers = None
+            try:
+                peers = parallel.SlabPeers(n_local * esz)
+                scratch = torch.empty_like(local)
+                ref = parallel.ntt_slab(local, lg, fid, pass_fn)
+                got = parallel.ntt_slab_p2p(local, lg, fid, rank, peers, scratch)
+                if not torch.equal(ref, got):
+                    raise RuntimeError("fused exchange result differs from the all-to-all route")
+            except Exception as e:                       # e.g. no peer access between these GPUs
+                why = f"{type(e).__name__}: {e}"
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)    # all ranks take the same route
+            if int(ok.item()):
+                ms = timed(lambda: parallel.ntt_slab_p2p(local, lg, fid, rank, peers, scratch), iters)
+                exchange = "fused into stage 1: NVLink peer stores (CUDA IPC), 4-byte all-reduce as the barrier"
+            if peers is not None:
+                try:
+                    peers.close()
+                except Exception:
+                    pass
         alg = 2 * (1 << lg) * esz
         n1 = 1 << parallel.slab_first_digit(lg, fid)
         return {"metric": f"{name} NTT/s @2^{lg} (NN, forward)", "value": 1e3 / ms, "unit": "NTT/s",
                 "ms_per_ntt": ms, "scaling": "strong", "iters": iters,
-                "sharding": f"column slabs x{world} of a {n1} x {(1 << lg) // n1} matrix, one all-to-all of "
-                            f"{n_local * esz * (world - 1) // world} B per rank",
+                "sharding": f"column slabs x{world} of a {n1} x {(1 << lg) // n1} matrix, "
+                            f"{n_local * esz * (world - 1) // world} B per rank cross NVLink",
+                "exchange": exchange, "ms_with_nccl_all_to_all": ms_nccl, "fused_exchange_error": why,
                 "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
                              "frac": alg / (ms * 1e-3) / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src},
                 "e2e": None}

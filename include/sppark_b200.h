@@ -132,6 +132,22 @@ RustError sppark_b200_ntt_slab_pass(int field, int which, const void *d_in, void
                                     uint32_t lg_domain_size, uint32_t lg_g, uint32_t rank,
                                     int ntt_direction, void *stream);
 
+/* Fused exchange: stage 1 of the slab-sharded NTT storing every output row directly into the
+ * receive buffer of the rank that owns it (NVLink peer memory) -- no staging buffer, no
+ * all-to-all.  peer_recv[q], q < 2^lg_g (<= 8), = rank q's receive buffer of 2^(lg-lg_g)
+ * elements as mapped into THIS process (sppark_b200_peer_open; peer_recv[rank] = the local
+ * buffer).  The caller synchronises the ranks (any collective on `stream`) before stage 2
+ * (sppark_b200_ntt_slab_pass, which = 2) reads its own buffer. */
+RustError sppark_b200_ntt_slab_pass_p2p(int field, const void *d_in, void *const *peer_recv,
+                                        uint32_t lg_domain_size, uint32_t lg_g, uint32_t rank,
+                                        int ntt_direction, void *stream);
+/* Peer buffers (one process per GPU): cudaMalloc + CUDA IPC handle (64 bytes) on the owner,
+ * cudaIpcOpenMemHandle / cudaIpcCloseMemHandle on the other ranks of the same node. */
+RustError sppark_b200_peer_alloc(size_t bytes, void **d_ptr, void *ipc_handle_64);
+RustError sppark_b200_peer_open(const void *ipc_handle_64, void **d_ptr);
+RustError sppark_b200_peer_close(void *d_ptr);
+RustError sppark_b200_peer_free(void *d_ptr);
+
 /* MSM on any supported curve with host pointers (mult_pippenger's signature + curve id;
  * the reference has no PoC boundary for Pasta). */
 RustError sppark_b200_msm(int curve, void *out_jacobian, const void *points_affine,

@@ -35,6 +35,12 @@ _SIGS = {
     "sppark_b200_lde": [C.c_int, C.c_size_t, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p],
     "sppark_b200_ntt_slab_pass": [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                   C.c_int, C.c_void_p],
+    "sppark_b200_ntt_slab_pass_p2p": [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                      C.c_int, C.c_void_p],
+    "sppark_b200_peer_alloc": [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p],
+    "sppark_b200_peer_open": [C.c_void_p, C.POINTER(C.c_void_p)],
+    "sppark_b200_peer_close": [C.c_void_p],
+    "sppark_b200_peer_free": [C.c_void_p],
     "sppark_b200_msm": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t],
     "sppark_b200_msm_dev": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p],
     "sppark_b200_generate_points_dev": [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p],

@@ -92,3 +92,51 @@ extern "C" void* sppark_b200_gpu_ptr_get(const gpu_ptr_t* ref)
 
 extern "C" size_t sppark_b200_gpu_ptr_refs(const gpu_ptr_t* ref)
 {   gpu_ptr_inner* in = inner_of(ref); return in ? in->ref_cnt.load() : 0;   }
+
+// ---- peer buffers for the fused NTT exchange (ntt/ntt_plan.hpp: make_slab_plan) -------------
+// One process per GPU: each rank allocates its receive buffer with cudaMalloc, exports a CUDA IPC
+// handle (64 bytes, exchanged by the caller over its process group), and maps the other ranks'
+// buffers; stores to the mapped pointers travel over NVLink / NVSwitch.
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+
+extern "C" RustError sppark_b200_peer_alloc(size_t bytes, void** d_ptr, void* ipc_handle)
+{
+    try {
+        if (d_ptr == nullptr || ipc_handle == nullptr) throw cuda_error(-(int)cudaErrorInvalidValue, "peer_alloc: null argument");
+        (void)gpu_of_current_device();
+        CUDA_OK(cudaMalloc(d_ptr, bytes ? bytes : 1));
+        cudaIpcMemHandle_t h;
+        cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
+        if (e != cudaSuccess) { (void)cudaFree(*d_ptr); *d_ptr = nullptr; CUDA_OK(e); }
+        memcpy(ipc_handle, &h, sizeof(h));
+    } catch (const cuda_error& e) {
+        return rust_err(e.code(), e.what());
+    }
+    return rust_ok();
+}
+
+extern "C" RustError sppark_b200_peer_open(const void* ipc_handle, void** d_ptr)
+{
+    try {
+        if (d_ptr == nullptr || ipc_handle == nullptr) throw cuda_error(-(int)cudaErrorInvalidValue, "peer_open: null argument");
+        (void)gpu_of_current_device();
+        cudaIpcMemHandle_t h;
+        memcpy(&h, ipc_handle, sizeof(h));
+        CUDA_OK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    } catch (const cuda_error& e) {
+        return rust_err(e.code(), e.what());
+    }
+    return rust_ok();
+}
+
+extern "C" RustError sppark_b200_peer_close(void* d_ptr)
+{
+    cudaError_t e = cudaIpcCloseMemHandle(d_ptr);
+    return e == cudaSuccess ? rust_ok() : rust_err(-(int)e, cudaGetErrorString(e));
+}
+
+extern "C" RustError sppark_b200_peer_free(void* d_ptr)
+{
+    cudaError_t e = cudaFree(d_ptr);
+    return e == cudaSuccess ? rust_ok() : rust_err(-(int)e, cudaGetErrorString(e));
+}

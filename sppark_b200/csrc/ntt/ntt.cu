@@ -120,14 +120,14 @@ static RustError ntt_dev(void* d_inout, uint32_t lg, int order, int direction, i
 
 template<class F>
 static RustError ntt_slab(int which, const void* d_in, void* d_out, uint32_t lg, uint32_t lg_g, uint32_t rank,
-                          int direction, void* stream)
+                          int direction, void* stream, void* const* peers = nullptr)
 {
     typedef ntt::NTT<F> N;
     if (direction < 0 || direction > 1 || (which != 1 && which != 2))
         return rust_err(-(int)cudaErrorInvalidValue, "ntt_slab_pass: bad direction / pass");
     try {
         N::slab_pass(gpu_of_current_device(), which, (const typename F::T*)d_in, (typename F::T*)d_out, lg, lg_g,
-                     rank, (typename N::Direction)direction, (cudaStream_t)stream);
+                     rank, (typename N::Direction)direction, (cudaStream_t)stream, peers);
         return rust_ok();
     } catch (const cuda_error& e) {
         return rust_err(e.code(), e.what());
@@ -170,6 +170,20 @@ extern "C" RustError sppark_b200_ntt_slab_pass(int field, int which, const void*
     case SPPARK_FIELD_PALLAS_FR: return ntt_slab<ff::pallas_fr_ntt>(which, d_in, d_out, lg, lg_g, rank, direction, stream);
     case SPPARK_FIELD_VESTA_FR: return ntt_slab<ff::vesta_fr_ntt>(which, d_in, d_out, lg, lg_g, rank, direction, stream);
     default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_ntt_slab_pass: unknown field");
+    }
+}
+
+extern "C" RustError sppark_b200_ntt_slab_pass_p2p(int field, const void* d_in, void* const* peer_recv,
+                                                   uint32_t lg, uint32_t lg_g, uint32_t rank, int direction, void* stream)
+{
+    if (peer_recv == nullptr) return rust_err(-(int)cudaErrorInvalidValue, "ntt_slab_pass_p2p: no peer buffers");
+    switch (field) {
+    case SPPARK_FIELD_GL64: return ntt_slab<gl64>(1, d_in, nullptr, lg, lg_g, rank, direction, stream, peer_recv);
+    case SPPARK_FIELD_BB31: return ntt_slab<bb31>(1, d_in, nullptr, lg, lg_g, rank, direction, stream, peer_recv);
+    case SPPARK_FIELD_BLS12_381_FR: return ntt_slab<ff::bls12_381_fr_ntt>(1, d_in, nullptr, lg, lg_g, rank, direction, stream, peer_recv);
+    case SPPARK_FIELD_PALLAS_FR: return ntt_slab<ff::pallas_fr_ntt>(1, d_in, nullptr, lg, lg_g, rank, direction, stream, peer_recv);
+    case SPPARK_FIELD_VESTA_FR: return ntt_slab<ff::vesta_fr_ntt>(1, d_in, nullptr, lg, lg_g, rank, direction, stream, peer_recv);
+    default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_ntt_slab_pass_p2p: unknown field");
     }
 }
 

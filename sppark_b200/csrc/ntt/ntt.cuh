@@ -272,8 +272,12 @@ public:
     // [N2][N1/G] matrix, transformed down its columns with the result left in d_in; d_out is
     // scratch of the same size, touched only when N2 needs more than one pass (it may equal d_in
     // otherwise).  Enqueued on `stream`.
+    // peers != nullptr (which = 1 only): fused exchange -- 2^lg_g device pointers, peers[q] = rank
+    // q's receive buffer mapped into this process (NVLink peer memory); the pass stores every
+    // output row straight into its receiver and d_out is not touched.
     static void slab_pass(const gpu_t& gpu, int which, const T* d_in, T* d_out, uint32_t lg_n,
-                          uint32_t lg_g, uint32_t rank, Direction direction, cudaStream_t stream)
+                          uint32_t lg_g, uint32_t rank, Direction direction, cudaStream_t stream,
+                          void* const* peers = nullptr)
     {
         const bool inverse = direction == Direction::inverse;
         if (lg_n > (uint32_t)F::MAX_LG || lg_n > 30 || rank >= (1u << lg_g))
@@ -304,7 +308,14 @@ public:
             COUNT_LAUNCH();
             CUDA_OK(cudaGetLastError());
         };
-        if (which == 1) {
+        if (which == 1 && peers != nullptr) {
+            if (lg_g > 3)
+                throw cuda_error(-(int)cudaErrorInvalidValue, "NTT slab: fused exchange supports up to 8 ranks");
+            Pass d = sp.pass1;
+            d.peer_on = 1;
+            for (uint32_t q = 0; q < (1u << lg_g); q++) d.peer[q] = (uint64_t)(uintptr_t)peers[q];
+            run(d, d_in, nullptr);
+        } else if (which == 1) {
             run(sp.pass1, d_in, d_out);
         } else {
             T* buf[2] = {const_cast<T*>(d_in), d_out};

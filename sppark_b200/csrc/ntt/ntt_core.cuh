@@ -50,6 +50,12 @@ struct Pass {
     // twiddle column is offset by the first column this rank owns
     uint32_t out_split_bits, out_split_shift;
     uint32_t tw_col_offset;
+    // fused exchange (peer_on != 0): the store goes straight into the RECEIVING rank's buffer over
+    // NVLink instead of a local staging block: destination q = row >> peer_shift, address =
+    // peer[q] + peer_block (this sender's block in every receiver) + tile/row/column offsets
+    uint32_t peer_on, peer_shift;
+    uint64_t peer_block;
+    uint64_t peer[8];
 };
 
 template<class F> struct Tables {
@@ -266,6 +272,12 @@ HD void phase_store(const K k, const Pass& d, const Tables<F>& tb, typename F::T
             if (d.scale)
                 x = F::mul(x, tb.ninv);
             uint64_t row_off = (uint64_t)v << d.out_lg_sa;
+            if (d.peer_on) {
+                const uint32_t vl = v & ((1u << d.peer_shift) - 1);
+                T* dst = reinterpret_cast<T*>(d.peer[v >> d.peer_shift]);
+                dst[d.peer_block + obase + ((uint64_t)vl << d.out_lg_sa) + ((uint64_t)c << d.out_lg_sc)] = F::canon(x);
+                continue;
+            }
             if (d.out_split_bits)
                 row_off = ((uint64_t)(v >> d.out_split_bits) << d.out_split_shift) +
                           ((uint64_t)(v & ((1u << d.out_split_bits) - 1)) << d.out_lg_sa);

@@ -212,6 +212,10 @@ inline bool make_slab_plan(SlabPlan& sp, uint32_t lg_n, uint32_t lg_g, uint32_t 
         d.out_tl = 1ull << lg_w;
     }
     d.src = 0; d.dst = 1;
+    // fused-exchange variant: same tile, rows routed to the receivers (enabled by the caller
+    // filling d.peer[] and setting peer_on)
+    d.peer_shift = ld;                                    // ld == 0: the row IS the destination
+    d.peer_block = (uint64_t)rank << (lc + ld);
     sp.pass1 = d;
 
     // digits 2..P on the received [N2][N1/G] array: the NN schedule of make_plan with the global

@@ -128,3 +128,100 @@ def gpu_slab_pass(field, lg_n, lg_g, rank, inverse=False):
                                                        rank, int(inverse), torch.cuda.current_stream().cuda_stream)
         _lib.check(err)
     return run
+
+
+# ------------------------------------------------------------ fused exchange over peer memory
+class _DevMem:
+    """Exposes a raw device allocation to torch (torch.as_tensor aliases it, no copy)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class SlabPeers:
+    """Receive buffers of the slab-sharded NTT, mapped into every rank of the node.
+
+    Each rank cudaMallocs `nbuf` receive buffers of `nbytes` (its [N2][N1/G] slab), the CUDA IPC
+    handles are all-gathered over the process group and opened by the other ranks, so stage 1 can
+    store its output rows directly into the rank that owns them (sppark_b200_ntt_slab_pass_p2p):
+    the all-to-all disappears into the store phase of the kernel and overlaps its arithmetic.
+    Buffers alternate between calls, so a rank may start the next transform while a peer still
+    reads the previous result (see ntt_slab_p2p)."""
+
+    def __init__(self, nbytes, nbuf=2, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        self._lib, self.nbytes, self.nbuf = _lib, nbytes, nbuf
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.local, self.opened, handles = [], [], []
+        for _ in range(nbuf):
+            ptr, h = C.c_void_p(), (C.c_ubyte * 64)()
+            _lib.check(_lib.lib().sppark_b200_peer_alloc(nbytes, C.byref(ptr), h))
+            self.local.append(ptr.value)
+            handles.append(bytes(h))
+        everyone = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(everyone, handles, group=group)
+        else:
+            everyone[0] = handles
+        self.ptrs = []                                   # ptrs[k] = ctypes array of `world` pointers
+        for k in range(nbuf):
+            arr = (C.c_void_p * max(self.world, 1))()
+            for q in range(self.world):
+                if q == self.rank:
+                    arr[q] = self.local[k]
+                else:
+                    p = C.c_void_p()
+                    _lib.check(_lib.lib().sppark_b200_peer_open(everyone[q][k], C.byref(p)))
+                    self.opened.append(p.value)
+                    arr[q] = p.value
+            self.ptrs.append(arr)
+        self.flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self.turn = 0
+        self._views = [torch.as_tensor(_DevMem(p, nbytes), device="cuda") for p in self.local]
+        if self.world > 1:
+            dist.barrier(group=group)                    # every mapping exists before anyone stores
+
+    def tensor(self, k, dtype):
+        return self._views[k].view(dtype)
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize()
+        for p in self.opened:
+            self._lib.lib().sppark_b200_peer_close(p)
+        self.opened = []
+        self._views = []
+        for p in self.local:
+            self._lib.lib().sppark_b200_peer_free(p)
+        self.local = []
+
+
+def ntt_slab_p2p(local, lg_n, field, rank, peers, scratch, inverse=False):
+    """Slab-sharded NTT with the exchange fused into stage 1 (NVLink peer stores).  `local`: this
+    rank's [N1][N2/G] slab (CUDA tensor); returns its [N2][N1/G] slab of the result, a view of one
+    of `peers`' buffers, valid until the call after next.  `scratch`: a tensor like `local`, used
+    only when N2 takes several passes.
+
+    Ordering: the tiny all-reduce after stage 1 completes on a rank only when every rank's stage 1
+    (stream-ordered before its contribution) has finished, i.e. when all rows have landed; the
+    receive buffers alternate, and reaching call k+2 implies every peer has passed the all-reduce
+    of call k+1, which it enqueued after its stage 2 of call k -- so buffer k%2 is free again."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    lg_g = max(peers.world.bit_length() - 1, 0)
+    k = peers.turn
+    peers.turn = (k + 1) % peers.nbuf
+    stream = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.lib().sppark_b200_ntt_slab_pass_p2p(field, local.data_ptr(), peers.ptrs[k], lg_n, lg_g, rank,
+                                                         int(inverse), stream))
+    if peers.world > 1:
+        dist.all_reduce(peers.flag)
+    recv = peers.tensor(k, local.dtype)
+    _lib.check(_lib.lib().sppark_b200_ntt_slab_pass(field, 2, recv.data_ptr(), scratch.data_ptr(), lg_n, lg_g, rank,
+                                                     int(inverse), stream))
+    return recv

@@ -81,7 +81,7 @@ static int emu_run(typename F::T* data, uint32_t lg_n, int order, int inverse, u
 // which = 1: in -> out (staging); which = 2: `in` transformed with `out` as scratch, result in `in`
 template<class F>
 static int emu_slab_pass(int which, const typename F::T* in, typename F::T* out, uint32_t lg_n, uint32_t lg_g,
-                         uint32_t rank, int inverse, uint32_t lg_tile)
+                         uint32_t rank, int inverse, uint32_t lg_tile, void* const* peers = nullptr)
 {
     typedef typename F::T T;
     HostTables<F> tb(lg_n, inverse != 0);
@@ -101,7 +101,12 @@ static int emu_slab_pass(int which, const typename F::T* in, typename F::T* out,
             for (uint32_t tid = 0; tid < nthreads; tid++) phase_store<F>(k, d, tb.view, dst, smem.data(), t, tid, nthreads);
         }
     };
-    if (which == 1) {
+    if (which == 1 && peers) {                       // fused exchange: rows go straight to their receiver
+        Pass d = sp.pass1;
+        d.peer_on = 1;
+        for (uint32_t q = 0; q < (1u << lg_g); q++) d.peer[q] = (uint64_t)(uintptr_t)peers[q];
+        run(d, in, nullptr);
+    } else if (which == 1) {
         run(sp.pass1, in, out);
     } else {
         T* buf[2] = {const_cast<T*>(in), out};
@@ -109,6 +114,12 @@ static int emu_slab_pass(int which, const typename F::T* in, typename F::T* out,
     }
     return 0;
 }
+extern "C" int emu_ntt_slab_p2p_gl64(const uint64_t* in, void* const* peers, uint32_t lg_n, uint32_t lg_g,
+                                     uint32_t rank, int inverse, uint32_t lg_tile)
+{   return emu_slab_pass<gl64>(1, in, nullptr, lg_n, lg_g, rank, inverse, lg_tile, peers);   }
+extern "C" int emu_ntt_slab_p2p_bb31(const uint32_t* in, void* const* peers, uint32_t lg_n, uint32_t lg_g,
+                                     uint32_t rank, int inverse, uint32_t lg_tile)
+{   return emu_slab_pass<bb31>(1, in, nullptr, lg_n, lg_g, rank, inverse, lg_tile, peers);   }
 extern "C" int emu_slab_first_digit(uint32_t lg_n, uint32_t max_lg_r) { return (int)slab_first_digit(lg_n, max_lg_r); }
 extern "C" int emu_ntt_slab_gl64(int which, const uint64_t* in, uint64_t* out, uint32_t lg_n, uint32_t lg_g,
                                  uint32_t rank, int inverse, uint32_t lg_tile)

@@ -32,6 +32,8 @@ def ntt_emu():
     l.emu_ntt_slab_gl64.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_uint]
     l.emu_ntt_slab_bb31.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_uint]
     l.emu_slab_first_digit.argtypes = [C.c_uint, C.c_uint]
+    l.emu_ntt_slab_p2p_gl64.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_uint]
+    l.emu_ntt_slab_p2p_bb31.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_uint]
     return l
 
 
@@ -143,6 +145,37 @@ def test_ntt_slab_sharded_multipass(oracle, ntt_emu, lg, lg_g, split, lg_tile, m
                 assert fn(2, recv.ctypes.data, scratch.ctypes.data, lg, lg_g, r, inv, lg_tile) == 0
                 outs.append(recv)
             assert np.array_equal(parallel.gather_columns(outs, lg, lg_g, s1=s1), ofn(x, 0, bool(inv))), (field, inv)
+
+
+@pytest.mark.parametrize("lg,lg_g,split,lg_tile", [(4, 1, None, 14), (6, 2, None, 14), (8, 3, None, 6), (10, 3, None, 14),
+                                                   (6, 3, None, 14), (2, 1, None, 14), (12, 0, None, 14),
+                                                   (9, 3, "3,3,3", 14), (11, 2, "3,4,4", 7)])
+def test_ntt_slab_fused_exchange(oracle, ntt_emu, lg, lg_g, split, lg_tile, monkeypatch):
+    """Stage 1 storing its rows directly into the receivers' buffers (the NVLink peer-memory path
+    of sppark_b200_ntt_slab_pass_p2p; here the "peers" are G host arrays) must leave in every
+    receive buffer exactly what the staging + all-to-all route delivers."""
+    from sppark_b200 import parallel
+    if split:
+        monkeypatch.setenv("SPPARK_B200_NTT_SPLIT", split)
+    else:
+        monkeypatch.delenv("SPPARK_B200_NTT_SPLIT", raising=False)
+    s1 = int(split.split(",")[0]) if split else None
+    G = 1 << lg_g
+    rng = np.random.default_rng(lg * 32 + lg_g)
+    for fn, p2p, ofn, dt, p in ((ntt_emu.emu_ntt_slab_gl64, ntt_emu.emu_ntt_slab_p2p_gl64, oracle.ntt_gl64, np.uint64, 2**64 - 2**32 + 1),
+                                (ntt_emu.emu_ntt_slab_bb31, ntt_emu.emu_ntt_slab_p2p_bb31, oracle.ntt_bb31, np.uint32, 0x78000001)):
+        x = rng.integers(0, p, size=1 << lg, dtype=dt)
+        recv = [np.zeros((1 << lg) // G, dtype=dt) for _ in range(G)]
+        ptrs = (C.c_void_p * G)(*[r.ctypes.data for r in recv])
+        for r in range(G):
+            loc = parallel.scatter_columns(x, lg, lg_g, r, s1=s1).reshape(-1).copy()
+            assert p2p(loc.ctypes.data, ptrs, lg, lg_g, r, 0, lg_tile) == 0
+        outs = []
+        for r in range(G):
+            scratch = np.zeros_like(recv[r])
+            assert fn(2, recv[r].ctypes.data, scratch.ctypes.data, lg, lg_g, r, 0, lg_tile) == 0
+            outs.append(recv[r])
+        assert np.array_equal(parallel.gather_columns(outs, lg, lg_g, s1=s1), ofn(x, 0, False))
 
 
 def test_slab_first_digit_matches_planner(ntt_emu, monkeypatch):

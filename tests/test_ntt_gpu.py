@@ -240,6 +240,38 @@ def test_slab_sharded_transform_on_one_gpu(oracle, field, lg, lg_g):
     assert np.array_equal(got, ofn(x, oracle.NN, nthreads=16))
 
 
+@pytest.mark.parametrize("field,lg,lg_g", [("gl64", 16, 1), ("gl64", 20, 3), ("bb31", 18, 2), ("gl64", 24, 3), ("bb31", 25, 3)])
+def test_slab_fused_exchange_on_one_gpu(oracle, field, lg, lg_g):
+    """sppark_b200_ntt_slab_pass_p2p: stage 1 stores its rows straight into the receivers' buffers
+    (NVLink peer memory between processes; here the G receivers are G allocations of this GPU,
+    one of them through the library's peer_alloc).  No staging buffer, no exchange step."""
+    import ctypes as C
+    import torch
+    from sppark_b200 import _lib, parallel
+    G = 1 << lg_g
+    fid = 0 if field == "gl64" else 1
+    x = _rand(field, 1 << lg, lg + lg_g + 1)
+    tdt = torch.int64 if field == "gl64" else torch.int32
+    sdt = np.int64 if field == "gl64" else np.int32
+    n_local = (1 << lg) // G
+    peers = parallel.SlabPeers(n_local * x.dtype.itemsize, nbuf=1)          # world = 1: owns one buffer
+    recv = [peers.tensor(0, tdt)] + [torch.empty(n_local, dtype=tdt, device="cuda") for _ in range(G - 1)]
+    ptrs = (C.c_void_p * G)(*[t.data_ptr() for t in recv])
+    stream = torch.cuda.current_stream().cuda_stream
+    for r in range(G):
+        loc = torch.from_numpy(parallel.scatter_columns(x, lg, lg_g, r, fid).reshape(-1).view(sdt).copy()).cuda()
+        _lib.check(_lib.lib().sppark_b200_ntt_slab_pass_p2p(fid, loc.data_ptr(), ptrs, lg, lg_g, r, 0, stream))
+    outs = []
+    scratch = torch.empty(n_local, dtype=tdt, device="cuda")
+    for r in range(G):
+        parallel.gpu_slab_pass(fid, lg, lg_g, r)(2, recv[r], scratch)
+        outs.append(recv[r].cpu().numpy().view(x.dtype))
+    got = parallel.gather_columns(outs, lg, lg_g, fid)
+    peers.close()
+    ofn = oracle.ntt_gl64 if field == "gl64" else oracle.ntt_bb31
+    assert np.array_equal(got, ofn(x, oracle.NN, nthreads=16))
+
+
 def test_gpu_ptr_handles():
     """clone_gpu_ptr_t / drop_gpu_ptr_t keep the reference's ownership protocol
     (util/gpu_t.cuh:268-316): the memory lives until the last handle is dropped."""
