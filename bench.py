@@ -447,6 +447,11 @@ def bench_ntt(args, torch, ntt, _lib, peak, peak_src, barrier, max_over_ranks, w
     return res
 
 
+# NCCL may be told to print its version banner (NCCL_DEBUG=VERSION): keep it off stdout, which
+# carries exactly one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
 def bench_ntt_sharded(args, torch, _lib, peak, peak_src, barrier, max_over_ranks, world):
     """ONE transform slab-sharded over the ranks.  Headline: Goldilocks 2^lg.  Also reported
     (SURVEY.md section 8d config 5): BabyBear 2^27, the largest transform that field admits

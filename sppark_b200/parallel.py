@@ -156,34 +156,52 @@ class SlabPeers:
         self._lib, self.nbytes, self.nbuf = _lib, nbytes, nbuf
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.local, self.opened, handles = [], [], []
-        for _ in range(nbuf):
-            ptr, h = C.c_void_p(), (C.c_ubyte * 64)()
-            _lib.check(_lib.lib().sppark_b200_peer_alloc(nbytes, C.byref(ptr), h))
-            self.local.append(ptr.value)
-            handles.append(bytes(h))
+        self.local, self.opened, handles, err = [], [], [], None
+        # every rank takes part in every collective below, whatever happened to it locally: a
+        # failure (no IPC support, no peer access) is agreed on and raised by ALL ranks together
+        try:
+            for _ in range(nbuf):
+                ptr, h = C.c_void_p(), (C.c_ubyte * 64)()
+                _lib.check(_lib.lib().sppark_b200_peer_alloc(nbytes, C.byref(ptr), h))
+                self.local.append(ptr.value)
+                handles.append(bytes(h))
+        except Exception as e:
+            err, handles = f"rank {self.rank}: {e}", None
         everyone = [None] * self.world
         if self.world > 1:
             dist.all_gather_object(everyone, handles, group=group)
         else:
             everyone[0] = handles
         self.ptrs = []                                   # ptrs[k] = ctypes array of `world` pointers
-        for k in range(nbuf):
-            arr = (C.c_void_p * max(self.world, 1))()
-            for q in range(self.world):
-                if q == self.rank:
-                    arr[q] = self.local[k]
-                else:
-                    p = C.c_void_p()
-                    _lib.check(_lib.lib().sppark_b200_peer_open(everyone[q][k], C.byref(p)))
-                    self.opened.append(p.value)
-                    arr[q] = p.value
-            self.ptrs.append(arr)
+        if all(h is not None for h in everyone):
+            try:
+                for k in range(nbuf):
+                    arr = (C.c_void_p * max(self.world, 1))()
+                    for q in range(self.world):
+                        if q == self.rank:
+                            arr[q] = self.local[k]
+                        else:
+                            p = C.c_void_p()
+                            _lib.check(_lib.lib().sppark_b200_peer_open(everyone[q][k], C.byref(p)))
+                            self.opened.append(p.value)
+                            arr[q] = p.value
+                    self.ptrs.append(arr)
+            except Exception as e:
+                err = f"rank {self.rank}: {e}"
+        elif err is None:
+            err = "a peer could not allocate its receive buffer"
+        status = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(status, err, group=group)     # doubles as the barrier: every mapping exists
+        else:
+            status[0] = err
+        self._views = []
+        if any(st is not None for st in status):
+            self.close()
+            raise RuntimeError("SlabPeers: " + "; ".join(st for st in status if st is not None))
         self.flag = torch.zeros(1, dtype=torch.int32, device="cuda")
         self.turn = 0
         self._views = [torch.as_tensor(_DevMem(p, nbytes), device="cuda") for p in self.local]
-        if self.world > 1:
-            dist.barrier(group=group)                    # every mapping exists before anyone stores
 
     def tensor(self, k, dtype):
         return self._views[k].view(dtype)
