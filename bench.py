@@ -182,10 +182,26 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "MSM/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "MSM/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line, on the process's ORIGINAL stdout."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    # stdout carries exactly one JSON line: anything a library prints on fd 1 (NCCL's version
+    # banner, for one) is sent to stderr instead
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -202,12 +218,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
+    if args.impl == "reference":            # CPU only: no CUDA, no process group
+        run_reference(args, rank, world)
+        return
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -360,7 +376,7 @@ def main():
                            "l2": "inputs (8.6 GB at 2^26) exceed L2; no flush needed"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
                 "cpu_baseline": cpu, "check": check, "ntt": ntt_res}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -445,11 +461,6 @@ def bench_ntt(args, torch, ntt, _lib, peak, peak_src, barrier, max_over_ranks, w
     res["e2e"] = {"value": 1.0 / dt, "unit": "NTT/s", "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
                   "api": "compute_ntt (host pointer, pinned)"}
     return res
-
-
-# NCCL may be told to print its version banner (NCCL_DEBUG=VERSION): keep it off stdout, which
-# carries exactly one JSON line
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 
 def bench_ntt_sharded(args, torch, _lib, peak, peak_src, barrier, max_over_ranks, world):

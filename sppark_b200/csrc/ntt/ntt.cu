@@ -65,7 +65,8 @@ template<class F> bool launch_static(const Pass& d, const Tables<F>& tb, const t
         || try_shapes<F, 11, 1>(d, tb, in, out, ntiles, smem, stream)
         || try_shapes<F, 11, 0>(d, tb, in, out, ntiles, smem, stream)
         || try_shapes<F, 10, 1>(d, tb, in, out, ntiles, smem, stream)
-        || try_shapes<F, 10, 0>(d, tb, in, out, ntiles, smem, stream);
+        || try_shapes<F, 10, 0>(d, tb, in, out, ntiles, smem, stream)
+        || try_shapes<F, 9, 5>(d, tb, in, out, ntiles, smem, stream);    // 2^27 = 9+9+9 (BabyBear's maximum)
 }
 
 template bool launch_static<gl64>(const Pass&, const Tables<gl64>&, const uint64_t*, uint64_t*, uint32_t, size_t, cudaStream_t);
