@@ -30,9 +30,12 @@
 extern "C" {
 #endif
 
-typedef struct {
+typedef struct RustError {
     int   code;
     char *message;
+#ifdef __cplusplus
+    typedef struct RustError by_value;         /* the reference's RustError::by_value: same two words */
+#endif
 } RustError;                                   /* util/rusterror.h:18-36 */
 
 /* --- memory layouts (ABI) ---------------------------------------------------------
@@ -58,6 +61,10 @@ enum { SPPARK_NTT_STANDARD = 0, SPPARK_NTT_COSET = 1 };    /* NTT::Type,      nt
 
 /* ================================ drop-in surface ================================= */
 
+/* (C++ callers that DEFINE these entry points themselves, with their own typed signatures, on
+ * top of include/sppark_b200.hpp -- the reference's poc glue does -- hide the four declarations
+ * below with SPPARK_B200_NO_DROPIN_DECLS.) */
+#ifndef SPPARK_B200_NO_DROPIN_DECLS
 /* poc/msm-cuda/cuda/pippenger.cu:20-25 ; Rust decl poc/msm-cuda/src/lib.rs:24-29.
  * BLS12-381 G1: out = sum scalars[i] * points[i]. */
 RustError mult_pippenger(void *out_jacobian, const void *points_affine, size_t npoints,
@@ -79,6 +86,7 @@ RustError mult_pippenger_fp2_inf(void *out_jacobian, const void *points_affine_i
  * poc/ntt-cuda/go/goldilocks.go:24-40 loads); in place on HOST memory; lg == 0 is a no-op. */
 RustError compute_ntt(size_t device_id, void *inout, uint32_t lg_domain_size,
                       int ntt_order, int ntt_direction, int ntt_type);
+#endif /* SPPARK_B200_NO_DROPIN_DECLS */
 
 /* util/all_gpus.cpp:65-86 */
 int  cuda_available(void);                     /* bool in the reference */
@@ -152,6 +160,11 @@ RustError sppark_b200_peer_free(void *d_ptr);
  * the reference has no PoC boundary for Pasta). */
 RustError sppark_b200_msm(int curve, void *out_jacobian, const void *points_affine,
                           size_t npoints, const void *scalars, size_t ffi_affine_sz);
+/* Same with the reference template's `mont` flag (msm/pippenger.cuh:730-733): scalars_mont != 0
+ * means the scalars are Montgomery residues (the C++ default there; the crates pass false). */
+RustError sppark_b200_msm_ex(int curve, void *out_jacobian, const void *points_affine,
+                             size_t npoints, const void *scalars, size_t ffi_affine_sz,
+                             int scalars_mont);
 /* msm_t::invoke with device-resident points and scalars (msm/pippenger.cuh:582-601):
  * d_points: packed affine {X,Y}; d_scalars: 32-B LE; result written to HOST out_jacobian
  * after synchronising `stream`. */
@@ -171,6 +184,7 @@ RustError sppark_b200_msm_combine(int curve, void *out_jacobian, const void *par
 RustError sppark_b200_selftest_field(int field, int op, size_t n, void *r, const void *a, const void *b);
 
 /* introspection */
+size_t      sppark_b200_ngpus(void);               /* ngpus(), util/gpu_t.cuh:21 */
 int         sppark_b200_sm_count(int device_id);
 const char *sppark_b200_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */

@@ -42,6 +42,7 @@ _SIGS = {
     "sppark_b200_peer_close": [C.c_void_p],
     "sppark_b200_peer_free": [C.c_void_p],
     "sppark_b200_msm": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t],
+    "sppark_b200_msm_ex": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int],
     "sppark_b200_msm_dev": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p],
     "sppark_b200_generate_points_dev": [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p],
     "sppark_b200_msm_combine": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t],
@@ -49,7 +50,7 @@ _SIGS = {
 }
 
 # every symbol include/sppark_b200.h declares (tests check the .so exports all of them)
-EXPORTS = list(_SIGS) + ["cuda_available", "drop_error_message", "sppark_b200_sm_count",
+EXPORTS = list(_SIGS) + ["cuda_available", "drop_error_message", "sppark_b200_sm_count", "sppark_b200_ngpus",
                          "sppark_b200_version", "sppark_b200_launch_count",
                          "sppark_b200_profile_enable", "sppark_b200_profile_read",
                          "drop_gpu_ptr_t", "clone_gpu_ptr_t", "sppark_b200_gpu_ptr_alloc",

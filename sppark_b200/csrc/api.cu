@@ -11,6 +11,11 @@ extern "C" int cuda_available(void)
 
 extern "C" void drop_error_message(char* msg) { free(msg); }
 
+extern "C" size_t sppark_b200_ngpus(void)
+{
+    try { return ngpus(); } catch (...) { return 0; }
+}
+
 extern "C" int sppark_b200_sm_count(int device_id)
 {
     try { return select_gpu(device_id).sm_count(); } catch (...) { return -1; }

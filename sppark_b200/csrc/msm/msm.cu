@@ -1,14 +1,14 @@
 // Curve dispatch for the extended MSM entry points (include/sppark_b200.h).
 #include "../util/gpu.cuh"
 
-RustError msm_host_bls12_381(void*, const void*, size_t, const void*, size_t, bool);
+RustError msm_host_bls12_381(void*, const void*, size_t, const void*, size_t, bool, bool);
 RustError msm_dev_bls12_381(void*, const void*, size_t, const void*, void*);
-RustError msm_host_pallas(void*, const void*, size_t, const void*, size_t, bool);
+RustError msm_host_pallas(void*, const void*, size_t, const void*, size_t, bool, bool);
 RustError msm_dev_pallas(void*, const void*, size_t, const void*, void*);
-RustError msm_host_vesta(void*, const void*, size_t, const void*, size_t, bool);
+RustError msm_host_vesta(void*, const void*, size_t, const void*, size_t, bool, bool);
 RustError msm_dev_vesta(void*, const void*, size_t, const void*, void*);
 
-RustError msm_host_bls12_381_g2(void*, const void*, size_t, const void*, size_t, bool);
+RustError msm_host_bls12_381_g2(void*, const void*, size_t, const void*, size_t, bool, bool);
 RustError msm_dev_bls12_381_g2(void*, const void*, size_t, const void*, void*);
 RustError gen_points_bls12_381_g2(void*, size_t, void*);
 RustError combine_bls12_381_g2(void*, const void*, size_t);
@@ -42,22 +42,30 @@ extern "C" RustError sppark_b200_msm_combine(int curve, void* out, const void* p
     }
 }
 
-extern "C" RustError sppark_b200_msm(int curve, void* out, const void* points, size_t npoints,
-                                     const void* scalars, size_t ffi_affine_sz)
+static RustError msm_any(int curve, void* out, const void* points, size_t npoints, const void* scalars,
+                         size_t ffi_affine_sz, bool mont)
 {
     switch (curve) {
     case SPPARK_CURVE_BLS12_381_G1:
-        return msm_host_bls12_381(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 96, ffi_affine_sz > 96);
+        return msm_host_bls12_381(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 96, ffi_affine_sz > 96, mont);
     case SPPARK_CURVE_PALLAS:
-        return msm_host_pallas(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 64, ffi_affine_sz > 64);
+        return msm_host_pallas(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 64, ffi_affine_sz > 64, mont);
     case SPPARK_CURVE_VESTA:
-        return msm_host_vesta(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 64, ffi_affine_sz > 64);
+        return msm_host_vesta(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 64, ffi_affine_sz > 64, mont);
     case SPPARK_CURVE_BLS12_381_G2:
-        return msm_host_bls12_381_g2(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 192, ffi_affine_sz > 192);
+        return msm_host_bls12_381_g2(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 192, ffi_affine_sz > 192, mont);
     default:
         return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_msm: unknown curve");
     }
 }
+
+extern "C" RustError sppark_b200_msm(int curve, void* out, const void* points, size_t npoints,
+                                     const void* scalars, size_t ffi_affine_sz)
+{   return msm_any(curve, out, points, npoints, scalars, ffi_affine_sz, false);   }
+
+extern "C" RustError sppark_b200_msm_ex(int curve, void* out, const void* points, size_t npoints,
+                                        const void* scalars, size_t ffi_affine_sz, int scalars_mont)
+{   return msm_any(curve, out, points, npoints, scalars, ffi_affine_sz, scalars_mont != 0);   }
 
 extern "C" RustError sppark_b200_msm_dev(int curve, void* out, const void* d_points, size_t npoints,
                                          const void* d_scalars, void* stream)

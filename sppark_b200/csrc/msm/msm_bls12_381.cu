@@ -2,8 +2,11 @@
 #include "msm_host.cuh"
 
 RustError msm_host_bls12_381(void* out, const void* points, size_t npoints, const void* scalars,
-                             size_t stride, bool has_flag)
-{   return msm_host<ff::bls12_381_fp_t>(out, points, npoints, scalars, stride, has_flag);   }
+                             size_t stride, bool has_flag, bool mont)
+{
+    return msm_host<ff::bls12_381_fp_t>(out, points, npoints, scalars, stride, has_flag,
+                                        mont ? scalars_from_mont<ff::bls12_381_fr_t> : nullptr);
+}
 RustError msm_dev_bls12_381(void* out, const void* d_points, size_t npoints, const void* d_scalars, void* stream)
 {   return msm_dev<ff::bls12_381_fp_t>(out, d_points, npoints, d_scalars, stream);   }
 
@@ -13,11 +16,11 @@ RustError combine_bls12_381(void* out, const void* partials, size_t count)
 {   return combine_host<ff::bls12_381_fp_t>(out, partials, count);   }
 
 extern "C" RustError mult_pippenger(void* out, const void* points, size_t npoints, const void* scalars)
-{   return msm_host_bls12_381(out, points, npoints, scalars, 96, false);   }
+{   return msm_host_bls12_381(out, points, npoints, scalars, 96, false, false);   }
 
 extern "C" RustError mult_pippenger_inf(void* out, const void* points, size_t npoints,
                                         const void* scalars, size_t ffi_affine_sz)
-{   return msm_host_bls12_381(out, points, npoints, scalars, ffi_affine_sz, true);   }
+{   return msm_host_bls12_381(out, points, npoints, scalars, ffi_affine_sz, true, false);   }
 
 // ---- device self-test hook: element-wise field ops through the PTX arithmetic -------------
 // op 0 mul, 1 add, 2 sub, 3 sqr, 4 mul_shared, 5 sqr_shared, 6 msub_shared(x,y,y,x^2).  Host arrays of n 48-byte elements.  Used by the GPU KAT tests.

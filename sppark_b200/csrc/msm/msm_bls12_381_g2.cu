@@ -10,8 +10,11 @@ struct g2_gen : ff::bls12_381_g2_gen { typedef fp2 F; };
 }
 
 RustError msm_host_bls12_381_g2(void* out, const void* points, size_t npoints, const void* scalars,
-                                size_t stride, bool has_flag)
-{   return msm_host<fp2>(out, points, npoints, scalars, stride, has_flag);   }
+                                size_t stride, bool has_flag, bool mont)
+{
+    return msm_host<fp2>(out, points, npoints, scalars, stride, has_flag,
+                         mont ? scalars_from_mont<ff::bls12_381_fr_t> : nullptr);
+}
 RustError msm_dev_bls12_381_g2(void* out, const void* d_points, size_t npoints, const void* d_scalars, void* stream)
 {   return msm_dev<fp2>(out, d_points, npoints, d_scalars, stream);   }
 RustError gen_points_bls12_381_g2(void* d_out, size_t n, void* stream)
@@ -21,4 +24,4 @@ RustError combine_bls12_381_g2(void* out, const void* partials, size_t count)
 
 extern "C" RustError mult_pippenger_fp2_inf(void* out, const void* points, size_t npoints,
                                             const void* scalars, size_t ffi_affine_sz)
-{   return msm_host_bls12_381_g2(out, points, npoints, scalars, ffi_affine_sz, true);   }
+{   return msm_host_bls12_381_g2(out, points, npoints, scalars, ffi_affine_sz, true, false);   }

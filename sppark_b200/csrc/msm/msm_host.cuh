@@ -15,9 +15,33 @@ namespace {
 // sorted and folded into the persistent buckets (compute stream).  The reference overlaps the
 // same way with its batches (msm/pippenger.cuh:505-557); here the bucket file is shared by all
 // slices, so the running sums and the Horner pass run once at the end instead of once per batch.
+// scalars handed over in Montgomery form (the reference's `mont = true`, the default of its C++
+// mult_pippenger template, msm/pippenger.cuh:730-733; `breakdown` calls from() per scalar,
+// :99-101): one Montgomery multiplication by 1 per scalar, in place on the device copy
+template<class Fr>
+__global__ void scalars_from_mont_kernel(uint32_t* scalars, size_t n)
+{
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr s, one;
+#pragma unroll
+    for (int k = 0; k < Fr::N; k++) { s.l[k] = scalars[i * Fr::N + k]; one.l[k] = k == 0; }
+    s = s * one;
+#pragma unroll
+    for (int k = 0; k < Fr::N; k++) scalars[i * Fr::N + k] = s.l[k];
+}
+template<class Fr>
+void scalars_from_mont(uint32_t* d_scalars, size_t n, cudaStream_t stream)
+{
+    scalars_from_mont_kernel<Fr><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_scalars, n);
+    COUNT_LAUNCH();
+    CUDA_OK(cudaGetLastError());
+}
+typedef void (*unmont_fn)(uint32_t*, size_t, cudaStream_t);
+
 template<class F>
 RustError msm_host(void* out, const void* points, size_t npoints, const void* scalars,
-                   size_t stride, bool has_flag)
+                   size_t stride, bool has_flag, unmont_fn unmont = nullptr)
 {
     constexpr size_t PB = 2 * F::N * 4, JB = 3 * F::N * 4;
     try {
@@ -82,6 +106,7 @@ RustError msm_host(void* out, const void* points, size_t npoints, const void* sc
             }
             CUDA_OK(cudaEventRecord(copied[b], copy));
             CUDA_OK(cudaStreamWaitEvent(compute, copied[b], 0));
+            if (unmont) unmont(ds, n, compute);
             m.slice(job, dp, ds, n, compute);
             CUDA_OK(cudaEventRecord(consumed[b], compute));
         }

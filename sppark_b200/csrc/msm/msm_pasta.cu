@@ -2,14 +2,21 @@
 // these are reached through sppark_b200_msm / sppark_b200_msm_dev).
 #include "msm_host.cuh"
 
+// scalar fields: Pallas' group order is Vesta's base-field modulus and vice versa (ff/pasta.hpp:92-103)
 RustError msm_host_pallas(void* out, const void* points, size_t npoints, const void* scalars,
-                          size_t stride, bool has_flag)
-{   return msm_host<ff::pallas_fp_t>(out, points, npoints, scalars, stride, has_flag);   }
+                          size_t stride, bool has_flag, bool mont)
+{
+    return msm_host<ff::pallas_fp_t>(out, points, npoints, scalars, stride, has_flag,
+                                     mont ? scalars_from_mont<ff::vesta_fp_t> : nullptr);
+}
 RustError msm_dev_pallas(void* out, const void* d_points, size_t npoints, const void* d_scalars, void* stream)
 {   return msm_dev<ff::pallas_fp_t>(out, d_points, npoints, d_scalars, stream);   }
 RustError msm_host_vesta(void* out, const void* points, size_t npoints, const void* scalars,
-                         size_t stride, bool has_flag)
-{   return msm_host<ff::vesta_fp_t>(out, points, npoints, scalars, stride, has_flag);   }
+                         size_t stride, bool has_flag, bool mont)
+{
+    return msm_host<ff::vesta_fp_t>(out, points, npoints, scalars, stride, has_flag,
+                                    mont ? scalars_from_mont<ff::pallas_fp_t> : nullptr);
+}
 RustError msm_dev_vesta(void* out, const void* d_points, size_t npoints, const void* d_scalars, void* stream)
 {   return msm_dev<ff::vesta_fp_t>(out, d_points, npoints, d_scalars, stream);   }
 RustError gen_points_pallas(void* d_out, size_t n, void* stream)
