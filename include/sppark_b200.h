@@ -109,9 +109,13 @@ enum { SPPARK_FIELD_GL64 = 0, SPPARK_FIELD_BB31 = 1,
        /* 256-bit Montgomery scalar fields, 8 x uint32 limbs per element (the reference's "wide"
         * NTT kernels, ntt/kernels/{ct,gs}_mixed_radix_wide.cu): fr of FEATURE_BLS12_381,
         * FEATURE_PALLAS (= Vesta's base field) and FEATURE_VESTA (= Pallas' base field) */
-       SPPARK_FIELD_BLS12_381_FR = 2, SPPARK_FIELD_PALLAS_FR = 3, SPPARK_FIELD_VESTA_FR = 4 };
+       SPPARK_FIELD_BLS12_381_FR = 2, SPPARK_FIELD_PALLAS_FR = 3, SPPARK_FIELD_VESTA_FR = 4,
+       /* FEATURE_BN254 (ff/alt_bn128.hpp, domains up to 2^28), FEATURE_BLS12_377 (ff/bls12-377.hpp) */
+       SPPARK_FIELD_BN254_FR = 5, SPPARK_FIELD_BLS12_377_FR = 6 };
 enum { SPPARK_CURVE_BLS12_381_G1 = 0, SPPARK_CURVE_PALLAS = 1, SPPARK_CURVE_VESTA = 2,
-       SPPARK_CURVE_BLS12_381_G2 = 3 };
+       SPPARK_CURVE_BLS12_381_G2 = 3,
+       /* the other two G1 groups poc/msm-cuda builds (features bn254, bls12_377; Cargo.toml:12-17) */
+       SPPARK_CURVE_BN254_G1 = 4, SPPARK_CURVE_BLS12_377_G1 = 5 };
 
 /* compute_ntt for any single-word field (the reference builds one .so per FEATURE_*) */
 RustError sppark_b200_ntt(int field, size_t device_id, void *inout, uint32_t lg_domain_size,

@@ -13,7 +13,7 @@
 //   gpu_t, stream_t, select_gpu(), ngpus(), cuda_available()   util/gpu_t.cuh:20-24,57-267
 // The value types are LAYOUT types (the bytes that cross the boundary); arithmetic happens on the
 // GPU.  Select the field set as the reference does, with -DFEATURE_BLS12_381 / FEATURE_PALLAS /
-// FEATURE_VESTA / FEATURE_GOLDILOCKS / FEATURE_BABY_BEAR; include/compat/ holds forwarding headers
+// FEATURE_VESTA / FEATURE_BN254 / FEATURE_BLS12_377 / FEATURE_GOLDILOCKS / FEATURE_BABY_BEAR; include/compat/ holds forwarding headers
 // under the reference's own file names so that its poc glue (poc/msm-cuda/cuda/pippenger_inf.cu,
 // poc/ntt-cuda/cuda/ntt_api.cu) compiles unmodified against this library.
 #pragma once
@@ -74,8 +74,16 @@ typedef fr_t gl64_t;
 #elif defined(FEATURE_BABY_BEAR)
 typedef sppark_b200::felem_t<8, 1, SPPARK_FIELD_BB31, -1> fr_t;                     // bb31_t
 typedef fr_t bb31_t;
-#elif defined(FEATURE_BLS12_377) || defined(FEATURE_BN254)
-# error "sppark_b200: BLS12-377 / BN254 are not instantiated in this library (DESIGN.md section 8)"
+#elif defined(FEATURE_BN254)
+typedef sppark_b200::felem_t<9, 8, -1, SPPARK_CURVE_BN254_G1> fp_t;                // ff/alt_bn128.hpp
+typedef sppark_b200::felem_t<10, 8, SPPARK_FIELD_BN254_FR, -1> fr_t;
+typedef sppark_b200::felem_t<13, 16, -1, -1> fp2_t;         // layout only: G2 is not instantiated
+#elif defined(FEATURE_BLS12_377)
+typedef sppark_b200::felem_t<11, 12, -1, SPPARK_CURVE_BLS12_377_G1> fp_t;          // ff/bls12-377.hpp
+typedef sppark_b200::felem_t<12, 8, SPPARK_FIELD_BLS12_377_FR, -1> fr_t;
+typedef sppark_b200::felem_t<14, 24, -1, -1> fp2_t;         // layout only: G2 is not instantiated
+#elif defined(FEATURE_MERSENNE31)
+# error "sppark_b200: Mersenne31 is not instantiated in this library (DESIGN.md section 1)"
 #endif
 
 // ---- curve point layouts (ec/*.hpp) -----------------------------------------------------------
@@ -146,11 +154,15 @@ public:
     {
         typedef decltype(points[0].X) fe_ref;
         typedef std::remove_cv_t<std::remove_reference_t<fe_ref>> field_t;
-        static_assert(field_t::msm_curve >= 0, "no MSM is instantiated over this field");
         static_assert(sizeof(scalar_t) == 32, "scalars are 256-bit");
         static_assert(sizeof(point_t) == 3 * sizeof(field_t) && sizeof(bucket_t) == 4 * sizeof(field_t), "layout");
         (void)device_id;                                   // the MSM runs on the caller's current device
-        return sppark_b200_msm_ex(field_t::msm_curve, &out, points, npoints, scalars, ffi_affine_sz, mont);
+        if constexpr (field_t::msm_curve < 0) {            // e.g. G2 of BN254 / BLS12-377
+            out.inf();
+            return RustError{-1, strdup("sppark_b200: no MSM is instantiated over this field")};
+        } else {
+            return sppark_b200_msm_ex(field_t::msm_curve, &out, points, npoints, scalars, ffi_affine_sz, mont);
+        }
     }
     RustError invoke(point_t& out, const affine_t points[], size_t npoints, const scalar_t scalars[],
                      bool mont, size_t ffi_affine_sz, std::nullptr_t) = delete;
@@ -167,7 +179,8 @@ static RustError mult_pippenger(point_t* out, const affine_t points[], size_t np
 
 // ---- NTT (ntt/ntt.cuh) -------------------------------------------------------------------------------
 #if defined(FEATURE_BLS12_381) || defined(FEATURE_PALLAS) || defined(FEATURE_VESTA) || \
-    defined(FEATURE_GOLDILOCKS) || defined(FEATURE_BABY_BEAR)
+    defined(FEATURE_GOLDILOCKS) || defined(FEATURE_BABY_BEAR) || defined(FEATURE_BN254) || \
+    defined(FEATURE_BLS12_377)
 class NTT {
 public:
     enum class InputOutputOrder { NN, NR, RN, RR };

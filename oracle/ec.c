@@ -390,3 +390,32 @@ void ec_jac_mul(const ec_curve *c, ec_jac *r, const ec_affine *p,
     }
     *r = acc;
 }
+
+/* BN254 (alt_bn128): y^2 = x^3 + 3, generator (1, 2) */
+const ec_curve *ec_bn254_g1(void)
+{
+    static ec_curve c;
+    static int ready;
+    if (!ready) {
+        static const uint64_t gx[4] = {1, 0, 0, 0}, gy[4] = {2, 0, 0, 0};
+        curve_init(&c, ff_bn254_fp(), ff_bn254_fr(), 3, gx, gy);
+        __atomic_store_n(&ready, 1, __ATOMIC_RELEASE);
+    }
+    return &c;
+}
+
+/* BLS12-377 G1: y^2 = x^3 + 1, the arkworks generator */
+const ec_curve *ec_bls12_377_g1(void)
+{
+    static ec_curve c;
+    static int ready;
+    if (!ready) {
+        static const uint64_t gx[6] = {0xeab9b16eb21be9efULL, 0xd5481512ffcd394eULL, 0x188282c8bd37cb5cULL,
+                                       0x85951e2caa9d41bbULL, 0xc8fc6225bf87ff54ULL, 0x008848defe740a67ULL};
+        static const uint64_t gy[6] = {0xfd82de55559c8ea6ULL, 0xc2fe3d3634a9591aULL, 0x6d182ad44fb82305ULL,
+                                       0xbd7fb348ca3e52d9ULL, 0x1f674f5d30afeec4ULL, 0x01914a69c5102effULL};
+        curve_init(&c, ff_bls12_377_fp(), ff_bls12_377_fr(), 1, gx, gy);
+        __atomic_store_n(&ready, 1, __ATOMIC_RELEASE);
+    }
+    return &c;
+}

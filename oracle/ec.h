@@ -29,6 +29,8 @@ typedef struct { ff_t X, Y, Z; } ec_jac;
 const ec_curve *ec_bls12_381_g1(void);
 const ec_curve *ec_pallas(void);
 const ec_curve *ec_vesta(void);
+const ec_curve *ec_bn254_g1(void);
+const ec_curve *ec_bls12_377_g1(void);
 
 int  ec_affine_is_inf(const ec_curve *c, const ec_affine *p);
 int  ec_affine_on_curve(const ec_curve *c, const ec_affine *p);

@@ -215,3 +215,16 @@ DEFINE_FIELD(ff_pallas_fp, 4, 255,
 DEFINE_FIELD(ff_vesta_fp, 4, 255,
              0x8c46eb2100000001ULL, 0x224698fc0994a8ddULL, 0x0000000000000000ULL,
              0x4000000000000000ULL)
+/* ff/alt_bn128.hpp:13-16,31-34; ff/bls12-377.hpp:13-17,35-38 */
+DEFINE_FIELD(ff_bn254_fp, 4, 254,
+             0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL,
+             0x30644e72e131a029ULL)
+DEFINE_FIELD(ff_bn254_fr, 4, 254,
+             0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL,
+             0x30644e72e131a029ULL)
+DEFINE_FIELD(ff_bls12_377_fp, 6, 377,
+             0x8508c00000000001ULL, 0x170b5d4430000000ULL, 0x1ef3622fba094800ULL,
+             0x1a22d9f300f5138fULL, 0xc63b05c06ca1493bULL, 0x01ae3a4617c510eaULL)
+DEFINE_FIELD(ff_bls12_377_fr, 4, 253,
+             0x0a11800000000001ULL, 0x59aa76fed0000001ULL, 0x60b44d1e5c37b001ULL,
+             0x12ab655e9a2ca556ULL)

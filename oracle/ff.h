@@ -60,6 +60,10 @@ const ff_ctx *ff_bls12_381_fp(void);
 const ff_ctx *ff_bls12_381_fr(void);
 const ff_ctx *ff_pallas_fp(void);   /* Pallas base field  = Vesta scalar field */
 const ff_ctx *ff_vesta_fp(void);    /* Vesta base field   = Pallas scalar field */
+const ff_ctx *ff_bn254_fp(void);
+const ff_ctx *ff_bn254_fr(void);
+const ff_ctx *ff_bls12_377_fp(void);
+const ff_ctx *ff_bls12_377_fr(void);
 
 #ifdef __cplusplus
 }

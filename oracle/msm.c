@@ -284,7 +284,13 @@ void oracle_gen_points(const ec_curve *c, ec_affine *out, size_t ndistinct)
 
 static const ec_curve *curve_by_id(int id)
 {
-    return id == 0 ? ec_bls12_381_g1() : id == 1 ? ec_pallas() : ec_vesta();
+    switch (id) {                                 /* ids as include/sppark_b200.h (3 = G2: ec2.c) */
+    case 0: return ec_bls12_381_g1();
+    case 1: return ec_pallas();
+    case 4: return ec_bn254_g1();
+    case 5: return ec_bls12_377_g1();
+    default: return ec_vesta();
+    }
 }
 
 static void unpack_affine(const ec_curve *c, ec_affine *dst, const uint64_t *src, size_t n,
@@ -360,11 +366,23 @@ int oracle_affine_on_curve(int curve_id, const uint64_t *xy)
 }
 
 /* field KAT access: op 0 mul, 1 add, 2 sub, 3 to_mont, 4 from_mont, 5 inv */
+static const ff_ctx *field_by_id(int id)
+{
+    switch (id) {
+    case 0: return ff_bls12_381_fp();
+    case 1: return ff_bls12_381_fr();
+    case 2: return ff_pallas_fp();
+    case 4: return ff_bn254_fp();
+    case 5: return ff_bn254_fr();
+    case 6: return ff_bls12_377_fp();
+    case 7: return ff_bls12_377_fr();
+    default: return ff_vesta_fp();
+    }
+}
+
 void oracle_ff_op(int field_id, int op, uint64_t *r, const uint64_t *a, const uint64_t *b)
 {
-    const ff_ctx *f = field_id == 0 ? ff_bls12_381_fp()
-                    : field_id == 1 ? ff_bls12_381_fr()
-                    : field_id == 2 ? ff_pallas_fp() : ff_vesta_fp();
+    const ff_ctx *f = field_by_id(field_id);
     ff_t x, y, z;
     ff_set_zero(&x);
     ff_set_zero(&y);
@@ -384,9 +402,7 @@ void oracle_ff_op(int field_id, int op, uint64_t *r, const uint64_t *a, const ui
 
 void oracle_ff_consts(int field_id, uint64_t *p, uint64_t *m0, uint64_t *rr, uint64_t *one)
 {
-    const ff_ctx *f = field_id == 0 ? ff_bls12_381_fp()
-                    : field_id == 1 ? ff_bls12_381_fr()
-                    : field_id == 2 ? ff_pallas_fp() : ff_vesta_fp();
+    const ff_ctx *f = field_by_id(field_id);
     memcpy(p, f->p, 8 * f->n);
     *m0 = f->m0;
     memcpy(rr, f->rr, 8 * f->n);

@@ -236,11 +236,16 @@ NTT_IMPL(oracle_ntt_bb31, uint32_t, bb_add, bb_sub, bb_mul, bb_pow, oracle_bb31_
  * tests/test_params_pin.py). */
 #include "ff.h"
 
-static const ff_ctx *ntt_field(int id, uint64_t *gen)
+/* multiplicative generator and 2-adicity: ntt/parameters/{bls12_381,pallas,vesta,alt_bn128,
+ * bls12_377}.h (group_gen, S) */
+static const ff_ctx *ntt_field(int id, uint64_t *gen, unsigned *two_adicity)
 {
+    *two_adicity = 32;
     switch (id) {
     case 1: *gen = 7; return ff_bls12_381_fr();
     case 2: *gen = 5; return ff_pallas_fp();
+    case 5: *gen = 5; *two_adicity = 28; return ff_bn254_fr();
+    case 7: *gen = 22; *two_adicity = 47; return ff_bls12_377_fr();
     default: *gen = 5; return ff_vesta_fp();
     }
 }
@@ -265,17 +270,17 @@ static void ffx_small(const ff_ctx *c, ff_t *r, uint64_t v)
     ff_to_mont(c, r, &t);
 }
 
-static void ffx_root(const ff_ctx *c, uint64_t gen, unsigned lg, int inverse, ff_t *w)
+static void ffx_root(const ff_ctx *c, uint64_t gen, unsigned S, unsigned lg, int inverse, ff_t *w)
 {
-    uint64_t e[FF_MAX_LIMBS] = {0};              /* (p - 1) >> 32 */
+    uint64_t e[FF_MAX_LIMBS] = {0};              /* (p - 1) >> S, 0 < S < 64 */
     for (int i = 0; i < c->n; i++) {
-        uint64_t lo = c->p[i] >> 32, hi = i + 1 < c->n ? c->p[i + 1] << 32 : 0;
+        uint64_t lo = c->p[i] >> S, hi = i + 1 < c->n ? c->p[i + 1] << (64 - S) : 0;
         e[i] = lo | hi;
     }
     ff_t g;
     ffx_small(c, &g, gen);
     ffx_pow(c, w, &g, e, c->n);
-    for (unsigned i = 32; i > lg; i--)
+    for (unsigned i = S; i > lg; i--)
         ff_sqr(c, w, w);
     if (inverse)
         ff_inv(c, w, w);
@@ -288,7 +293,10 @@ int oracle_ntt_ff(int field_id, uint64_t *data, unsigned lg, int order, int dire
     if (lg > 26)
         return -1;
     uint64_t gen;
-    const ff_ctx *c = ntt_field(field_id, &gen);
+    unsigned S;
+    const ff_ctx *c = ntt_field(field_id, &gen, &S);
+    if (lg > S)
+        return -1;
     const int nl = c->n;
     size_t n = (size_t)1 << lg;
     ff_t *a = malloc(n * sizeof(ff_t)), *tmp = malloc(n * sizeof(ff_t));
@@ -314,7 +322,7 @@ int oracle_ntt_ff(int field_id, uint64_t *data, unsigned lg, int order, int dire
         }
     }
     ff_t w;
-    ffx_root(c, gen, lg, direction, &w);
+    ffx_root(c, gen, S, lg, direction, &w);
     ff_t *pwr = malloc(n * sizeof(ff_t));
     ff_set_one(c, &pwr[0]);
     for (size_t i = 1; i < n; i++) ff_mul(c, &pwr[i], &pwr[i - 1], &w);

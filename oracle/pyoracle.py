@@ -14,10 +14,11 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 
-CURVES = {"bls12_381": 0, "pallas": 1, "vesta": 2}
-FIELDS = {"bls12_381_fp": 0, "bls12_381_fr": 1, "pallas_fp": 2, "vesta_fp": 3}
-FIELD_LIMBS = {0: 6, 1: 4, 2: 4, 3: 4}
-CURVE_LIMBS = {0: 6, 1: 4, 2: 4}
+CURVES = {"bls12_381": 0, "pallas": 1, "vesta": 2, "bn254": 4, "bls12_377": 5}      # 3 = G2 (g2_* below)
+FIELDS = {"bls12_381_fp": 0, "bls12_381_fr": 1, "pallas_fp": 2, "vesta_fp": 3,
+          "bn254_fp": 4, "bn254_fr": 5, "bls12_377_fp": 6, "bls12_377_fr": 7}
+FIELD_LIMBS = {0: 6, 1: 4, 2: 4, 3: 4, 4: 4, 5: 4, 6: 6, 7: 4}
+CURVE_LIMBS = {0: 6, 1: 4, 2: 4, 4: 4, 5: 6}
 NN, NR, RN, RR, BB = 0, 1, 2, 3, 4
 
 _lib = None

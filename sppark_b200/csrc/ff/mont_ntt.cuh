@@ -65,5 +65,7 @@ struct mont_ntt {
 typedef mont_ntt<bls12_381_fr_params> bls12_381_fr_ntt;   // FEATURE_BLS12_381
 typedef mont_ntt<vesta_fp_params> pallas_fr_ntt;          // FEATURE_PALLAS: fr = Vesta's base field
 typedef mont_ntt<pallas_fp_params> vesta_fr_ntt;          // FEATURE_VESTA:  fr = Pallas' base field
+typedef mont_ntt<bn254_fr_params> bn254_fr_ntt;           // FEATURE_BN254     (2-adicity 28)
+typedef mont_ntt<bls12_377_fr_params> bls12_377_fr_ntt;   // FEATURE_BLS12_377 (2-adicity 47)
 
 }  // namespace ff

@@ -12,6 +12,14 @@ RustError msm_host_bls12_381_g2(void*, const void*, size_t, const void*, size_t,
 RustError msm_dev_bls12_381_g2(void*, const void*, size_t, const void*, void*);
 RustError gen_points_bls12_381_g2(void*, size_t, void*);
 RustError combine_bls12_381_g2(void*, const void*, size_t);
+RustError msm_host_bn254(void*, const void*, size_t, const void*, size_t, bool, bool);
+RustError msm_dev_bn254(void*, const void*, size_t, const void*, void*);
+RustError gen_points_bn254(void*, size_t, void*);
+RustError combine_bn254(void*, const void*, size_t);
+RustError msm_host_bls12_377(void*, const void*, size_t, const void*, size_t, bool, bool);
+RustError msm_dev_bls12_377(void*, const void*, size_t, const void*, void*);
+RustError gen_points_bls12_377(void*, size_t, void*);
+RustError combine_bls12_377(void*, const void*, size_t);
 RustError gen_points_bls12_381(void*, size_t, void*);
 RustError gen_points_pallas(void*, size_t, void*);
 RustError gen_points_vesta(void*, size_t, void*);
@@ -27,6 +35,8 @@ extern "C" RustError sppark_b200_generate_points_dev(int curve, void* d_out, siz
     case SPPARK_CURVE_PALLAS: return gen_points_pallas(d_out, n, stream);
     case SPPARK_CURVE_VESTA: return gen_points_vesta(d_out, n, stream);
     case SPPARK_CURVE_BLS12_381_G2: return gen_points_bls12_381_g2(d_out, n, stream);
+    case SPPARK_CURVE_BN254_G1: return gen_points_bn254(d_out, n, stream);
+    case SPPARK_CURVE_BLS12_377_G1: return gen_points_bls12_377(d_out, n, stream);
     default: return rust_err(-(int)cudaErrorInvalidValue, "generate_points: unknown curve");
     }
 }
@@ -38,6 +48,8 @@ extern "C" RustError sppark_b200_msm_combine(int curve, void* out, const void* p
     case SPPARK_CURVE_PALLAS: return combine_pallas(out, partials, count);
     case SPPARK_CURVE_VESTA: return combine_vesta(out, partials, count);
     case SPPARK_CURVE_BLS12_381_G2: return combine_bls12_381_g2(out, partials, count);
+    case SPPARK_CURVE_BN254_G1: return combine_bn254(out, partials, count);
+    case SPPARK_CURVE_BLS12_377_G1: return combine_bls12_377(out, partials, count);
     default: return rust_err(-(int)cudaErrorInvalidValue, "msm_combine: unknown curve");
     }
 }
@@ -54,6 +66,10 @@ static RustError msm_any(int curve, void* out, const void* points, size_t npoint
         return msm_host_vesta(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 64, ffi_affine_sz > 64, mont);
     case SPPARK_CURVE_BLS12_381_G2:
         return msm_host_bls12_381_g2(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 192, ffi_affine_sz > 192, mont);
+    case SPPARK_CURVE_BN254_G1:
+        return msm_host_bn254(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 64, ffi_affine_sz > 64, mont);
+    case SPPARK_CURVE_BLS12_377_G1:
+        return msm_host_bls12_377(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 96, ffi_affine_sz > 96, mont);
     default:
         return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_msm: unknown curve");
     }
@@ -75,6 +91,8 @@ extern "C" RustError sppark_b200_msm_dev(int curve, void* out, const void* d_poi
     case SPPARK_CURVE_PALLAS: return msm_dev_pallas(out, d_points, npoints, d_scalars, stream);
     case SPPARK_CURVE_VESTA: return msm_dev_vesta(out, d_points, npoints, d_scalars, stream);
     case SPPARK_CURVE_BLS12_381_G2: return msm_dev_bls12_381_g2(out, d_points, npoints, d_scalars, stream);
+    case SPPARK_CURVE_BN254_G1: return msm_dev_bn254(out, d_points, npoints, d_scalars, stream);
+    case SPPARK_CURVE_BLS12_377_G1: return msm_dev_bls12_377(out, d_points, npoints, d_scalars, stream);
     default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_msm_dev: unknown curve");
     }
 }

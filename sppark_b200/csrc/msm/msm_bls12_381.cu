@@ -71,6 +71,10 @@ extern "C" RustError sppark_b200_selftest_field(int field, int op, size_t n, voi
     case 1: return selftest<ff::bls12_381_fr_t>(op, n, r, a, b);
     case 2: return selftest<ff::pallas_fp_t>(op, n, r, a, b);
     case 3: return selftest<ff::vesta_fp_t>(op, n, r, a, b);
+    case 4: return selftest<ff::bn254_fp_t>(op, n, r, a, b);
+    case 5: return selftest<ff::bn254_fr_t>(op, n, r, a, b);
+    case 6: return selftest<ff::bls12_377_fp_t>(op, n, r, a, b);
+    case 7: return selftest<ff::bls12_377_fr_t>(op, n, r, a, b);
     default: return rust_err(-(int)cudaErrorInvalidValue, "selftest: unknown field");
     }
 }

@@ -12,6 +12,8 @@ template<> struct FieldId<bb31> { static constexpr uint32_t id = 2, lg_tile = 14
 template<> struct FieldId<ff::bls12_381_fr_ntt> { static constexpr uint32_t id = 3, lg_tile = 11; };
 template<> struct FieldId<ff::pallas_fr_ntt> { static constexpr uint32_t id = 4, lg_tile = 11; };
 template<> struct FieldId<ff::vesta_fr_ntt> { static constexpr uint32_t id = 5, lg_tile = 11; };
+template<> struct FieldId<ff::bn254_fr_ntt> { static constexpr uint32_t id = 6, lg_tile = 11; };
+template<> struct FieldId<ff::bls12_377_fr_ntt> { static constexpr uint32_t id = 7, lg_tile = 11; };
 // ---- statically shaped twins of the passes the planner emits for the common sizes ----------
 // key = (lg_r, lg_w, in row-fast, out row-fast, in_rev, out_rev, tw_mode)
 template<class F, uint32_t R, uint32_t W, bool IRF, bool ORF, bool IREV, bool OREV, uint32_t TW>
@@ -75,12 +77,16 @@ template bool launch_static<bb31>(const Pass&, const Tables<bb31>&, const uint32
 template bool launch_static<ff::bls12_381_fr_ntt>(const Pass&, const Tables<ff::bls12_381_fr_ntt>&, const ff::bls12_381_fr_ntt::T*, ff::bls12_381_fr_ntt::T*, uint32_t, size_t, cudaStream_t);
 template bool launch_static<ff::pallas_fr_ntt>(const Pass&, const Tables<ff::pallas_fr_ntt>&, const ff::pallas_fr_ntt::T*, ff::pallas_fr_ntt::T*, uint32_t, size_t, cudaStream_t);
 template bool launch_static<ff::vesta_fr_ntt>(const Pass&, const Tables<ff::vesta_fr_ntt>&, const ff::vesta_fr_ntt::T*, ff::vesta_fr_ntt::T*, uint32_t, size_t, cudaStream_t);
+template bool launch_static<ff::bn254_fr_ntt>(const Pass&, const Tables<ff::bn254_fr_ntt>&, const ff::bn254_fr_ntt::T*, ff::bn254_fr_ntt::T*, uint32_t, size_t, cudaStream_t);
+template bool launch_static<ff::bls12_377_fr_ntt>(const Pass&, const Tables<ff::bls12_377_fr_ntt>&, const ff::bls12_377_fr_ntt::T*, ff::bls12_377_fr_ntt::T*, uint32_t, size_t, cudaStream_t);
 
 template class NTT<gl64>;
 template class NTT<bb31>;
 template class NTT<ff::bls12_381_fr_ntt>;
 template class NTT<ff::pallas_fr_ntt>;
 template class NTT<ff::vesta_fr_ntt>;
+template class NTT<ff::bn254_fr_ntt>;
+template class NTT<ff::bls12_377_fr_ntt>;
 }  // namespace ntt
 
 template<class F>
@@ -157,6 +163,8 @@ extern "C" RustError sppark_b200_lde(int field, size_t device_id, void* inout, u
     case SPPARK_FIELD_BLS12_381_FR: return lde_host<ff::bls12_381_fr_ntt>(device_id, inout, lg, lg_blowup, aux_out);
     case SPPARK_FIELD_PALLAS_FR: return lde_host<ff::pallas_fr_ntt>(device_id, inout, lg, lg_blowup, aux_out);
     case SPPARK_FIELD_VESTA_FR: return lde_host<ff::vesta_fr_ntt>(device_id, inout, lg, lg_blowup, aux_out);
+    case SPPARK_FIELD_BN254_FR: return lde_host<ff::bn254_fr_ntt>(device_id, inout, lg, lg_blowup, aux_out);
+    case SPPARK_FIELD_BLS12_377_FR: return lde_host<ff::bls12_377_fr_ntt>(device_id, inout, lg, lg_blowup, aux_out);
     default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_lde: unknown field");
     }
 }
@@ -170,6 +178,8 @@ extern "C" RustError sppark_b200_ntt_slab_pass(int field, int which, const void*
     case SPPARK_FIELD_BLS12_381_FR: return ntt_slab<ff::bls12_381_fr_ntt>(which, d_in, d_out, lg, lg_g, rank, direction, stream);
     case SPPARK_FIELD_PALLAS_FR: return ntt_slab<ff::pallas_fr_ntt>(which, d_in, d_out, lg, lg_g, rank, direction, stream);
     case SPPARK_FIELD_VESTA_FR: return ntt_slab<ff::vesta_fr_ntt>(which, d_in, d_out, lg, lg_g, rank, direction, stream);
+    case SPPARK_FIELD_BN254_FR: return ntt_slab<ff::bn254_fr_ntt>(which, d_in, d_out, lg, lg_g, rank, direction, stream);
+    case SPPARK_FIELD_BLS12_377_FR: return ntt_slab<ff::bls12_377_fr_ntt>(which, d_in, d_out, lg, lg_g, rank, direction, stream);
     default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_ntt_slab_pass: unknown field");
     }
 }
@@ -184,6 +194,8 @@ extern "C" RustError sppark_b200_ntt_slab_pass_p2p(int field, const void* d_in, 
     case SPPARK_FIELD_BLS12_381_FR: return ntt_slab<ff::bls12_381_fr_ntt>(1, d_in, nullptr, lg, lg_g, rank, direction, stream, peer_recv);
     case SPPARK_FIELD_PALLAS_FR: return ntt_slab<ff::pallas_fr_ntt>(1, d_in, nullptr, lg, lg_g, rank, direction, stream, peer_recv);
     case SPPARK_FIELD_VESTA_FR: return ntt_slab<ff::vesta_fr_ntt>(1, d_in, nullptr, lg, lg_g, rank, direction, stream, peer_recv);
+    case SPPARK_FIELD_BN254_FR: return ntt_slab<ff::bn254_fr_ntt>(1, d_in, nullptr, lg, lg_g, rank, direction, stream, peer_recv);
+    case SPPARK_FIELD_BLS12_377_FR: return ntt_slab<ff::bls12_377_fr_ntt>(1, d_in, nullptr, lg, lg_g, rank, direction, stream, peer_recv);
     default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_ntt_slab_pass_p2p: unknown field");
     }
 }
@@ -201,6 +213,8 @@ extern "C" RustError sppark_b200_ntt(int field, size_t device_id, void* inout, u
     case SPPARK_FIELD_BLS12_381_FR: return ntt_host<ff::bls12_381_fr_ntt>(device_id, inout, lg, order, direction, type);
     case SPPARK_FIELD_PALLAS_FR: return ntt_host<ff::pallas_fr_ntt>(device_id, inout, lg, order, direction, type);
     case SPPARK_FIELD_VESTA_FR: return ntt_host<ff::vesta_fr_ntt>(device_id, inout, lg, order, direction, type);
+    case SPPARK_FIELD_BN254_FR: return ntt_host<ff::bn254_fr_ntt>(device_id, inout, lg, order, direction, type);
+    case SPPARK_FIELD_BLS12_377_FR: return ntt_host<ff::bls12_377_fr_ntt>(device_id, inout, lg, order, direction, type);
     default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_ntt: unknown field");
     }
 }
@@ -214,6 +228,8 @@ extern "C" RustError sppark_b200_ntt_dev(int field, void* d_inout, uint32_t lg, 
     case SPPARK_FIELD_BLS12_381_FR: return ntt_dev<ff::bls12_381_fr_ntt>(d_inout, lg, order, direction, type, stream);
     case SPPARK_FIELD_PALLAS_FR: return ntt_dev<ff::pallas_fr_ntt>(d_inout, lg, order, direction, type, stream);
     case SPPARK_FIELD_VESTA_FR: return ntt_dev<ff::vesta_fr_ntt>(d_inout, lg, order, direction, type, stream);
+    case SPPARK_FIELD_BN254_FR: return ntt_dev<ff::bn254_fr_ntt>(d_inout, lg, order, direction, type, stream);
+    case SPPARK_FIELD_BLS12_377_FR: return ntt_dev<ff::bls12_377_fr_ntt>(d_inout, lg, order, direction, type, stream);
     default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_ntt_dev: unknown field");
     }
 }

@@ -9,8 +9,8 @@ import numpy as np
 
 from . import _lib
 
-BLS12_381_G1, PALLAS, VESTA, BLS12_381_G2 = 0, 1, 2, 3
-_LIMBS = {BLS12_381_G1: 6, PALLAS: 4, VESTA: 4, BLS12_381_G2: 12}    # 64-bit limbs per coordinate
+BLS12_381_G1, PALLAS, VESTA, BLS12_381_G2, BN254_G1, BLS12_377_G1 = 0, 1, 2, 3, 4, 5
+_LIMBS = {BLS12_381_G1: 6, PALLAS: 4, VESTA: 4, BLS12_381_G2: 12, BN254_G1: 4, BLS12_377_G1: 6}    # 64-bit limbs per coordinate
 
 
 def _check(points, scalars):
@@ -56,14 +56,16 @@ def multi_scalar_mult_fp2_arkworks(points, scalars):
     return out
 
 
-def msm(curve, points, scalars):
-    """Any supported curve, packed affine host arrays."""
+def msm(curve, points, scalars, mont=False):
+    """Any supported curve; host arrays of packed affine points (n, 2*limbs) or rows with an
+    infinity-flag word appended (n, 2*limbs + 1).  mont=True: the scalars are Montgomery residues
+    (the `mont` flag of the reference's C++ template, msm/pippenger.cuh:730-733)."""
     _check(points, scalars)
     nl = _LIMBS[curve]
-    assert points.shape[1] == 2 * nl
+    assert points.shape[1] in (2 * nl, 2 * nl + 1)
     out = np.zeros(3 * nl, dtype=np.uint64)
-    err = _lib.lib().sppark_b200_msm(curve, out.ctypes.data, points.ctypes.data, points.shape[0],
-                                     scalars.ctypes.data, points.strides[0])
+    err = _lib.lib().sppark_b200_msm_ex(curve, out.ctypes.data, points.ctypes.data, points.shape[0],
+                                        scalars.ctypes.data, points.strides[0], int(mont))
     _lib.check(err)
     return out
 

@@ -12,6 +12,7 @@ FORWARD, INVERSE = 0, 1                # sppark::NTTDirection
 STANDARD, COSET = 0, 1                 # sppark::NTTType
 GL64, BB31 = 0, 1
 BLS12_381_FR, PALLAS_FR, VESTA_FR = 2, 3, 4      # (n, 4) uint64 arrays of Montgomery residues
+BN254_FR, BLS12_377_FR = 5, 6                    # likewise (domains up to 2^28 / 2^30)
 
 
 def _field_of(a):

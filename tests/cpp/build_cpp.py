@@ -20,7 +20,9 @@ GLUE = [("libdropin_msm_g1.so", "poc/msm-cuda/cuda/pippenger.cu", "FEATURE_BLS12
         ("libdropin_msm.so", "poc/msm-cuda/cuda/pippenger_inf.cu", "FEATURE_BLS12_381"),
         ("libdropin_ntt_gl64.so", "poc/ntt-cuda/cuda/ntt_api.cu", "FEATURE_GOLDILOCKS"),
         ("libdropin_ntt_bb31.so", "poc/ntt-cuda/cuda/ntt_api.cu", "FEATURE_BABY_BEAR"),
-        ("libdropin_ntt_bls12_381.so", "poc/ntt-cuda/cuda/ntt_api.cu", "FEATURE_BLS12_381")]
+        ("libdropin_ntt_bls12_381.so", "poc/ntt-cuda/cuda/ntt_api.cu", "FEATURE_BLS12_381"),
+        ("libdropin_msm_bn254.so", "poc/msm-cuda/cuda/pippenger_inf.cu", "FEATURE_BN254"),
+        ("libdropin_msm_bls12_377.so", "poc/msm-cuda/cuda/pippenger_inf.cu", "FEATURE_BLS12_377")]
 
 
 def build_example():

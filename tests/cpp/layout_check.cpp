@@ -14,6 +14,12 @@ static_assert(offsetof(xyzz_t<fp_t>, ZZZ) == 96 && offsetof(xyzz_t<fp_t>, ZZ) ==
 static_assert(sizeof(fp_t) == 32 && sizeof(fr_t) == 32, "field sizes");
 static_assert(sizeof(Affine_t<fp_t>) == 64 && sizeof(Affine_inf_t<fp_t>) == 72, "affine");
 static_assert(sizeof(jacobian_t<fp_t>) == 96 && sizeof(xyzz_t<fp_t>) == 128, "points");
+#elif defined(FEATURE_BN254)
+static_assert(sizeof(fp_t) == 32 && sizeof(fr_t) == 32 && sizeof(Affine_inf_t<fp_t>) == 72, "BN254");
+static_assert(sizeof(jacobian_t<fp_t>) == 96, "G1Projective");
+#elif defined(FEATURE_BLS12_377)
+static_assert(sizeof(fp_t) == 48 && sizeof(fr_t) == 32 && sizeof(Affine_inf_t<fp_t>) == 104, "BLS12-377");
+static_assert(sizeof(jacobian_t<fp_t>) == 144, "G1Projective");
 #elif defined(FEATURE_GOLDILOCKS)
 static_assert(sizeof(fr_t) == 8 && alignof(fr_t) == 8, "gl64_t");
 #elif defined(FEATURE_BABY_BEAR)

@@ -7,6 +7,7 @@
   msm_ref_gpu.npz   same for the reference's CUDA mult_pippenger (BLS12-381 G1).
   msm_g2_ref_gpu.npz  the reference's mult_pippenger_fp2_inf (BLS12-381 G2) and mult_pippenger_inf
                     (G1, arkworks layout with infinity flags): `... make_golden.py g2` on a GPU.
+  msm_curves2_ref_gpu.npz  the reference's CUDA MSM for BN254 and BLS12-377 G1: `... make_golden.py curves2`.
   msm_ref_cpu.npz   the reference's CPU msm/pippenger.hpp (oracle/_ref/libref_msm_cpu.so);
                     runs anywhere: `python tests/golden/make_golden.py cpu`.
 
@@ -206,6 +207,38 @@ def gen_g2(outdir):
     print("wrote msm_g2_ref_gpu.npz")
 
 
+def gen_curves2(outdir):
+    """msm_curves2_ref_gpu.npz: the reference's CUDA MSM templates for the msm crate's bn254 and
+    bls12_377 features (oracle/ref_msm_g1.cu -> mult_pippenger_inf, arkworks rows with flags)."""
+    out = {}
+    for curve, lib, r in (("bn254", "libref_msm_bn254_gpu.so", 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001),
+                          ("bls12_377", "libref_msm_bls12_377_gpu.so", 0x12ab655e9a2ca55660b44d1e5c37b00159aa76fed00000010a11800000000001)):
+        ref = C.CDLL(o.ref_path(lib))
+        ref.mult_pippenger_inf.restype = RE
+        ref.mult_pippenger_inf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        nl = o.CURVE_LIMBS[o.CURVES[curve]]
+        rng = np.random.default_rng(nl)
+        base = o.gen_points(curve, 64)
+        k = 0
+        for n in (1, 2, 33, 200, 1000):
+            pts = np.zeros((n, 2 * nl + 1), dtype=np.uint64)
+            pts[:, :2 * nl] = base[rng.integers(0, 64, size=n)]
+            sc = np.array([o.int_to_limbs(int.from_bytes(rng.bytes(32), "little") % r, 4) for _ in range(n)], dtype=np.uint64)
+            if n > 10:
+                pts[3, 2 * nl] = 1
+                pts[4, :2 * nl] = 0
+                sc[5] = 0
+                sc[7] = o.int_to_limbs(r - 1, 4)
+                pts[9], sc[9] = pts[8], sc[8]
+            jac = np.zeros(3 * nl, dtype=np.uint64)
+            ok(ref.mult_pippenger_inf(jac.ctypes.data, pts.ctypes.data, n, sc.ctypes.data, pts.strides[0]), f"{curve} n={n}")
+            out[f"{curve}_points{k}"], out[f"{curve}_scalars{k}"], out[f"{curve}_out{k}"] = pts, sc, jac
+            k += 1
+        out[f"{curve}_ncases"] = np.int64(k)
+    np.savez_compressed(os.path.join(outdir, "msm_curves2_ref_gpu.npz"), **out)
+    print("wrote msm_curves2_ref_gpu.npz")
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "cpu"
     if mode == "cpu":
@@ -215,5 +248,7 @@ if __name__ == "__main__":
         os.makedirs(outdir, exist_ok=True)
         if mode == "g2":
             gen_g2(outdir)
+        elif mode == "curves2":
+            gen_curves2(outdir)
         else:
             gen_gpu(outdir)

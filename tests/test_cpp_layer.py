@@ -24,14 +24,14 @@ def _builder():
     return m
 
 
-@pytest.mark.parametrize("feature", ["BLS12_381", "PALLAS", "VESTA", "GOLDILOCKS", "BABY_BEAR"])
+@pytest.mark.parametrize("feature", ["BLS12_381", "PALLAS", "VESTA", "BN254", "BLS12_377", "GOLDILOCKS", "BABY_BEAR"])
 def test_layouts_compile(feature):
     subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", f"-DFEATURE_{feature}", "-I" + os.path.join(ROOT, "include"),
                            os.path.join(CPP, "layout_check.cpp")])
 
 
 def test_unbuilt_curves_are_refused_at_compile_time():
-    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-DFEATURE_BN254", "-I" + os.path.join(ROOT, "include"),
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-DFEATURE_MERSENNE31", "-I" + os.path.join(ROOT, "include"),
                         os.path.join(CPP, "layout_check.cpp")], capture_output=True, text=True)
     assert r.returncode != 0 and "not instantiated" in r.stderr
 
@@ -48,7 +48,7 @@ def test_reference_poc_glue_compiles_unmodified(lib):
     if not os.path.isdir("/root/reference"):
         pytest.skip("reference sources are not on this machine")
     built = _builder().build_reference_glue()
-    assert len(built) == 5
+    assert len(built) == 7
     syms = subprocess.check_output(["nm", "-D", os.path.join(OUT, "libdropin_msm.so")], text=True)
     assert " T mult_pippenger_inf" in syms and " T mult_pippenger_fp2_inf" in syms
     syms = subprocess.check_output(["nm", "-D", os.path.join(OUT, "libdropin_ntt_gl64.so")], text=True)
@@ -133,6 +133,20 @@ def test_reference_poc_glue_runs_on_this_library(oracle):
     flat = np.ascontiguousarray(pts[:, :12])
     assert g1.mult_pippenger(out.ctypes.data, flat.ctypes.data, n, sc.ctypes.data).code == 0
     assert np.array_equal(oracle.jac_to_affine("bls12_381", out), oracle.jac_to_affine("bls12_381", want))
+    for curve, lib, fr in (("bn254", "libdropin_msm_bn254.so", "bn254_fr"), ("bls12_377", "libdropin_msm_bls12_377.so", "bls12_377_fr")):
+        glue = C.CDLL(os.path.join(OUT, lib))                # pippenger_inf.cu built with FEATURE_BN254 / _BLS12_377
+        glue.mult_pippenger_inf.restype = RE
+        glue.mult_pippenger_inf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        nl = oracle.CURVE_LIMBS[oracle.CURVES[curve]]
+        rmod = oracle.ff_consts(fr)["p"]
+        rnd = random.Random(nl)
+        sc2 = np.array([_limbs(rnd.randrange(rmod)) for _ in range(500)], dtype=np.uint64)
+        ark = np.zeros((500, 2 * nl + 1), dtype=np.uint64)
+        ark[:, :2 * nl] = oracle.gen_points(curve, 50)[np.arange(500) % 50]
+        o2 = np.zeros(3 * nl, dtype=np.uint64)
+        assert glue.mult_pippenger_inf(o2.ctypes.data, ark.ctypes.data, 500, sc2.ctypes.data, ark.strides[0]).code == 0
+        w2 = oracle.msm(curve, np.ascontiguousarray(ark[:, :2 * nl]), sc2, "pippenger", ncpus=8)
+        assert np.array_equal(oracle.jac_to_affine(curve, o2), oracle.jac_to_affine(curve, w2)), curve
     rng = np.random.default_rng(5)
     for lib, dt, p, ofn in (("libdropin_ntt_gl64.so", np.uint64, GL_P, oracle.ntt_gl64),
                             ("libdropin_ntt_bb31.so", np.uint32, 0x78000001, oracle.ntt_bb31)):

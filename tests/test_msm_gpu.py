@@ -9,7 +9,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 R_BLS = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
-FIELDS = [("bls12_381_fp", 0, 6), ("bls12_381_fr", 1, 4), ("pallas_fp", 2, 4), ("vesta_fp", 3, 4)]
+FIELDS = [("bls12_381_fp", 0, 6), ("bls12_381_fr", 1, 4), ("pallas_fp", 2, 4), ("vesta_fp", 3, 4),
+          ("bn254_fp", 4, 4), ("bn254_fr", 5, 4), ("bls12_377_fp", 6, 6), ("bls12_377_fr", 7, 4)]
 
 
 def _limbs(x, n):
@@ -120,6 +121,47 @@ def test_pasta_msm_matches_oracle(oracle, curve, cid):
     got = msm.msm(cid, pts, sc)
     want = oracle.msm(curve, pts, sc, "pippenger", ncpus=8)
     assert _same_point(oracle, curve, got, want)
+
+
+@pytest.mark.parametrize("curve,cid,fr", [("bn254", 4, "bn254_fr"), ("bls12_377", 5, "bls12_377_fr")])
+def test_bn254_bls12_377_msm(oracle, curve, cid, fr):
+    """The msm crate's other two curve features (poc/msm-cuda/Cargo.toml: bn254, bls12_377): vs the
+    oracle on packed and arkworks rows, scalars plain and in Montgomery form, device-resident
+    entry + generated points, and vs the reference's own CUDA MSM recorded on a B200."""
+    import os
+    import torch
+    from sppark_b200 import msm
+    r = oracle.ff_consts(fr)["p"]
+    nl = oracle.CURVE_LIMBS[oracle.CURVES[curve]]
+    for n in (1, 33, 5000, 1 << 15):
+        base = oracle.gen_points(curve, min(n, 512))
+        pts = base[np.arange(n) % base.shape[0]].copy()
+        if n > 3:
+            pts[3] = 0
+        sc = _scalars(n, n + cid, r)
+        want = oracle.msm(curve, pts, sc, "pippenger", ncpus=8)
+        assert _same_point(oracle, curve, msm.msm(cid, pts, sc), want), n
+        ark = np.zeros((n, 2 * nl + 1), dtype=np.uint64)
+        ark[:, :2 * nl] = pts
+        if n > 7:
+            ark[7, 2 * nl] = 1
+            pts[7] = 0
+            want = oracle.msm(curve, pts, sc, "pippenger", ncpus=8)
+        assert _same_point(oracle, curve, msm.msm(cid, ark, sc), want), n
+        if n == 5000:
+            mont = np.array([_limbs(oracle.ff_op(fr, "to_mont", _int(row)), 4) for row in sc], dtype=np.uint64)
+            assert _same_point(oracle, curve, msm.msm(cid, ark, mont, mont=True), want)
+    gen = msm.generate_points_dev(cid, 300)
+    assert np.array_equal(gen.cpu().numpy().view(np.uint64), oracle.gen_points(curve, 300))
+    sc = _scalars(300, 3, r)
+    got = msm.msm_dev(cid, gen, torch.from_numpy(sc.view(np.int64)).cuda())
+    assert _same_point(oracle, curve, got, oracle.msm(curve, oracle.gen_points(curve, 300), sc, "pippenger", ncpus=8))
+    path = os.path.join(os.path.dirname(__file__), "golden", "msm_curves2_ref_gpu.npz")
+    if os.path.exists(path):
+        g = np.load(path)
+        for k in range(int(g[f"{curve}_ncases"])):
+            got = msm.msm(cid, np.ascontiguousarray(g[f"{curve}_points{k}"]), np.ascontiguousarray(g[f"{curve}_scalars{k}"]))
+            assert _same_point(oracle, curve, got, g[f"{curve}_out{k}"]), k
 
 
 def test_bls12_381_msm_2pow20_folded(oracle):

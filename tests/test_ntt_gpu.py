@@ -162,7 +162,8 @@ def test_babybear_2pow27_field_maximum():
         _lib.lib().drop_error_message(e.message)
 
 
-@pytest.mark.parametrize("fid,name", [(2, "bls12_381_fr"), (3, "vesta_fp"), (4, "pallas_fp")])
+@pytest.mark.parametrize("fid,name", [(2, "bls12_381_fr"), (3, "vesta_fp"), (4, "pallas_fp"), (5, "bn254_fr"),
+                                      (6, "bls12_377_fr")])
 def test_ntt_256bit_fields_match_oracle(oracle, fid, name):
     """256-bit Montgomery scalar fields (the reference's "wide" kernels)."""
     import random

@@ -16,7 +16,8 @@ R_BLS = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
 
 def test_field_arithmetic_vs_python(oracle):
     rnd = random.Random(1)
-    for name in ("bls12_381_fp", "bls12_381_fr", "pallas_fp", "vesta_fp"):
+    for name in ("bls12_381_fp", "bls12_381_fr", "pallas_fp", "vesta_fp", "bn254_fp", "bn254_fr",
+                 "bls12_377_fp", "bls12_377_fr"):
         c = oracle.ff_consts(name)
         p, n = c["p"], c["n"]
         R = 1 << (64 * n)
@@ -44,11 +45,43 @@ def test_reference_constants(oracle):
     assert c["one"] >> 192 == 0x1824b159acc5056f
 
 
-@pytest.mark.parametrize("curve", ["bls12_381", "pallas", "vesta"])
+@pytest.mark.parametrize("curve", ["bls12_381", "pallas", "vesta", "bn254", "bls12_377"])
 def test_generated_points_on_curve(oracle, curve):
     pts = oracle.gen_points(curve, 40)
     assert all(oracle.on_curve(curve, p) for p in pts)
     assert len({tuple(p) for p in pts}) == 40
+
+
+R_OF = {"bn254": 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001,
+        "bls12_377": 0x12ab655e9a2ca55660b44d1e5c37b00159aa76fed00000010a11800000000001}
+
+
+@pytest.mark.parametrize("curve", ["bn254", "bls12_377"])
+def test_bn254_bls12_377_oracle(oracle, curve):
+    """group order, naive == Pippenger (serial and threaded), and the golden recorded from the
+    reference's own CUDA MSM for these curves on a B200 (tests/golden/make_golden.py curves2)."""
+    r = R_OF[curve]
+    nl = oracle.CURVE_LIMBS[oracle.CURVES[curve]]
+    base = oracle.gen_points(curve, 32)
+    inf = oracle.msm(curve, base[3:4], np.array([oracle.int_to_limbs(r, 4)], dtype=np.uint64), "naive")
+    assert not inf[2 * nl:].any()
+    n = 300
+    pts = base[np.arange(n) % 32].copy()
+    pts[3] = 0
+    sc = _sc(n, 5, r)
+    a = oracle.jac_to_affine(curve, oracle.msm(curve, pts, sc, "naive"))
+    b = oracle.jac_to_affine(curve, oracle.msm(curve, pts, sc, "serial"))
+    c = oracle.jac_to_affine(curve, oracle.msm(curve, pts, sc, "pippenger", ncpus=4))
+    assert np.array_equal(a, b) and np.array_equal(a, c) and oracle.on_curve(curve, a)
+    path = os.path.join(GOLD, "msm_curves2_ref_gpu.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden not recorded")
+    g = np.load(path)
+    for k in range(int(g[f"{curve}_ncases"])):
+        p = g[f"{curve}_points{k}"].copy()
+        p[p[:, 2 * nl] != 0, :2 * nl] = 0                    # flagged rows are infinity
+        got = oracle.jac_to_affine(curve, oracle.msm(curve, np.ascontiguousarray(p[:, :2 * nl]), g[f"{curve}_scalars{k}"]))
+        assert np.array_equal(got, oracle.jac_to_affine(curve, g[f"{curve}_out{k}"])), k
 
 
 def _sc(n, seed, r=R_BLS):

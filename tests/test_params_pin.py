@@ -77,6 +77,22 @@ def test_msm_field_constants():
     assert ours("vesta_fp", "P") == theirs(q, "Vesta_P")
     assert ours("vesta_fp", "ONE") == theirs(q, "Vesta_one")
     assert "M0 = 0xfffcfffdu" in gen.split("struct bls12_381_fp_params")[1].split("typedef")[0]
+    # ff/alt_bn128.hpp:13-47, ff/bls12-377.hpp:13-51
+    a = f"{REF}/ff/alt_bn128.hpp"
+    assert ours("bn254_fp", "P") == theirs(a, "ALT_BN128_P")
+    assert ours("bn254_fp", "RR") == theirs(a, "ALT_BN128_RR")
+    assert ours("bn254_fp", "ONE") == theirs(a, "ALT_BN128_one")
+    assert ours("bn254_fr", "P") == theirs(a, "ALT_BN128_r")
+    assert ours("bn254_fr", "RR") == theirs(a, "ALT_BN128_rRR")
+    assert ours("bn254_fr", "ONE") == theirs(a, "ALT_BN128_rone")
+    assert "M0 = 0xe4866389u" in gen.split("struct bn254_fp_params")[1].split("typedef")[0]
+    assert "M0 = 0xefffffffu" in gen.split("struct bn254_fr_params")[1].split("typedef")[0]
+    c = f"{REF}/ff/bls12-377.hpp"
+    assert ours("bls12_377_fp", "P") == theirs(c, "BLS12_377_P")
+    assert ours("bls12_377_fp", "RR") == theirs(c, "BLS12_377_RR")
+    assert ours("bls12_377_fp", "ONE") == theirs(c, "BLS12_377_one")
+    assert ours("bls12_377_fr", "P") == theirs(c, "BLS12_377_r")
+    assert ours("bls12_377_fr", "ONE") == theirs(c, "BLS12_377_rone")
 
 
 def test_256bit_ntt_roots():
@@ -96,12 +112,15 @@ def test_256bit_ntt_roots():
         out["group_gen"] = sum(v << (64 * i) for i, v in enumerate(l))
         return out
     R = 1 << 256
-    for name, p, g in (("bls12_381", 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001, 7),
-                       ("vesta", 0x40000000000000000000000000000000224698fc0994a8dd8c46eb2100000001, 5),
-                       ("pallas", 0x40000000000000000000000000000000224698fc094cf91b992d30ed00000001, 5)):
+    for name, p, g, S in (("bls12_381", 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001, 7, 32),
+                          ("vesta", 0x40000000000000000000000000000000224698fc0994a8dd8c46eb2100000001, 5, 32),
+                          ("pallas", 0x40000000000000000000000000000000224698fc094cf91b992d30ed00000001, 5, 32),
+                          ("alt_bn128", 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001, 5, 28),
+                          ("bls12_377", 0x12ab655e9a2ca55660b44d1e5c37b00159aa76fed00000010a11800000000001, 22, 47)):
         t = table(f"{REF}/ntt/parameters/{name}.h")
         assert t["group_gen"] == g * R % p
-        w = pow(g, (p - 1) >> 32, p)
-        for lg in range(33):
-            assert t["forward_roots_of_unity"][lg] == pow(w, 1 << (32 - lg), p) * R % p
+        assert len(t["forward_roots_of_unity"]) == S + 1
+        w = pow(g, (p - 1) >> S, p)
+        for lg in range(S + 1):
+            assert t["forward_roots_of_unity"][lg] == pow(w, 1 << (S - lg), p) * R % p
             assert t["domain_size_inverse"][lg] == pow(2, -lg, p) * R % p
