@@ -53,16 +53,37 @@ RustError msm_host(void* out, const void* points, size_t npoints, const void* sc
         const stream_t &compute = gpu[0], &copy = gpu[1];
         const bool packed = stride == PB && !has_flag;
 
-        // slice schedule: short first slices (the GPU idles while slice 0 crosses PCIe), then
-        // longer ones (fewer bucket reloads); slice k+1 is copied while slice k is computed
+        // slice schedule: a short first slice (the GPU idles while slice 0 crosses PCIe), then
+        // doubling ones (fewer bucket reloads); slice k+1 is copied while slice k is computed
         std::vector<size_t> sched;
-        if (const char* env = getenv("SPPARK_B200_MSM_SLICES")) {
+        if (const char* env = getenv("SPPARK_B200_MSM_SCHED")) {
+            // experiments: relative slice sizes, e.g. "1,1,2,4,8"
+            std::vector<size_t> w;
+            size_t sum = 0;
+            for (const char* p = env; *p;) {
+                size_t v = strtoul(p, const_cast<char**>(&p), 10);
+                if (v == 0) { w.clear(); break; }
+                w.push_back(v);
+                sum += v;
+                if (*p == ',') p++;
+            }
+            size_t done = 0;
+            for (size_t k = 0; k < w.size() && done < npoints; k++) {
+                size_t part = k + 1 == w.size() ? npoints - done
+                                                : std::min(npoints - done, ((npoints / sum * w[k]) + 31) & ~(size_t)31);
+                if (part) sched.push_back(part);
+                done += part;
+            }
+            if (sched.empty()) sched.push_back(npoints);
+        } else if (const char* env = getenv("SPPARK_B200_MSM_SLICES")) {
             size_t k = std::max(1, atoi(env)), each = ((npoints + k - 1) / k + 31) & ~(size_t)31;
             for (size_t done = 0; done < npoints; done += each) sched.push_back(std::min(each, npoints - done));
         } else if (npoints >= (1u << 22)) {
-            const size_t e = (npoints / 8 + 31) & ~(size_t)31;
-            for (size_t part : {e, e, 2 * e}) sched.push_back(part);
-            sched.push_back(npoints - 4 * e);
+            // N/16, N/8, N/4, 9N/16 (measured at 2^26, tools/probe_e2e.py: 414 ms; N/8, N/8, N/4,
+            // N/2: 426 ms; five or six slices: 416-418 ms)
+            const size_t e = (npoints / 16 + 31) & ~(size_t)31;
+            for (size_t part : {e, 2 * e, 4 * e}) sched.push_back(part);
+            sched.push_back(npoints - 7 * e);
         } else {
             sched.push_back(npoints);
         }

@@ -188,6 +188,26 @@ def test_bls12_381_msm_2pow20_folded(oracle):
     assert _same_point(oracle, "bls12_381", got, want)
 
 
+def test_bls12_381_msm_2pow22_default_slicing(oracle):
+    """2^22 points through mult_pippenger: the size from which the host pipeline cuts the input into
+    N/16, N/8, N/4, 9N/16 slices copied while the previous slice is accumulated (msm_host.cuh);
+    checked by folding the scalars of the replicated points onto the 2^10 distinct ones."""
+    from sppark_b200 import msm
+    n, m = 1 << 22, 1 << 10
+    base = oracle.gen_points("bls12_381", m)
+    pts = np.tile(base, (n // m, 1))
+    pts[3] = 0
+    rng = np.random.default_rng(22)
+    sc = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
+    sc[:, 3] >>= np.uint64(2)
+    sc[3] = 0
+    got = msm.multi_scalar_mult(pts, sc)
+    halves = sc.reshape(n // m, m, 4).view(np.uint32).reshape(n // m, m, 8).astype(np.uint64).sum(axis=0)   # < 2^44 each
+    folded = np.array([_limbs(sum(int(v) << (32 * k) for k, v in enumerate(row)) % R_BLS, 4) for row in halves], dtype=np.uint64)
+    want = oracle.msm("bls12_381", base, folded, "pippenger", ncpus=8)
+    assert _same_point(oracle, "bls12_381", got, want)
+
+
 def test_matches_reference_golden(oracle):
     """Same group element as the reference's CUDA mult_pippenger (recorded on a B200) and as its
     CPU msm/pippenger.hpp, on the committed inputs."""
