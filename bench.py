@@ -448,7 +448,10 @@ def bench_ntt(args, torch, ntt, _lib, peak, peak_src, barrier, max_over_ranks, w
            "ms_per_ntt": ms, "scaling": "replicas", "iters": iters, "l2": "256 MiB write between iterations",
            "roofline": {"bound": "hbm", "kernel": "ntt::pass_kernel<gl64> (slowest pass)",
                         "achieved": alg / (worst * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                        "frac": alg / (worst * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                        "frac": alg / (worst * 1e-3) / 1e9 / peak,
+                        # dram__bytes_read.sum + dram__bytes_write.sum of that pass from the ncu --set full
+                        # capture (profiles/ntt_pass_r01.md: 134.5 MB + 89.4 MB), 2^24 only
+                        "traffic": 224.0e6 if lg == 24 else None, "peak_source": peak_src,
                         "pass_ms": [round(p, 4) for p in passes],
                         "whole_transform_frac": alg / (ms * 1e-3) / 1e9 / peak}}
     # e2e: in place on the pinned host buffer through compute_ntt
