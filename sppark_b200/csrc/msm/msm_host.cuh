@@ -100,11 +100,17 @@ RustError msm_host(void* out, const void* points, size_t npoints, const void* sc
         dev_ptr_t<uint32_t> d_out(JB / 4, compute);
         dev_ptr_t<uint32_t> d_points(nbuf * slice_n * (PB / 4), compute), d_scalars(nbuf * slice_n * 8, compute);
         dev_ptr_t<uint8_t> d_raw(packed ? 1 : nbuf * slice_n * stride, compute);
-        cudaEvent_t copied[2], consumed[2], ready;
-        for (auto* e : {&copied[0], &copied[1], &consumed[0], &consumed[1], &ready})
-            CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-        CUDA_OK(cudaEventRecord(ready, compute));                 // buffers exist
-        CUDA_OK(cudaStreamWaitEvent(copy, ready, 0));
+        event_t copied[2], consumed[2], ready;
+        ready.record(compute);                                    // buffers exist
+        ready.wait(copy);
+
+        // on any failure, drain both streams while the buffers above are still alive (their
+        // stream-ordered frees run during unwinding)
+        struct drain_t {
+            const stream_t &a, &b;
+            bool armed = true;
+            ~drain_t() { if (armed) { (void)cudaStreamSynchronize(a); (void)cudaStreamSynchronize(b); } }
+        } drain{compute, copy};
 
         msm::msm_t<F> m(gpu);
         auto job = m.begin(npoints, slice_n, compute);
@@ -113,7 +119,7 @@ RustError msm_host(void* out, const void* points, size_t npoints, const void* sc
             const size_t b = k & (nbuf - 1), n = sched[k];
             uint32_t* dp = d_points + b * slice_n * (PB / 4);
             uint32_t* ds = d_scalars + b * slice_n * 8;
-            if (k >= nbuf) CUDA_OK(cudaStreamWaitEvent(copy, consumed[b], 0));   // buffer free again
+            if (k >= nbuf) consumed[b].wait(copy);                                // buffer free again
             upload(ds, (const uint8_t*)scalars + first * 32, n * 32);
             if (packed) {
                 upload(dp, (const uint8_t*)points + first * PB, n * PB);
@@ -125,17 +131,17 @@ RustError msm_host(void* out, const void* points, size_t npoints, const void* sc
                 COUNT_LAUNCH();
                 CUDA_OK(cudaGetLastError());
             }
-            CUDA_OK(cudaEventRecord(copied[b], copy));
-            CUDA_OK(cudaStreamWaitEvent(compute, copied[b], 0));
+            copied[b].record(copy);
+            copied[b].wait(compute);
             if (unmont) unmont(ds, n, compute);
             m.slice(job, dp, ds, n, compute);
-            CUDA_OK(cudaEventRecord(consumed[b], compute));
+            consumed[b].record(compute);
         }
         m.finish(job, d_out, compute);
         compute.DtoH(out, d_out, JB);
         compute.sync();
         copy.sync();
-        for (auto e : {copied[0], copied[1], consumed[0], consumed[1], ready}) cudaEventDestroy(e);
+        drain.armed = false;
     } catch (const cuda_error& e) {
         memset(out, 0, JB);                      // out->inf(), as the reference does on failure
         return rust_err(e.code(), e.what());

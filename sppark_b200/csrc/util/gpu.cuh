@@ -88,6 +88,18 @@ public:
     void sync() const { CUDA_OK(cudaStreamSynchronize(s)); }
 };
 
+// cudaEvent_t with a lifetime (no timing): destroyed on every exit path
+class event_t {
+    cudaEvent_t e;
+public:
+    event_t() { CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
+    ~event_t() { (void)cudaEventDestroy(e); }
+    event_t(const event_t&) = delete;
+    operator cudaEvent_t() const { return e; }
+    void record(cudaStream_t s) const { CUDA_OK(cudaEventRecord(e, s)); }
+    void wait(cudaStream_t s) const { CUDA_OK(cudaStreamWaitEvent(s, e, 0)); }
+};
+
 // ---- pageable host memory -> device, at pinned-memory speed ---------------------------------
 // cudaMemcpyAsync from pageable memory is staged by the driver through a small bounce buffer on
 // the calling thread (~10 GB/s).  The reference's callers (Rust Vec, Go slices) hand over

@@ -74,8 +74,11 @@ def test_shard_range_properties():
             assert max(h - l for l, h in r) - min(h - l for l, h in r) <= 1
 
 
-def _ntt_worker(rank, world, port, lg, q):
+def _ntt_worker(rank, world, port, lg, q, split=None):
     sys.path.insert(0, ROOT)
+    if split:
+        os.environ["SPPARK_B200_NTT_SPLIT"] = split          # small digits: the multi-pass second stage
+    s1 = int(split.split(",")[0]) if split else None
     import ctypes as C
     import torch
     import torch.distributed as dist
@@ -87,7 +90,7 @@ def _ntt_worker(rank, world, port, lg, q):
     lg_g = world.bit_length() - 1
     rng = np.random.default_rng(77)                      # same full input on every rank
     x = rng.integers(0, 2**64 - 2**32 + 1, size=1 << lg, dtype=np.uint64)
-    local = torch.from_numpy(parallel.scatter_columns(x, lg, lg_g, rank).reshape(-1).view(np.int64).copy())
+    local = torch.from_numpy(parallel.scatter_columns(x, lg, lg_g, rank, s1=s1).reshape(-1).view(np.int64).copy())
 
     def pass_fn(which, src, dst):                        # CPU single-stepper stands in for the CUDA pass
         assert emu.emu_ntt_slab_gl64(which, src.data_ptr(), dst.data_ptr(), lg, lg_g, rank, 0, 14) == 0
@@ -95,13 +98,13 @@ def _ntt_worker(rank, world, port, lg, q):
     mine = parallel.ntt_slab(local, lg, 0, pass_fn, all_to_all=False).numpy().view(np.uint64)
     gathered = [torch.empty_like(torch.from_numpy(mine.view(np.int64))) for _ in range(world)]
     dist.all_gather(gathered, torch.from_numpy(mine.view(np.int64).copy()))
-    full = parallel.gather_columns([g.numpy().view(np.uint64) for g in gathered], lg, lg_g)
+    full = parallel.gather_columns([g.numpy().view(np.uint64) for g in gathered], lg, lg_g, s1=s1)
     q.put((rank, bool(np.array_equal(full, o.ntt_gl64(x, o.NN)))))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,lg", [(2, 10), (4, 12)])
-def test_slab_sharded_ntt_over_gloo(world, lg):
+@pytest.mark.parametrize("world,lg,split", [(2, 10, None), (4, 12, None), (2, 9, "3,3,3"), (4, 11, "4,3,4")])
+def test_slab_sharded_ntt_over_gloo(world, lg, split):
     import subprocess
     import torch.multiprocessing as mp
     so = os.path.join(ROOT, "tests", "emu", "libntt_emu.so")
@@ -111,7 +114,7 @@ def test_slab_sharded_ntt_over_gloo(world, lg):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_ntt_worker, args=(r, world, port, lg, q)) for r in range(world)]
+    procs = [ctx.Process(target=_ntt_worker, args=(r, world, port, lg, q, split)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in range(world)]
