@@ -169,6 +169,15 @@ RustError sppark_b200_msm(int curve, void *out_jacobian, const void *points_affi
 RustError sppark_b200_msm_ex(int curve, void *out_jacobian, const void *points_affine,
                              size_t npoints, const void *scalars, size_t ffi_affine_sz,
                              int scalars_mont);
+/* Preloaded points: the reference's msm_t{points, npoints} constructor + invoke(out, scalars)
+ * (msm/pippenger.cuh:377-390,582-601) -- a fixed SRS stays on the device (of the calling thread's
+ * current GPU), each invoke moves only the scalars (host pointer; npoints <= preloaded count). */
+typedef struct sppark_b200_msm_ctx sppark_b200_msm_ctx;
+RustError sppark_b200_msm_ctx_create(int curve, const void *points_affine, size_t npoints,
+                                     size_t ffi_affine_sz, sppark_b200_msm_ctx **out);
+RustError sppark_b200_msm_ctx_invoke(sppark_b200_msm_ctx *ctx, void *out_jacobian, const void *scalars,
+                                     size_t npoints, int scalars_mont);
+void      sppark_b200_msm_ctx_free(sppark_b200_msm_ctx *ctx);
 /* msm_t::invoke with device-resident points and scalars (msm/pippenger.cuh:582-601):
  * d_points: packed affine {X,Y}; d_scalars: 32-B LE; result written to HOST out_jacobian
  * after synchronising `stream`. */

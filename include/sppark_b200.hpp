@@ -143,11 +143,38 @@ inline const gpu_t& select_gpu(int id = 0)
 template<class bucket_t, class point_t, class affine_t, class scalar_t>
 class msm_t {
     int device_id;
+    sppark_b200_msm_ctx* ctx = nullptr;                    // preloaded points, if any
+    size_t preloaded = 0;
+    RustError ctor_error{0, nullptr};
+    msm_t(const msm_t&) = delete;
+    msm_t& operator=(const msm_t&) = delete;
 public:
     // the reference pre-sizes its scratch from npoints; scratch here is allocated per call from the
-    // stream-ordered pool, so the constructor only records the device
+    // stream-ordered pool, so these constructors only record the device
     msm_t(std::nullptr_t = nullptr, size_t /*npoints*/ = 0, int device = -1) : device_id(device) {}
     explicit msm_t(size_t /*npoints*/, int device = -1) : device_id(device) {}
+    // points preloaded on the (current) device: msm_t{points, npoints[, ffi_affine_sz]}
+    // (msm/pippenger.cuh:377-380), then invoke(out, scalars[, mont]) per scalar vector
+    msm_t(const affine_t points[], size_t npoints, size_t ffi_affine_sz = sizeof(affine_t), int device = -1)
+        : device_id(device), preloaded(npoints)
+    {
+        typedef std::remove_cv_t<std::remove_reference_t<decltype(points[0].X)>> field_t;
+        if constexpr (field_t::msm_curve >= 0)
+            ctor_error = sppark_b200_msm_ctx_create(field_t::msm_curve, points, npoints, ffi_affine_sz, &ctx);
+    }
+    ~msm_t() { sppark_b200_msm_ctx_free(ctx); if (ctor_error.message) drop_error_message(ctor_error.message); }
+
+    RustError invoke(point_t& out, const scalar_t scalars[], bool mont = true)
+    {   return invoke(out, preloaded, scalars, mont);   }
+    RustError invoke(point_t& out, size_t npoints, const scalar_t scalars[], bool mont = true)
+    {
+        if (ctx == nullptr) {
+            out.inf();
+            return ctor_error.code ? RustError{ctor_error.code, ctor_error.message ? strdup(ctor_error.message) : nullptr}
+                                   : RustError{-1, strdup("sppark_b200: msm_t has no preloaded points")};
+        }
+        return sppark_b200_msm_ctx_invoke(ctx, &out, scalars, npoints, mont);
+    }
 
     RustError invoke(point_t& out, const affine_t points[], size_t npoints, const scalar_t scalars[],
                      bool mont = true, size_t ffi_affine_sz = sizeof(affine_t))

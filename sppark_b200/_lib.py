@@ -43,6 +43,8 @@ _SIGS = {
     "sppark_b200_peer_free": [C.c_void_p],
     "sppark_b200_msm": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t],
     "sppark_b200_msm_ex": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int],
+    "sppark_b200_msm_ctx_create": [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p)],
+    "sppark_b200_msm_ctx_invoke": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int],
     "sppark_b200_msm_dev": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p],
     "sppark_b200_generate_points_dev": [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p],
     "sppark_b200_msm_combine": [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t],
@@ -53,7 +55,7 @@ _SIGS = {
 EXPORTS = list(_SIGS) + ["cuda_available", "drop_error_message", "sppark_b200_sm_count", "sppark_b200_ngpus",
                          "sppark_b200_version", "sppark_b200_launch_count",
                          "sppark_b200_profile_enable", "sppark_b200_profile_read",
-                         "drop_gpu_ptr_t", "clone_gpu_ptr_t", "sppark_b200_gpu_ptr_alloc",
+                         "drop_gpu_ptr_t", "clone_gpu_ptr_t", "sppark_b200_msm_ctx_free", "sppark_b200_gpu_ptr_alloc",
                          "sppark_b200_gpu_ptr_get", "sppark_b200_gpu_ptr_refs"]
 
 
@@ -73,6 +75,8 @@ def lib():
         l.sppark_b200_sm_count.argtypes = [C.c_int]
         l.sppark_b200_version.restype = C.c_char_p
         l.sppark_b200_launch_count.restype = C.c_uint64
+        l.sppark_b200_msm_ctx_free.argtypes = [C.c_void_p]
+        l.sppark_b200_msm_ctx_free.restype = None
         l.drop_gpu_ptr_t.argtypes = [C.POINTER(GpuPtr)]
         l.clone_gpu_ptr_t.argtypes = [C.POINTER(GpuPtr)]
         l.clone_gpu_ptr_t.restype = GpuPtr

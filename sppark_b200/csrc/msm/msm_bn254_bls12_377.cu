@@ -29,3 +29,19 @@ RustError gen_points_bls12_377(void* d_out, size_t n, void* stream)
 {   return gen_points_dev<ff::bls12_377_g1_gen>(d_out, n, stream);   }
 RustError combine_bls12_377(void* out, const void* partials, size_t count)
 {   return combine_host<ff::bls12_377_fp_t>(out, partials, count);   }
+
+RustError msm_preload_bn254(const void* points, size_t npoints, size_t stride, bool has_flag, void** d_points)
+{   return msm_preload<ff::bn254_fp_t>(points, npoints, stride, has_flag, d_points);   }
+RustError msm_resident_bn254(void* out, const void* d_points, size_t npoints, const void* scalars, bool mont)
+{
+    return msm_host<ff::bn254_fp_t>(out, nullptr, npoints, scalars, 0, false, mont ? scalars_from_mont<ff::bn254_fr_t> : nullptr,
+                      (const uint32_t*)d_points);
+}
+
+RustError msm_preload_bls12_377(const void* points, size_t npoints, size_t stride, bool has_flag, void** d_points)
+{   return msm_preload<ff::bls12_377_fp_t>(points, npoints, stride, has_flag, d_points);   }
+RustError msm_resident_bls12_377(void* out, const void* d_points, size_t npoints, const void* scalars, bool mont)
+{
+    return msm_host<ff::bls12_377_fp_t>(out, nullptr, npoints, scalars, 0, false, mont ? scalars_from_mont<ff::bls12_377_fr_t> : nullptr,
+                      (const uint32_t*)d_points);
+}

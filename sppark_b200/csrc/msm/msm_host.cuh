@@ -39,19 +39,23 @@ void scalars_from_mont(uint32_t* d_scalars, size_t n, cudaStream_t stream)
 }
 typedef void (*unmont_fn)(uint32_t*, size_t, cudaStream_t);
 
+// `resident` != nullptr: the points are already on the device as packed affine rows (preloaded by
+// msm_preload below -- the reference's msm_t{points, npoints} constructor + invoke(out, scalars),
+// msm/pippenger.cuh:377-390,582-601): only the scalars cross PCIe, sliced the same way.
 template<class F>
 RustError msm_host(void* out, const void* points, size_t npoints, const void* scalars,
-                   size_t stride, bool has_flag, unmont_fn unmont = nullptr)
+                   size_t stride, bool has_flag, unmont_fn unmont = nullptr,
+                   const uint32_t* resident = nullptr)
 {
     constexpr size_t PB = 2 * F::N * 4, JB = 3 * F::N * 4;
     try {
         const gpu_t& gpu = select_gpu(-1);
         gpu.select();
         if (npoints == 0) { memset(out, 0, JB); return rust_ok(); }
-        if (stride < PB + (has_flag ? 1 : 0))
+        if (!resident && stride < PB + (has_flag ? 1 : 0))
             return rust_err(-(int)cudaErrorInvalidValue, "msm: affine stride too small");
         const stream_t &compute = gpu[0], &copy = gpu[1];
-        const bool packed = stride == PB && !has_flag;
+        const bool packed = resident || (stride == PB && !has_flag);
 
         // slice schedule: a short first slice (the GPU idles while slice 0 crosses PCIe), then
         // doubling ones (fewer bucket reloads); slice k+1 is copied while slice k is computed
@@ -89,7 +93,7 @@ RustError msm_host(void* out, const void* points, size_t npoints, const void* sc
         }
         const size_t nslices = sched.size(), nbuf = nslices > 1 ? 2 : 1;
         const size_t slice_n = *std::max_element(sched.begin(), sched.end());
-        const bool pageable = stager_t::is_pageable(points) || stager_t::is_pageable(scalars);
+        const bool pageable = (!resident && stager_t::is_pageable(points)) || stager_t::is_pageable(scalars);
         std::unique_lock<std::mutex> stage_lock(gpu.stage_mtx, std::defer_lock);
         if (pageable) stage_lock.lock();
         auto upload = [&](void* dst, const void* src, size_t bytes) {
@@ -98,7 +102,7 @@ RustError msm_host(void* out, const void* points, size_t npoints, const void* sc
         };
 
         dev_ptr_t<uint32_t> d_out(JB / 4, compute);
-        dev_ptr_t<uint32_t> d_points(nbuf * slice_n * (PB / 4), compute), d_scalars(nbuf * slice_n * 8, compute);
+        dev_ptr_t<uint32_t> d_points(resident ? 1 : nbuf * slice_n * (PB / 4), compute), d_scalars(nbuf * slice_n * 8, compute);
         dev_ptr_t<uint8_t> d_raw(packed ? 1 : nbuf * slice_n * stride, compute);
         event_t copied[2], consumed[2], ready;
         ready.record(compute);                                    // buffers exist
@@ -117,17 +121,19 @@ RustError msm_host(void* out, const void* points, size_t npoints, const void* sc
         size_t first = 0;
         for (size_t k = 0; k < nslices; first += sched[k], k++) {
             const size_t b = k & (nbuf - 1), n = sched[k];
-            uint32_t* dp = d_points + b * slice_n * (PB / 4);
+            const uint32_t* dp = resident ? resident + first * (PB / 4) : d_points + b * slice_n * (PB / 4);
             uint32_t* ds = d_scalars + b * slice_n * 8;
             if (k >= nbuf) consumed[b].wait(copy);                                // buffer free again
             upload(ds, (const uint8_t*)scalars + first * 32, n * 32);
-            if (packed) {
-                upload(dp, (const uint8_t*)points + first * PB, n * PB);
+            if (resident) {
+            } else if (packed) {
+                upload(d_points + b * slice_n * (PB / 4), (const uint8_t*)points + first * PB, n * PB);
             } else {
                 uint8_t* dr = d_raw + b * slice_n * stride;
                 upload(dr, (const uint8_t*)points + first * stride, n * stride);
                 uint32_t blocks = (uint32_t)std::min<size_t>((n + 255) / 256, (size_t)gpu.sm_count() * 8);
-                msm::pack_points_kernel<<<blocks, 256, 0, copy>>>(dr, stride, PB / 4, has_flag, dp, (uint32_t)n);
+                msm::pack_points_kernel<<<blocks, 256, 0, copy>>>(dr, stride, PB / 4, has_flag,
+                                                                  d_points + b * slice_n * (PB / 4), (uint32_t)n);
                 COUNT_LAUNCH();
                 CUDA_OK(cudaGetLastError());
             }
@@ -147,6 +153,55 @@ RustError msm_host(void* out, const void* points, size_t npoints, const void* sc
         return rust_err(e.code(), e.what());
     } catch (const std::exception& e) {
         memset(out, 0, JB);
+        return rust_err(-1, e.what());
+    }
+    return rust_ok();
+}
+
+// host points -> a plain cudaMalloc'ed buffer of packed affine rows that outlives the call
+template<class F>
+RustError msm_preload(const void* points, size_t npoints, size_t stride, bool has_flag, void** d_out)
+{
+    constexpr size_t PB = 2 * F::N * 4;
+    *d_out = nullptr;
+    try {
+        const gpu_t& gpu = select_gpu(-1);
+        gpu.select();
+        if (stride < PB + (has_flag ? 1 : 0))
+            return rust_err(-(int)cudaErrorInvalidValue, "msm: affine stride too small");
+        const stream_t& copy = gpu[1];
+        uint32_t* d_points = nullptr;
+        CUDA_OK(cudaMalloc((void**)&d_points, npoints ? npoints * PB : 1));
+        struct guard_t { uint32_t* p; ~guard_t() { if (p) (void)cudaFree(p); } } guard{d_points};
+        const bool pageable = stager_t::is_pageable(points);
+        std::unique_lock<std::mutex> stage_lock(gpu.stage_mtx, std::defer_lock);
+        if (pageable) stage_lock.lock();
+        auto upload = [&](void* dst, const void* src, size_t bytes) {
+            if (pageable) gpu.stager().HtoD(copy, dst, src, bytes);
+            else copy.HtoD(dst, src, bytes);
+        };
+        if (stride == PB && !has_flag) {
+            upload(d_points, points, npoints * PB);
+        } else {
+            const size_t chunk = std::min<size_t>(npoints, (size_t)1 << 22);
+            dev_ptr_t<uint8_t> d_raw(chunk * stride, copy);
+            for (size_t first = 0; first < npoints; first += chunk) {
+                const size_t n = std::min(chunk, npoints - first);
+                upload(d_raw, (const uint8_t*)points + first * stride, n * stride);
+                uint32_t blocks = (uint32_t)std::min<size_t>((n + 255) / 256, (size_t)gpu.sm_count() * 8);
+                msm::pack_points_kernel<<<blocks, 256, 0, copy>>>(d_raw, stride, PB / 4, has_flag,
+                                                                  d_points + first * (PB / 4), (uint32_t)n);
+                COUNT_LAUNCH();
+                CUDA_OK(cudaGetLastError());
+            }
+            copy.sync();
+        }
+        copy.sync();
+        guard.p = nullptr;
+        *d_out = d_points;
+    } catch (const cuda_error& e) {
+        return rust_err(e.code(), e.what());
+    } catch (const std::exception& e) {
         return rust_err(-1, e.what());
     }
     return rust_ok();

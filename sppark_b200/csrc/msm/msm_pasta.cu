@@ -27,3 +27,19 @@ RustError combine_pallas(void* out, const void* partials, size_t count)
 {   return combine_host<ff::pallas_fp_t>(out, partials, count);   }
 RustError combine_vesta(void* out, const void* partials, size_t count)
 {   return combine_host<ff::vesta_fp_t>(out, partials, count);   }
+
+RustError msm_preload_pallas(const void* points, size_t npoints, size_t stride, bool has_flag, void** d_points)
+{   return msm_preload<ff::pallas_fp_t>(points, npoints, stride, has_flag, d_points);   }
+RustError msm_resident_pallas(void* out, const void* d_points, size_t npoints, const void* scalars, bool mont)
+{
+    return msm_host<ff::pallas_fp_t>(out, nullptr, npoints, scalars, 0, false, mont ? scalars_from_mont<ff::vesta_fp_t> : nullptr,
+                      (const uint32_t*)d_points);
+}
+
+RustError msm_preload_vesta(const void* points, size_t npoints, size_t stride, bool has_flag, void** d_points)
+{   return msm_preload<ff::vesta_fp_t>(points, npoints, stride, has_flag, d_points);   }
+RustError msm_resident_vesta(void* out, const void* d_points, size_t npoints, const void* scalars, bool mont)
+{
+    return msm_host<ff::vesta_fp_t>(out, nullptr, npoints, scalars, 0, false, mont ? scalars_from_mont<ff::pallas_fp_t> : nullptr,
+                      (const uint32_t*)d_points);
+}

@@ -70,6 +70,40 @@ def msm(curve, points, scalars, mont=False):
     return out
 
 
+class MsmContext:
+    """Points preloaded on the current GPU (the reference's msm_t{points, npoints}): every
+    `invoke(scalars)` moves only the scalars.  Host arrays as for msm()."""
+
+    def __init__(self, curve, points):
+        import ctypes as C
+        if points.dtype != np.uint64 or not points.flags["C_CONTIGUOUS"]:
+            raise TypeError("points must be a C-contiguous uint64 limb array")
+        nl = _LIMBS[curve]
+        assert points.shape[1] in (2 * nl, 2 * nl + 1)
+        self.curve, self.npoints, self._h = curve, points.shape[0], C.c_void_p()
+        _lib.check(_lib.lib().sppark_b200_msm_ctx_create(curve, points.ctypes.data, points.shape[0],
+                                                         points.strides[0], C.byref(self._h)))
+
+    def invoke(self, scalars, mont=False):
+        if scalars.dtype != np.uint64 or scalars.ndim != 2 or scalars.shape[1] != 4 or not scalars.flags["C_CONTIGUOUS"]:
+            raise TypeError("scalars must be a C-contiguous (n, 4) uint64 array")
+        out = np.zeros(3 * _LIMBS[self.curve], dtype=np.uint64)
+        _lib.check(_lib.lib().sppark_b200_msm_ctx_invoke(self._h, out.ctypes.data, scalars.ctypes.data,
+                                                         scalars.shape[0], int(mont)))
+        return out
+
+    def close(self):
+        if self._h:
+            _lib.lib().sppark_b200_msm_ctx_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def msm_dev(curve, d_points, d_scalars, npoints=None, stream=None):
     """msm_t::invoke with device-resident inputs (msm/pippenger.cuh:582-601): torch CUDA tensors
     of packed affine points / 32-byte scalars; synchronises the stream and returns the Jacobian

@@ -4,6 +4,7 @@
 // against include/sppark_b200.hpp + libsppark_b200.so.  tests/test_cpp_layer.py feeds it inputs
 // through stdin-less binary files and checks the outputs against the oracle.
 //   dropin_example msm <points.bin> <scalars.bin> <n> <mont 0|1> <out.bin>
+//   dropin_example ctx <points.bin> <scalars.bin> <n> <mont 0|1> <out.bin>   (msm_t with preloaded points)
 //   dropin_example ntt <data.bin> <lg> <order> <direction> <type>       (in place)
 #include <cstdio>
 #include <cstdlib>
@@ -54,6 +55,17 @@ int main(int argc, char** argv)
                                                sizeof(affine_t));
         if (report(e)) return 1;
         dump(argv[6], &out, 1);
+        return 0;
+    }
+    if (argc == 7 && argv[1][0] == 'c') {                  // preloaded points, two invocations
+        size_t n = strtoull(argv[4], nullptr, 10);
+        auto points = slurp<affine_t>(argv[2], n);
+        auto scalars = slurp<scalar_t>(argv[3], n);
+        msm_t<bucket_t, point_t, affine_t, scalar_t> msm{points.data(), n, sizeof(affine_t)};
+        point_t out[2];
+        if (report(msm.invoke(out[0], scalars.data(), atoi(argv[5]) != 0))) return 1;
+        if (report(msm.invoke(out[1], n / 2, scalars.data(), atoi(argv[5]) != 0))) return 1;   // a prefix
+        dump(argv[6], out, 2);
         return 0;
     }
 #endif

@@ -95,6 +95,24 @@ def test_cpp_example_msm(oracle, tmp_path, mont):
 
 
 @pytest.mark.gpu
+def test_cpp_example_preloaded_points(oracle, tmp_path):
+    """msm_t{points, npoints}.invoke(out, scalars): the SRS stays on the GPU between invocations."""
+    exe, _ = _builder().build_example()
+    n = 4000
+    pts = np.zeros((n, 13), dtype=np.uint64)
+    pts[:, :12] = oracle.gen_points("bls12_381", 128)[np.arange(n) % 128]
+    sc = _scalars(n, 77)
+    pts.tofile(tmp_path / "p.bin")
+    sc.tofile(tmp_path / "s.bin")
+    subprocess.check_call([exe, "ctx", str(tmp_path / "p.bin"), str(tmp_path / "s.bin"), str(n), "0", str(tmp_path / "o.bin")])
+    got = np.fromfile(tmp_path / "o.bin", dtype=np.uint64).reshape(2, 18)
+    flat = np.ascontiguousarray(pts[:, :12])
+    for k, m in enumerate((n, n // 2)):
+        want = oracle.msm("bls12_381", flat[:m], sc[:m], "pippenger", ncpus=8)
+        assert np.array_equal(oracle.jac_to_affine("bls12_381", got[k]), oracle.jac_to_affine("bls12_381", want)), m
+
+
+@pytest.mark.gpu
 def test_cpp_example_ntt(oracle, tmp_path):
     _, exe = _builder().build_example()
     rng = np.random.default_rng(3)

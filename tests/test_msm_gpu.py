@@ -208,6 +208,35 @@ def test_bls12_381_msm_2pow22_default_slicing(oracle):
     assert _same_point(oracle, "bls12_381", got, want)
 
 
+@pytest.mark.parametrize("curve,cid,fr", [("bls12_381", 0, "bls12_381_fr"), ("pallas", 1, "vesta_fp"), ("bn254", 4, "bn254_fr")])
+def test_preloaded_points_context(oracle, curve, cid, fr):
+    """sppark_b200_msm_ctx_*: points uploaded once (packed or arkworks rows), several scalar
+    vectors against them, prefixes, Montgomery-form scalars; and the error paths."""
+    from sppark_b200 import _lib, msm
+    r = oracle.ff_consts(fr)["p"]
+    nl = oracle.CURVE_LIMBS[oracle.CURVES[curve]]
+    n = 1 << 15
+    base = oracle.gen_points(curve, 256)
+    pts = base[np.arange(n) % 256].copy()
+    ark = np.zeros((n, 2 * nl + 1), dtype=np.uint64)
+    ark[:, :2 * nl] = pts
+    ark[11, 2 * nl] = 1
+    ref = pts.copy()
+    ref[11] = 0
+    for layout, want_pts in ((pts, pts), (ark, ref)):
+        ctx = msm.MsmContext(cid, layout)
+        for seed, m in ((1, n), (2, n), (3, 1000), (4, 1)):
+            sc = _scalars(m, seed, r)
+            assert _same_point(oracle, curve, ctx.invoke(sc), oracle.msm(curve, want_pts[:m], sc, "pippenger", ncpus=8)), (seed, m)
+        sc = _scalars(500, 9, r)
+        mont = np.array([_limbs(oracle.ff_op(fr, "to_mont", _int(row)), 4) for row in sc], dtype=np.uint64)
+        assert _same_point(oracle, curve, ctx.invoke(mont, mont=True), oracle.msm(curve, want_pts[:500], sc, "pippenger", ncpus=8))
+        assert not ctx.invoke(np.zeros((0, 4), dtype=np.uint64)).any()          # no scalars: infinity
+        with pytest.raises(_lib.SpparkError):
+            ctx.invoke(_scalars(n + 1, 5, r))                                    # more scalars than points
+        ctx.close()
+
+
 def test_matches_reference_golden(oracle):
     """Same group element as the reference's CUDA mult_pippenger (recorded on a B200) and as its
     CPU msm/pippenger.hpp, on the committed inputs."""
