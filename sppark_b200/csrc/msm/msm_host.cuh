@@ -82,6 +82,12 @@ RustError msm_host(void* out, const void* points, size_t npoints, const void* sc
         } else if (const char* env = getenv("SPPARK_B200_MSM_SLICES")) {
             size_t k = std::max(1, atoi(env)), each = ((npoints + k - 1) / k + 31) & ~(size_t)31;
             for (size_t done = 0; done < npoints; done += each) sched.push_back(std::min(each, npoints - done));
+        } else if (resident && npoints >= (1u << 22)) {
+            // only 32 B per point cross PCIe: N/8 then the rest (2^26: 394 ms; N/4 + 3N/4: 403;
+            // N/16 + 15N/16: 399; the four-slice schedule below: 408)
+            const size_t e = (npoints / 8 + 31) & ~(size_t)31;
+            sched.push_back(e);
+            sched.push_back(npoints - e);
         } else if (npoints >= (1u << 22)) {
             // N/16, N/8, N/4, 9N/16 (measured at 2^26, tools/probe_e2e.py: 414 ms; N/8, N/8, N/4,
             // N/2: 426 ms; five or six slices: 416-418 ms)
