@@ -24,41 +24,63 @@ static __global__ void count_kernel(const Config cfg, const uint32_t* scalars, u
 
 // control block: [0] task counter, [1] #heavy buckets, [2] #chunks
 // heavy bucket h: heavy_list[3h] = slot, [3h+1] = first chunk, [3h+2] = #chunks; chunk_map[c] = h
-// one CTA per window: exclusive prefix of the bucket histogram; heavy buckets get chunked
+// one CTA (1024 threads) per window: exclusive prefix of the bucket histogram in tiles of 4096
+// counters (one 128-bit load per thread, warp-shuffle scans); heavy buckets get chunked
 static __global__ void __launch_bounds__(1024)
 scan_kernel(const Config cfg, const uint32_t* counts, uint32_t* offsets, uint32_t* cursor,
             uint32_t* ctrl, uint32_t* heavy_list, uint32_t* chunk_map)
 {
-    __shared__ uint32_t partial[1024];
-    const uint32_t w = blockIdx.x, nb = 1u << cfg.lg_nb;
-    const uint32_t per = (nb + blockDim.x - 1) / blockDim.x;
-    const uint32_t first = threadIdx.x * per, last = min(first + per, nb);
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t w = blockIdx.x, nb = 1u << cfg.lg_nb;            // nb >= 8: a multiple of 4
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const size_t base = (size_t)w << cfg.lg_nb;
-    uint32_t sum = 0;
-    for (uint32_t b = first; b < last; b++) sum += counts[base + b];
-    partial[threadIdx.x] = sum;
-    __syncthreads();
-    // Hillis-Steele inclusive scan over the per-thread sums
-    for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
-        uint32_t v = threadIdx.x >= d ? partial[threadIdx.x - d] : 0;
-        __syncthreads();
-        partial[threadIdx.x] += v;
-        __syncthreads();
-    }
-    uint32_t run = partial[threadIdx.x] - sum;
-    for (uint32_t b = first; b < last; b++) {
-        uint32_t c = counts[base + b];
-        offsets[base + b] = run;
-        cursor[base + b] = run;
-        if (c > cfg.heavy) {
-            uint32_t h = atomicAdd(&ctrl[1], 1), nch = (c + cfg.heavy_chunk - 1) / cfg.heavy_chunk;
-            uint32_t first_chunk = atomicAdd(&ctrl[2], nch);
-            heavy_list[3 * h] = (uint32_t)(base + b);
-            heavy_list[3 * h + 1] = first_chunk;
-            heavy_list[3 * h + 2] = nch;
-            for (uint32_t k = 0; k < nch; k++) chunk_map[first_chunk + k] = h;
+    uint32_t carry = 0;                                             // total of the tiles before this one
+    for (uint32_t t0 = 0; t0 < nb; t0 += 4096) {
+        const uint32_t b = t0 + threadIdx.x * 4;
+        uint4 c = make_uint4(0, 0, 0, 0);
+        if (b < nb) c = *reinterpret_cast<const uint4*>(counts + base + b);
+        const uint32_t s = c.x + c.y + c.z + c.w;
+        uint32_t x = s;                                             // inclusive scan inside the warp
+#pragma unroll
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
         }
-        run += c;
+        if (lane == 31) warp_tot[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t t = warp_tot[lane];
+#pragma unroll
+            for (uint32_t d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, t, d);
+                if (lane >= d) t += y;
+            }
+            warp_tot[lane] = t;
+        }
+        __syncthreads();
+        uint4 r;
+        r.x = carry + (wid ? warp_tot[wid - 1] : 0) + x - s;
+        r.y = r.x + c.x;
+        r.z = r.y + c.y;
+        r.w = r.z + c.z;
+        carry += warp_tot[31];
+        if (b < nb) {
+            *reinterpret_cast<uint4*>(offsets + base + b) = r;
+            *reinterpret_cast<uint4*>(cursor + base + b) = r;
+            const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                if (cc[k] > cfg.heavy) {
+                    uint32_t h = atomicAdd(&ctrl[1], 1), nch = (cc[k] + cfg.heavy_chunk - 1) / cfg.heavy_chunk;
+                    uint32_t first_chunk = atomicAdd(&ctrl[2], nch);
+                    heavy_list[3 * h] = (uint32_t)(base + b + k);
+                    heavy_list[3 * h + 1] = first_chunk;
+                    heavy_list[3 * h + 2] = nch;
+                    for (uint32_t q = 0; q < nch; q++) chunk_map[first_chunk + q] = h;
+                }
+            }
+        }
+        __syncthreads();                                            // warp_tot is reused by the next tile
     }
 }
 

@@ -281,7 +281,7 @@ inline uint32_t choose_wbits(size_t npoints)
     }
     if (const char* env = getenv("SPPARK_B200_MSM_WBITS")) {
         uint32_t c = (uint32_t)atoi(env);
-        if (c >= 2 && c <= 24) best = c;
+        if (c >= 3 && c <= 24) best = c;                 // >= 4 buckets per window (scan_kernel loads uint4)
     }
     return best;
 }
