@@ -162,8 +162,10 @@ heavy_fold_kernel(const Config cfg, const uint32_t* ctrl, const uint32_t* heavy_
     }
 }
 
+// 3 CTAs/SM: the <= 4096 items per window of a 2^26 MSM (416 CTAs) then fit one wave of 444
+// resident CTAs; at 255 registers (2 CTAs/SM) they took two
 template<class F>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (F::N > 12 ? 2 : 3))
 reduce1_kernel(const Config cfg, const uint32_t* buckets, uint32_t lg_l, uint32_t nitems,
                uint32_t* outR, uint32_t* outS)
 {
