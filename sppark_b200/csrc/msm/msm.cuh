@@ -3,6 +3,7 @@
 #pragma once
 #include "../util/gpu.cuh"
 #include "msm_core.cuh"
+#include "msm_pair.cuh"
 
 namespace msm {
 
@@ -89,6 +90,103 @@ static __global__ void scatter_kernel(const Config cfg, const uint32_t* scalars,
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cfg.npoints; i += gridDim.x * blockDim.x)
         scatter_body(cfg, scalars, cursor, sorted, i, w0, w1);
+}
+
+// ---- batched-affine pre-reduction of the bucket lists (msm_pair.cuh) ---------------------------
+static __global__ void pair_counts_kernel(const Config cfg, const uint32_t* counts, uint32_t* counts1, uint32_t nslots)
+{
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nslots; t += gridDim.x * blockDim.x)
+        pair_counts_body(cfg, counts, counts1, t);
+}
+
+// one CTA (1024 threads) per window: window-local exclusive prefix of counts1, window total
+static __global__ void __launch_bounds__(1024)
+pair_scan_kernel(const Config cfg, const uint32_t* counts1, uint32_t* off1, uint32_t* wintotal)
+{
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t w = blockIdx.x, nb = 1u << cfg.lg_nb, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t base = (size_t)w << cfg.lg_nb;
+    uint32_t carry = 0;
+    for (uint32_t t0 = 0; t0 < nb; t0 += 4096) {
+        const uint32_t b = t0 + threadIdx.x * 4;
+        uint4 c = make_uint4(0, 0, 0, 0);
+        if (b < nb) c = *reinterpret_cast<const uint4*>(counts1 + base + b);
+        const uint32_t s = c.x + c.y + c.z + c.w;
+        uint32_t x = s;
+#pragma unroll
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) warp_tot[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t t = warp_tot[lane];
+#pragma unroll
+            for (uint32_t d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, t, d);
+                if (lane >= d) t += y;
+            }
+            warp_tot[lane] = t;
+        }
+        __syncthreads();
+        uint4 r;
+        r.x = carry + (wid ? warp_tot[wid - 1] : 0) + x - s;
+        r.y = r.x + c.x;
+        r.z = r.y + c.y;
+        r.w = r.z + c.z;
+        carry += warp_tot[31];
+        if (b < nb) *reinterpret_cast<uint4*>(off1 + base + b) = r;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) wintotal[w] = carry;
+}
+
+static __global__ void pair_winbase_kernel(const Config cfg, const uint32_t* wintotal, uint32_t* winbase)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    uint32_t run = 0;
+    for (uint32_t w = 0; w < cfg.nwins; w++) { winbase[w] = run; run += wintotal[w]; }
+    winbase[cfg.nwins] = run;
+}
+
+template<class F>
+__global__ void __launch_bounds__(128)
+pair_forward_kernel(const Config cfg, const uint32_t* points, const uint32_t* sorted, const uint32_t* offsets,
+                    const uint32_t* counts, const uint32_t* counts1, const uint32_t* off1, const uint32_t* winbase,
+                    uint32_t o0, uint32_t nthreads, uint32_t* pre, uint32_t* totals)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < nthreads)
+        pair_forward_body<F>(cfg, points, sorted, offsets, counts, counts1, off1, winbase, o0, nthreads, pre, totals, tid);
+}
+
+template<class F>
+__global__ void __launch_bounds__(128)
+pair_invert_kernel(uint32_t* totals, uint32_t n)
+{
+    pair_invert_body<F>(totals, n, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+template<class F>
+__global__ void __launch_bounds__(128)
+pair_backward_kernel(const Config cfg, const uint32_t* points, const uint32_t* sorted, const uint32_t* offsets,
+                     const uint32_t* counts, const uint32_t* counts1, const uint32_t* off1, const uint32_t* winbase,
+                     uint32_t o0, uint32_t nthreads, const uint32_t* pre, const uint32_t* totals_inv, uint32_t* out)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < nthreads)
+        pair_backward_body<F>(cfg, points, sorted, offsets, counts, counts1, off1, winbase, o0, nthreads, pre,
+                              totals_inv, out, tid);
+}
+
+template<class F>
+__global__ void __launch_bounds__(ACC_THREADS, (F::N > 12 ? 2 : SPPARK_B200_ACC_MIN_BLOCKS))
+accumulate_direct_kernel(const Config cfg, const uint32_t* sums, const uint32_t* offsets, const uint32_t* counts,
+                         uint32_t* buckets, uint32_t* task_counter, const uint32_t* counts1, const uint32_t* off1,
+                         const uint32_t* winbase)
+{
+    accumulate_body<F, true>(cfg, sums, nullptr, offsets, counts, buckets, task_counter, counts1, off1, winbase);
 }
 
 template<class F>
@@ -217,6 +315,11 @@ public:
         uint32_t *counts, *offsets, *cursor, *ctrl, *heavy_list, *chunk_map, *partials, *sorted, *buckets;
         uint32_t *R[2], *S[2];
         uint32_t slices_done;
+        // batched-affine pre-reduction (msm_pair.cuh), off unless SPPARK_B200_MSM_PAIR=1
+        bool pair;
+        size_t pair_bound;          // most pair sums one slice can produce
+        uint32_t pair_threads;      // threads per forward/backward launch (PAIR_K outputs each)
+        uint32_t *counts1, *off1, *wintotal, *winbase, *sums, *pre, *totals;
     };
 
     // total_points fixes the window width; slice_cap is the most points one slice() call may carry
@@ -244,12 +347,28 @@ public:
         const size_t o_buckets = take(j.nslots * BW * 4);
         const size_t o_r0 = take((size_t)j.items1 * BW * 4), o_s0 = take((size_t)j.items1 * BW * 4);
         const size_t o_r1 = take((size_t)j.items1 * BW * 4 / 2 + 4096), o_s1 = take((size_t)j.items1 * BW * 4 / 2 + 4096);
+        // experimental, measured once in round 1: halves the bucket lists with
+        // batched affine pair sums before the XYZZ accumulation
+        const char* pair_env = getenv("SPPARK_B200_MSM_PAIR");
+        j.pair = pair_env && atoi(pair_env) != 0 && entries + j.nslots < (1ull << 31);
+        j.pair_bound = (entries + std::min<size_t>(entries, j.nslots) + 1) / 2;
+        j.pair_threads = (uint32_t)std::min<size_t>((j.pair_bound + PAIR_K - 1) / PAIR_K, (size_t)1 << 21);
+        size_t o_c1 = 0, o_o1 = 0, o_wt = 0, o_wb = 0, o_sums = 0, o_pre = 0, o_tot = 0;
+        if (j.pair) {
+            o_c1 = take(j.nslots * 4); o_o1 = take(j.nslots * 4);
+            o_wt = take((j.cfg.nwins + 1) * 4); o_wb = take((j.cfg.nwins + 1) * 4);
+            o_sums = take(j.pair_bound * 2 * F::N * 4);
+            o_pre = take((size_t)j.pair_threads * PAIR_K * F::N * 4);
+            o_tot = take((size_t)j.pair_threads * F::N * 4);
+        }
         CUDA_OK(cudaMallocAsync((void**)&j.blob, off, stream));
         auto U32 = [&](size_t o) { return reinterpret_cast<uint32_t*>(j.blob + o); };
         j.counts = U32(o_counts); j.offsets = U32(o_offsets); j.cursor = U32(o_cursor);
         j.ctrl = U32(o_ctrl); j.heavy_list = U32(o_heavy); j.chunk_map = U32(o_cmap);
         j.partials = U32(o_partials); j.sorted = U32(o_sorted); j.buckets = U32(o_buckets);
         j.R[0] = U32(o_r0); j.S[0] = U32(o_s0); j.R[1] = U32(o_r1); j.S[1] = U32(o_s1);
+        j.counts1 = U32(o_c1); j.off1 = U32(o_o1); j.wintotal = U32(o_wt); j.winbase = U32(o_wb);
+        j.sums = U32(o_sums); j.pre = U32(o_pre); j.totals = U32(o_tot);
         g_profile.reset();
         return j;
     }
@@ -295,8 +414,32 @@ public:
         if (occ < 1) occ = 1;
         size_t want = (j.nslots + ACC_THREADS - 1) / ACC_THREADS;
         uint32_t acc_blocks = (uint32_t)std::min<size_t>(want, (size_t)sms * occ);
-        accumulate_kernel<F><<<acc_blocks, ACC_THREADS, 0, stream>>>(cfg, d_points, j.sorted, j.offsets, j.counts,
-                                                                    j.buckets, j.ctrl);
+        if (j.pair) {
+            const uint32_t nslots = (uint32_t)j.nslots;
+            pair_counts_kernel<<<sms * 8, 256, 0, stream>>>(cfg, j.counts, j.counts1, nslots);
+            pair_scan_kernel<<<cfg.nwins, 1024, 0, stream>>>(cfg, j.counts1, j.off1, j.wintotal);
+            pair_winbase_kernel<<<1, 32, 0, stream>>>(cfg, j.wintotal, j.winbase);
+            // the host does not know how many pair sums this slice has (winbase[nwins], on the
+            // device): launches cover the bound, threads past the real total return at once
+            const size_t bound = ((size_t)cfg.nwins * n + std::min<size_t>((size_t)cfg.nwins * n, j.nslots) + 1) / 2;
+            const size_t per_launch = (size_t)j.pair_threads * PAIR_K;
+            for (size_t o0 = 0; o0 < bound; o0 += per_launch) {
+                const uint32_t nth = (uint32_t)std::min<size_t>(j.pair_threads, (bound - o0 + PAIR_K - 1) / PAIR_K);
+                pair_forward_kernel<F><<<(nth + 127) / 128, 128, 0, stream>>>(
+                    cfg, d_points, j.sorted, j.offsets, j.counts, j.counts1, j.off1, j.winbase, (uint32_t)o0, nth, j.pre, j.totals);
+                pair_invert_kernel<F><<<((nth + PAIR_M - 1) / PAIR_M + 127) / 128, 128, 0, stream>>>(j.totals, nth);
+                pair_backward_kernel<F><<<(nth + 127) / 128, 128, 0, stream>>>(
+                    cfg, d_points, j.sorted, j.offsets, j.counts, j.counts1, j.off1, j.winbase, (uint32_t)o0, nth, j.pre, j.totals, j.sums);
+                COUNT_LAUNCH(); COUNT_LAUNCH(); COUNT_LAUNCH();
+            }
+            CUDA_OK(cudaGetLastError());
+            g_profile.mark("accumulate_sums", stream);
+            accumulate_direct_kernel<F><<<acc_blocks, ACC_THREADS, 0, stream>>>(cfg, j.sums, j.offsets, j.counts, j.buckets,
+                                                                               j.ctrl, j.counts1, j.off1, j.winbase);
+        } else {
+            accumulate_kernel<F><<<acc_blocks, ACC_THREADS, 0, stream>>>(cfg, d_points, j.sorted, j.offsets, j.counts,
+                                                                        j.buckets, j.ctrl);
+        }
         COUNT_LAUNCH();
         g_profile.mark("heavy", stream);
         heavy_chunks_kernel<F><<<sms * 4, HEAVY_THREADS, HEAVY_THREADS * BW * 4, stream>>>(

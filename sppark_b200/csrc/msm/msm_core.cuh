@@ -157,15 +157,19 @@ HD ec::xyzz_t<F> load_bucket(const uint32_t* buckets, size_t slot)
 // Every lane repeatedly claims the next (window,bucket) from `task_counter` and folds that
 // bucket's points.  Empty buckets are written as infinity, heavy ones are skipped (the
 // cooperative kernel owns them).
-template<class F>
+// Direct mode (DIRECT = true; msm_pair.cuh): the lists were pre-reduced to pair sums stored
+// consecutively in `points`, slot t owning counts1[t] of them from winbase[w] + off1[t] on; `sorted`
+// is not read.
+template<class F, bool DIRECT = false>
 HD void accumulate_body(const Config& cfg, const uint32_t* points, const uint32_t* sorted,
                         const uint32_t* offsets, const uint32_t* counts, uint32_t* buckets,
-                        uint32_t* task_counter)
+                        uint32_t* task_counter, const uint32_t* counts1 = nullptr,
+                        const uint32_t* off1 = nullptr, const uint32_t* winbase = nullptr)
 {
     const uint32_t total = cfg.nwins << cfg.lg_nb;
     ec::xyzz_t<F> acc;
     const uint32_t* run = nullptr;
-    uint32_t t = 0, k = 0, cnt = 0;
+    uint32_t t = 0, k = 0, cnt = 0, direct_base = 0;
     bool open = false, live = true;
     // ONE loop, one mixed add per trip, the whole warp in lock step: a lane that finishes its
     // bucket swaps in the next one on the spot and re-joins the warp for the very next add.
@@ -191,8 +195,12 @@ HD void accumulate_body(const Config& cfg, const uint32_t* points, const uint32_
                 if (cnt > cfg.heavy) continue;
                 break;
             }
+            if (DIRECT && live) {
+                cnt = counts1[t];
+                direct_base = winbase[t >> cfg.lg_nb] + off1[t];
+            }
             if (live) {
-                run = sorted + (size_t)(t >> cfg.lg_nb) * cfg.npoints + offsets[t];
+                if (!DIRECT) run = sorted + (size_t)(t >> cfg.lg_nb) * cfg.npoints + offsets[t];
                 if (cfg.merge) acc = load_bucket<F>(buckets, t);
                 else acc.set_inf();
                 k = 0;
@@ -204,7 +212,7 @@ HD void accumulate_body(const Config& cfg, const uint32_t* points, const uint32_
 #else
         if (!live) return;
 #endif
-        if (live) acc.madd(load_point<F>(points, run[k++]));
+        if (live) acc.madd(load_point<F>(points, DIRECT ? direct_base + k++ : run[k++]));
         // (an explicit prefetch.global.L2 of the next point was measured: no gain at 2^24,
         //  6 % slower at 2^26 -- the 12 resident warps per SM already cover the gather latency)
     }

@@ -8,12 +8,13 @@
 #include <vector>
 #include "../../sppark_b200/csrc/ff/fields.cuh"
 #include "../../sppark_b200/csrc/msm/msm_core.cuh"
+#include "../../sppark_b200/csrc/msm/msm_pair.cuh"
 
 using namespace msm;
 
 template<class F>
 static void emu_msm(uint32_t* out, const uint32_t* points_all, size_t npoints_all, const uint32_t* scalars_all,
-                    uint32_t wbits, uint32_t heavy, uint32_t nslices = 1)
+                    uint32_t wbits, uint32_t heavy, uint32_t nslices = 1, bool pair = false)
 {
     size_t npoints = npoints_all;
     constexpr uint32_t BW = 4 * F::N, JW = 3 * F::N;
@@ -47,6 +48,37 @@ static void emu_msm(uint32_t* out, const uint32_t* points_all, size_t npoints_al
     }
     for (uint32_t i = 0; i < npoints; i++) scatter_body(cfg, scalars, cursor.data(), sorted.data(), i, 0, cfg.nwins);
     uint32_t task_counter = 0;
+    if (pair) {
+        // msm_pair.cuh: lists -> pair sums (same launch sequence as msm_t::slice with pairing on)
+        std::vector<uint32_t> counts1(nslots + 1, 1), off1(nslots), winbase(cfg.nwins + 1);   // sentinel slot stops pair_advance
+        for (uint32_t t = 0; t < nslots; t++) pair_counts_body(cfg, counts.data(), counts1.data(), t);
+        uint32_t total1 = 0;
+        for (uint32_t w = 0; w < cfg.nwins; w++) {
+            winbase[w] = total1;
+            uint32_t run = 0;
+            for (uint32_t b = 0; b < (1u << cfg.lg_nb); b++) {
+                off1[((size_t)w << cfg.lg_nb) + b] = run;
+                run += counts1[((size_t)w << cfg.lg_nb) + b];
+            }
+            total1 += run;
+        }
+        winbase[cfg.nwins] = total1;
+        std::vector<uint32_t> sums((size_t)std::max(total1, 1u) * 2 * F::N);
+        const uint32_t chunk = 5 * PAIR_K;                          // several launches, a ragged last one
+        for (uint32_t o0 = 0; o0 < total1; o0 += chunk) {
+            const uint32_t nth = chunk / PAIR_K;
+            std::vector<uint32_t> pre((size_t)PAIR_K * nth * F::N), totals((size_t)nth * F::N);
+            for (uint32_t tid = 0; tid < nth; tid++)
+                pair_forward_body<F>(cfg, points, sorted.data(), offsets.data(), counts.data(), counts1.data(), off1.data(),
+                                     winbase.data(), o0, nth, pre.data(), totals.data(), tid);
+            for (uint32_t tid = 0; tid * PAIR_M < nth; tid++) pair_invert_body<F>(totals.data(), nth, tid);
+            for (uint32_t tid = 0; tid < nth; tid++)
+                pair_backward_body<F>(cfg, points, sorted.data(), offsets.data(), counts.data(), counts1.data(), off1.data(),
+                                      winbase.data(), o0, nth, pre.data(), totals.data(), sums.data(), tid);
+        }
+        accumulate_body<F, true>(cfg, sums.data(), sorted.data(), offsets.data(), counts.data(), buckets.data(), &task_counter,
+                           counts1.data(), off1.data(), winbase.data());
+    } else
     accumulate_body<F>(cfg, points, sorted.data(), offsets.data(), counts.data(), buckets.data(), &task_counter);
     const uint32_t HT = 8;                                        // heavy_kernel with 8 "threads"
     for (uint32_t t : heavy_list) {
@@ -91,6 +123,12 @@ extern "C" void emu_msm_bls12_381(uint32_t* out, const uint32_t* points, size_t 
 extern "C" void emu_msm_bls12_381_sliced(uint32_t* out, const uint32_t* points, size_t n, const uint32_t* scalars,
                                          uint32_t wbits, uint32_t heavy, uint32_t nslices)
 {   emu_msm<ff::bls12_381_fp_t>(out, points, n, scalars, wbits, heavy, nslices);   }
+extern "C" void emu_msm_bls12_381_pair(uint32_t* out, const uint32_t* points, size_t n, const uint32_t* scalars,
+                                       uint32_t wbits, uint32_t heavy, uint32_t nslices)
+{   emu_msm<ff::bls12_381_fp_t>(out, points, n, scalars, wbits, heavy, nslices, true);   }
+extern "C" void emu_msm_pallas_pair(uint32_t* out, const uint32_t* points, size_t n, const uint32_t* scalars,
+                                    uint32_t wbits, uint32_t heavy, uint32_t nslices)
+{   emu_msm<ff::pallas_fp_t>(out, points, n, scalars, wbits, heavy, nslices, true);   }
 extern "C" void emu_msm_pallas(uint32_t* out, const uint32_t* points, size_t n, const uint32_t* scalars,
                                uint32_t wbits, uint32_t heavy)
 {   emu_msm<ff::pallas_fp_t>(out, points, n, scalars, wbits, heavy);   }

@@ -44,6 +44,8 @@ def msm_emu():
     l.emu_msm_bls12_381_sliced.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint, C.c_uint, C.c_uint]
     l.emu_msm_pallas.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint, C.c_uint]
     l.emu_fp_op.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.emu_msm_bls12_381_pair.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint, C.c_uint, C.c_uint]
+    l.emu_msm_pallas_pair.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint, C.c_uint, C.c_uint]
     return l
 
 
@@ -230,6 +232,61 @@ def test_msm_sliced_bucket_merging(oracle, msm_emu, n, wbits, heavy, nslices):
     msm_emu.emu_msm_bls12_381_sliced(out.ctypes.data, pts.ctypes.data, n, sc.ctypes.data, wbits, heavy, nslices)
     want = oracle.msm("bls12_381", pts, sc, "pippenger", ncpus=4)
     assert np.array_equal(oracle.jac_to_affine("bls12_381", out), oracle.jac_to_affine("bls12_381", want))
+
+
+def _run_pair(oracle, emu, pts, sc, wbits, heavy, nslices=1, curve="bls12_381"):
+    nl = 6 if curve == "bls12_381" else 4
+    out = np.zeros(3 * nl, dtype=np.uint64)
+    fn = emu.emu_msm_bls12_381_pair if curve == "bls12_381" else emu.emu_msm_pallas_pair
+    fn(out.ctypes.data, pts.ctypes.data, pts.shape[0], sc.ctypes.data, wbits, heavy, nslices)
+    want = oracle.msm(curve, pts, sc, "pippenger", ncpus=4)
+    return np.array_equal(oracle.jac_to_affine(curve, out), oracle.jac_to_affine(curve, want))
+
+
+@pytest.mark.parametrize("n,wbits,heavy,nslices", [(1, 0, 0, 1), (2, 0, 0, 1), (3, 4, 0, 1), (33, 0, 0, 1), (300, 0, 0, 1),
+                                                   (300, 5, 0, 1), (300, 9, 3, 1), (800, 7, 4, 1), (500, 4, 2, 1),
+                                                   (64, 13, 0, 1), (501, 5, 3, 4), (300, 6, 0, 3), (1000, 3, 0, 2)])
+def test_msm_batched_affine_prereduction(oracle, msm_emu, n, wbits, heavy, nslices):
+    """msm_pair.cuh: every bucket list halved by batched affine pair sums (Montgomery's trick over
+    16 pairs per thread and 32 thread totals per inversion), then the XYZZ accumulate in direct
+    mode -- chord, tangent (equal points), cancellation (P, -P), infinity inputs, odd tails, heavy
+    buckets left to the cooperative path, several slices, ragged last launch."""
+    rnd = random.Random(n * 7 + wbits + nslices)
+    pts = oracle.gen_points("bls12_381", 32)[np.arange(n) % 32].copy()
+    if n > 3:
+        pts[3] = 0
+    assert _run_pair(oracle, msm_emu, pts, _scalars([rnd.randrange(R_BLS) for _ in range(n)]), wbits, heavy, nslices)
+
+
+@pytest.mark.parametrize("val", [0, 1, R_BLS - 1, (1 << 254) + 12345, 0x8000000080000000800000008000])
+def test_msm_batched_affine_adversarial(oracle, msm_emu, val):
+    """all scalars equal: every pair of a bucket is (P_a, P_b) with many P_a == P_b (tangent) and a
+    planted (P, -P) (cancellation) -- the cases where the denominator x2 - x1 vanishes"""
+    n = 150
+    pts = oracle.gen_points("bls12_381", 4)[np.arange(n) % 4].copy()
+    p = oracle.ff_consts("bls12_381_fp")["p"]
+    y1 = sum(int(v) << (64 * i) for i, v in enumerate(pts[1][6:]))
+    pts[5][6:] = [((p - y1) >> (64 * i)) & (2**64 - 1) for i in range(6)]     # points 4,5 -> (P0, -P1); 1 vs 5 cancels when paired
+    pts[8:12] = pts[8]                                                         # runs of equal points: tangent pairs
+    pts[20] = 0
+    pts[21] = 0                                                                # an (inf, inf) pair
+    assert _run_pair(oracle, msm_emu, pts, _scalars([val] * n), 6, 1000)
+    assert _run_pair(oracle, msm_emu, pts, _scalars([val] * n), 5, 8)          # the same buckets, now heavy
+    same = np.tile(pts[7], (40, 1))
+    assert _run_pair(oracle, msm_emu, same, _scalars([val] * 40), 6, 1000)     # one point 40 times: only tangents
+    pm = same.copy()
+    pm[1::2, 6:] = [((p - sum(int(v) << (64 * i) for i, v in enumerate(same[0][6:]))) >> (64 * i)) & (2**64 - 1) for i in range(6)]
+    assert _run_pair(oracle, msm_emu, pm, _scalars([val] * 40), 6, 1000)       # (P, -P) pairs only
+
+
+def test_msm_batched_affine_pallas(oracle, msm_emu):
+    rnd = random.Random(4)
+    r = oracle.ff_consts("vesta_fp")["p"]
+    n = 400
+    pts = oracle.gen_points("pallas", 16)[np.arange(n) % 16].copy()
+    sc = _scalars([rnd.randrange(r) for _ in range(n)])
+    sc[: n // 2] = sc[0]
+    assert _run_pair(oracle, msm_emu, pts, sc, 6, 50, 2, curve="pallas")
 
 
 def test_portable_field_branch(oracle, msm_emu):

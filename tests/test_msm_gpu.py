@@ -237,6 +237,42 @@ def test_preloaded_points_context(oracle, curve, cid, fr):
         ctx.close()
 
 
+def test_batched_affine_prereduction(oracle, monkeypatch):
+    """SPPARK_B200_MSM_PAIR=1 (experimental, off by default; msm_pair.cuh): bucket lists halved by
+    batched affine pair sums before the XYZZ accumulation.  Same group element as the oracle on
+    random, replicated (tangent pairs), cancelling, heavy and sliced inputs."""
+    from sppark_b200 import msm
+    monkeypatch.setenv("SPPARK_B200_MSM_PAIR", "1")
+    base = oracle.gen_points("bls12_381", 512)
+    for n, seed in ((1, 1), (2, 2), (193, 3), (5000, 4), (1 << 16, 5)):
+        pts = base[np.arange(n) % 512].copy()
+        if n > 3:
+            pts[3] = 0
+        sc = _scalars(n, seed)
+        assert _same_point(oracle, "bls12_381", msm.multi_scalar_mult(pts, sc), oracle.msm("bls12_381", pts, sc, "pippenger", ncpus=8)), n
+    n = 3000
+    sc = _scalars(n, 6)
+    same = np.tile(base[7], (n, 1))                                   # one point, one scalar: tangents all the way
+    s1 = np.tile(sc[0], (n, 1))
+    assert _same_point(oracle, "bls12_381", msm.multi_scalar_mult(same, s1), oracle.msm("bls12_381", same, s1, "pippenger", ncpus=8))
+    p = oracle.ff_consts("bls12_381_fp")["p"]
+    pm = same.copy()
+    pm[1::2, 6:] = _limbs(p - _int(same[0][6:]), 6)                  # (P, -P) pairs: everything cancels
+    got = msm.multi_scalar_mult(pm, s1)
+    assert not got[12:].any()
+    mix = base[np.arange(n) % 16].copy()                              # few distinct points, few distinct scalars
+    s2 = sc[np.arange(n) % 5].copy()
+    assert _same_point(oracle, "bls12_381", msm.multi_scalar_mult(mix, s2), oracle.msm("bls12_381", mix, s2, "pippenger", ncpus=8))
+    monkeypatch.setenv("SPPARK_B200_MSM_SLICES", "3")
+    pts = base[np.arange(20000) % 512].copy()
+    sc = _scalars(20000, 8)
+    assert _same_point(oracle, "bls12_381", msm.multi_scalar_mult(pts, sc), oracle.msm("bls12_381", pts, sc, "pippenger", ncpus=8))
+    monkeypatch.delenv("SPPARK_B200_MSM_SLICES")
+    pal = oracle.gen_points("pallas", 64)[np.arange(4096) % 64].copy()
+    scp = _scalars(4096, 9, oracle.ff_consts("vesta_fp")["p"])
+    assert _same_point(oracle, "pallas", msm.msm(1, pal, scp), oracle.msm("pallas", pal, scp, "pippenger", ncpus=8))
+
+
 def test_matches_reference_golden(oracle):
     """Same group element as the reference's CUDA mult_pippenger (recorded on a B200) and as its
     CPU msm/pippenger.hpp, on the committed inputs."""
