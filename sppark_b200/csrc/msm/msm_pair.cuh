@@ -24,7 +24,7 @@
 namespace msm {
 
 constexpr uint32_t PAIR_K = 16;          // outputs per thread
-constexpr uint32_t PAIR_M = 32;          // thread totals per inversion
+constexpr uint32_t PAIR_M = 64;          // thread totals per inversion (3 KB of local memory per thread)
 
 struct PairCursor {                      // position of an output in the bucket structure
     uint32_t t, i;                       // slot, pair index inside it
@@ -84,6 +84,46 @@ HD PairTerm<F> pair_term(const Config& cfg, const uint32_t* points, const uint32
     return r;
 }
 
+// one coordinate (X: which = 0, Y: which = 1, sign applied) of the point an entry names
+template<class F>
+HD F load_coord(const uint32_t* points, uint32_t entry, int which)
+{
+    const uint32_t* p = points + (size_t)(entry & 0x7fffffffu) * 2 * F::N + which * F::N;
+    F v;
+#if defined(__CUDA_ARCH__)
+    static_assert(F::N % 4 == 0, "a coordinate must be a whole number of 16-byte words");
+#pragma unroll
+    for (int k = 0; k < F::N / 4; k++) {
+        uint4 q = __ldg(reinterpret_cast<const uint4*>(p) + k);
+        v.l[4 * k] = q.x; v.l[4 * k + 1] = q.y; v.l[4 * k + 2] = q.z; v.l[4 * k + 3] = q.w;
+    }
+#else
+    for (int k = 0; k < F::N; k++) v.l[k] = p[k];
+#endif
+    if (which && (entry >> 31)) v = v.neg();
+    return v;
+}
+
+// the denominator alone, from the X coordinates (half the gather traffic of pair_term); Y is
+// fetched only for the rare x == 0 and x1 == x2 cases.  Must agree with pair_term bit for bit.
+template<class F>
+HD F pair_denominator(const Config& cfg, const uint32_t* points, const uint32_t* sorted,
+                      const uint32_t* offsets, const uint32_t* counts, PairCursor c)
+{
+    const uint32_t* run = sorted + (size_t)(c.t >> cfg.lg_nb) * cfg.npoints + offsets[c.t];
+    if (2 * c.i + 1 >= counts[c.t]) return F::one();
+    const uint32_t e1 = run[2 * c.i], e2 = run[2 * c.i + 1];
+    const F x1 = load_coord<F>(points, e1, 0), x2 = load_coord<F>(points, e2, 0);
+    if (x2.is_zero() && load_coord<F>(points, e2, 1).is_zero()) return F::one();
+    if (x1.is_zero() && load_coord<F>(points, e1, 1).is_zero()) return F::one();
+    if (x1 == x2) {
+        const F y1 = load_coord<F>(points, e1, 1), y2 = load_coord<F>(points, e2, 1);
+        if (y1 == y2 && !y1.is_zero()) return y1 + y1;
+        return F::one();
+    }
+    return x2 - x1;
+}
+
 template<class F> HD void pair_store_f(uint32_t* dst, const F& v)
 {
 #pragma unroll
@@ -119,8 +159,7 @@ HD void pair_forward_body(const Config& cfg, const uint32_t* points, const uint3
     if (first < total) {
         PairCursor c = pair_locate(cfg, off1, winbase, first);
         for (uint32_t j = 0; j < PAIR_K && first + j < total; j++) {
-            PairTerm<F> term = pair_term<F>(cfg, points, sorted, offsets, counts, c);
-            acc = F::mul_shared(acc, term.d);
+            acc = F::mul_shared(acc, pair_denominator<F>(cfg, points, sorted, offsets, counts, c));
             pair_store_f<F>(pre + ((size_t)j * nthreads + tid) * F::N, acc);
             if (first + j + 1 < total) pair_advance(counts1, c);
         }
