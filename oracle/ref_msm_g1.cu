@@ -16,21 +16,25 @@
 #else
 # error "FEATURE_BN254 or FEATURE_BLS12_377"
 #endif
-
 #include <ec/jacobian_t.hpp>
 #include <ec/xyzz_t.hpp>
 
-typedef jacobian_t<fp_t> point_t;
-typedef xyzz_t<fp_t> bucket_t;
-typedef bucket_t::affine_inf_t affine_t;
-typedef fr_t scalar_t;
+/* msm/pippenger.cuh explicitly instantiates its kernels for these four global names */
+using bucket_t = xyzz_t<fp_t>;
+using point_t = jacobian_t<fp_t>;
+using affine_t = bucket_t::affine_inf_t;      /* arkworks rows: x, y, infinity flag */
+using scalar_t = fr_t;
 
 #include <msm/pippenger.cuh>
 
 #ifndef __CUDA_ARCH__
-extern "C" RustError::by_value mult_pippenger_inf(point_t* out, const affine_t points[], size_t npoints,
-                                                  const scalar_t scalars[], size_t ffi_affine_sz)
+/* same name and signature as the reference's entry point, so the golden generator and the
+ * probes load either library the same way; scalars are plain integers (mont = false) */
+extern "C" RustError::by_value mult_pippenger_inf(point_t* sum, const affine_t* rows, size_t n,
+                                                  const scalar_t* k, size_t row_bytes)
 {
-    return mult_pippenger<bucket_t>(out, points, npoints, scalars, false, ffi_affine_sz);
+    const bool scalars_in_montgomery_form = false;
+    RustError status = mult_pippenger<bucket_t>(sum, rows, n, k, scalars_in_montgomery_form, row_bytes);
+    return status;
 }
 #endif

@@ -14,27 +14,28 @@
  * The packed affine_t has no such field, so this instantiation is consistent and pins G2.
  */
 #include <cuda.h>
-
 #include <ff/bls12-381-fp2.hpp>
-
 #include <ec/jacobian_t.hpp>
 #include <ec/xyzz_t.hpp>
 
-typedef jacobian_t<fp_t> point_t;
-typedef xyzz_t<fp_t> bucket_t;
-typedef bucket_t::affine_t affine_t;
-typedef fr_t scalar_t;
+/* msm/pippenger.cuh explicitly instantiates its G1 kernels for these four global names */
+using bucket_t = xyzz_t<fp_t>;
+using point_t = jacobian_t<fp_t>;
+using affine_t = bucket_t::affine_t;
+using scalar_t = fr_t;
 
 #include <msm/pippenger.cuh>
 
-typedef jacobian_t<fp2_t> g2_point_t;
-typedef xyzz_t<fp2_t> g2_bucket_t;
-typedef g2_bucket_t::affine_t g2_affine_t;
+using g2_bucket_t = xyzz_t<fp2_t>;
+using g2_point_t = jacobian_t<fp2_t>;
+using g2_affine_t = g2_bucket_t::affine_t;    /* packed: x, y in Fp2, infinity = all zero */
 
 /* not guarded by __CUDA_ARCH__: the device pass must see the call to instantiate the fp2 kernels
  * (the reference's explicit instantiations, msm/pippenger.cuh:299-316, cover bucket_t only) */
-extern "C" RustError::by_value ref_mult_pippenger_fp2(g2_point_t* out, const g2_affine_t points[],
-                                            size_t npoints, const scalar_t scalars[])
+extern "C" RustError::by_value ref_mult_pippenger_fp2(g2_point_t* sum, const g2_affine_t* rows, size_t n,
+                                                      const scalar_t* k)
 {
-    return mult_pippenger<g2_bucket_t>(out, points, npoints, scalars, false);
+    const bool scalars_in_montgomery_form = false;
+    RustError status = mult_pippenger<g2_bucket_t>(sum, rows, n, k, scalars_in_montgomery_form);
+    return status;
 }
