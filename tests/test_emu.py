@@ -299,3 +299,63 @@ def test_portable_field_branch(oracle, msm_emu):
         for op, exp in ((0, a * b * pow(R, -1, p) % p), (1, (a + b) % p), (2, (a - b) % p)):
             msm_emu.emu_fp_op(op, r.ctypes.data, A.ctypes.data, B.ctypes.data)
             assert oracle.limbs_to_int(r) == exp
+
+
+def test_ntt_planner_random_splits(oracle, ntt_emu, monkeypatch):
+    """Property test of the digit planner + pass kernel (CPU single-stepper): random sizes, digit
+    splits, orders, directions and tile sizes must all give the oracle's transform."""
+    rnd = random.Random(2024)
+    for _ in range(60):
+        lg = rnd.randint(2, 11)
+        digits, left = [], lg
+        while left:
+            d = rnd.randint(1, min(left, 6))
+            digits.append(d)
+            left -= d
+        monkeypatch.setenv("SPPARK_B200_NTT_SPLIT", ",".join(map(str, digits)))
+        order, inv, lg_tile = rnd.randrange(5), rnd.randrange(2), rnd.choice([5, 7, 9, 14])
+        x = np.array([rnd.randrange(2**64 - 2**32 + 1) for _ in range(1 << lg)], dtype=np.uint64)
+        y = x.copy()
+        ntt_emu.emu_ntt_gl64(y.ctypes.data, lg, order, inv, lg_tile)
+        assert np.array_equal(y, oracle.ntt_gl64(x, order, bool(inv))), (lg, digits, order, inv, lg_tile)
+
+
+def test_ntt_slab_random_shapes(oracle, ntt_emu, monkeypatch):
+    """Same for the slab-sharded transform: random digit splits (one to four digits after the
+    first), rank counts and tile sizes, staging route and fused-exchange route."""
+    from sppark_b200 import parallel
+    rnd = random.Random(77)
+    done = 0
+    while done < 25:
+        lg = rnd.randint(4, 11)
+        lg_g = rnd.randint(0, 3)
+        digits, left = [], lg
+        while left:
+            d = rnd.randint(1, min(left, 5))
+            digits.append(d)
+            left -= d
+        if len(digits) < 2 or digits[0] < lg_g or lg - digits[0] < lg_g:
+            continue
+        done += 1
+        monkeypatch.setenv("SPPARK_B200_NTT_SPLIT", ",".join(map(str, digits)))
+        s1, G, lg_tile = digits[0], 1 << lg_g, rnd.choice([5, 8, 14])
+        x = np.array([rnd.randrange(2**64 - 2**32 + 1) for _ in range(1 << lg)], dtype=np.uint64)
+        inv = rnd.randrange(2)
+        recv = [np.zeros((1 << lg) // G, dtype=np.uint64) for _ in range(G)]
+        if rnd.randrange(2):                                            # fused exchange
+            ptrs = (C.c_void_p * G)(*[r.ctypes.data for r in recv])
+            for r in range(G):
+                loc = parallel.scatter_columns(x, lg, lg_g, r, s1=s1).reshape(-1).copy()
+                assert ntt_emu.emu_ntt_slab_p2p_gl64(loc.ctypes.data, ptrs, lg, lg_g, r, inv, lg_tile) == 0
+        else:                                                           # staging + all-to-all
+            stag = []
+            for r in range(G):
+                loc = parallel.scatter_columns(x, lg, lg_g, r, s1=s1).reshape(-1).copy()
+                st = np.zeros_like(loc)
+                assert ntt_emu.emu_ntt_slab_gl64(1, loc.ctypes.data, st.ctypes.data, lg, lg_g, r, inv, lg_tile) == 0
+                stag.append(st.reshape(G, -1))
+            recv = [np.concatenate([stag[q][r] for q in range(G)]).copy() for r in range(G)]
+        for r in range(G):
+            scratch = np.zeros_like(recv[r])
+            assert ntt_emu.emu_ntt_slab_gl64(2, recv[r].ctypes.data, scratch.ctypes.data, lg, lg_g, r, inv, lg_tile) == 0
+        assert np.array_equal(parallel.gather_columns(recv, lg, lg_g, s1=s1), oracle.ntt_gl64(x, 0, bool(inv))), (lg, lg_g, digits, inv)
