@@ -359,3 +359,28 @@ def test_ntt_slab_random_shapes(oracle, ntt_emu, monkeypatch):
             scratch = np.zeros_like(recv[r])
             assert ntt_emu.emu_ntt_slab_gl64(2, recv[r].ctypes.data, scratch.ctypes.data, lg, lg_g, r, inv, lg_tile) == 0
         assert np.array_equal(parallel.gather_columns(recv, lg, lg_g, s1=s1), oracle.ntt_gl64(x, 0, bool(inv))), (lg, lg_g, digits, inv)
+
+
+def test_msm_random_configurations(oracle, msm_emu):
+    """Random window widths, heavy thresholds, slice counts, duplicate-heavy inputs; plain and
+    batched-affine accumulation must both give the oracle's point."""
+    rnd = random.Random(31337)
+    base = oracle.gen_points("bls12_381", 24)
+    for _ in range(24):
+        n = rnd.randint(1, 400)
+        wbits = rnd.choice([3, 4, 5, 7, 9, 12])
+        heavy = rnd.choice([0, 2, 5, 50, 1000])
+        nslices = rnd.choice([1, 1, 2, 5])
+        pts = base[[rnd.randrange(rnd.choice([2, 24])) for _ in range(n)]].copy()
+        if rnd.random() < 0.5:
+            pts[rnd.randrange(n)] = 0
+        vals = [rnd.randrange(R_BLS) for _ in range(n)]
+        if rnd.random() < 0.4:
+            vals = [vals[rnd.randrange(3)] for _ in range(n)]          # three distinct scalars: long buckets
+        sc = _scalars(vals)
+        want = oracle.jac_to_affine("bls12_381", oracle.msm("bls12_381", pts, sc, "pippenger", ncpus=4))
+        out = np.zeros(18, dtype=np.uint64)
+        msm_emu.emu_msm_bls12_381_sliced(out.ctypes.data, pts.ctypes.data, n, sc.ctypes.data, wbits, heavy, nslices)
+        assert np.array_equal(oracle.jac_to_affine("bls12_381", out), want), ("plain", n, wbits, heavy, nslices)
+        msm_emu.emu_msm_bls12_381_pair(out.ctypes.data, pts.ctypes.data, n, sc.ctypes.data, wbits, heavy, nslices)
+        assert np.array_equal(oracle.jac_to_affine("bls12_381", out), want), ("pair", n, wbits, heavy, nslices)
