@@ -175,6 +175,8 @@ RustError msm_preload(const void* points, size_t npoints, size_t stride, bool ha
         gpu.select();
         if (stride < PB + (has_flag ? 1 : 0))
             return rust_err(-(int)cudaErrorInvalidValue, "msm: affine stride too small");
+        if (npoints >= (1ull << 31))
+            return rust_err(-(int)cudaErrorInvalidValue, "msm: npoints must be < 2^31");
         const stream_t& copy = gpu[1];
         uint32_t* d_points = nullptr;
         CUDA_OK(cudaMalloc((void**)&d_points, npoints ? npoints * PB : 1));
