@@ -195,6 +195,10 @@ RustError sppark_b200_msm_combine(int curve, void *out_jacobian, const void *par
  * arithmetic; field 0 = BLS12-381 fp (48 B), 1 = BLS12-381 fr, 2 = Pallas fp, 3 = Vesta fp
  * (32 B each); op 0 mul (Montgomery), 1 add, 2 sub, 3 sqr.  Host arrays. */
 RustError sppark_b200_selftest_field(int field, int op, size_t n, void *r, const void *a, const void *b);
+/* same for the single-word NTT fields (SPPARK_FIELD_GL64: 8-byte words, SPPARK_FIELD_BB31: 4-byte
+ * Montgomery words): op 0 mul (Goldilocks: b is a canonical constant in Montgomery form, the result
+ * a*b*2^-64 mod p, see csrc/ff/gl64.cuh), 1 add, 2 sub (b canonical), 3 tight, 4 canon. */
+RustError sppark_b200_selftest_word_field(int field, int op, size_t n, void *r, const void *a, const void *b);
 
 /* introspection */
 size_t      sppark_b200_ngpus(void);               /* ngpus(), util/gpu_t.cuh:21 */

@@ -1,11 +1,18 @@
 // Goldilocks field  p = 2^64 - 2^32 + 1  (the reference's gl64_t, ff/gl64_t.cuh:39-298).
-// Memory format is the reference's: one canonical uint64_t (< p), not Montgomery.
+// Memory format of the DATA is the reference's: one canonical uint64_t (< p), not Montgomery.
 //
-// Internal representation here: any uint64_t ("loose", value mod p).  mul() and the
-// final canon() return canonical values; add()/sub() require their SECOND operand to be
-// canonical and accept a loose first operand -- exactly the shape of a radix-2 butterfly
-// (u loose, t = v*w canonical), which saves the conditional subtraction on every
-// add/sub.  2^64 = 2^32 - 1 =: EPS (mod p), 2^96 = -1 (mod p).
+// Representation used by the NTT kernels:
+//  * data values travel as "loose" 64-bit residues (any uint64_t, value mod p);
+//  * every CONSTANT the data is multiplied by (twiddles, coset powers, n^-1) is kept in
+//    Montgomery form c' = c * 2^64 mod p, canonical; mul(x, c') = x * c' * 2^-64 = x * c mod p,
+//    so products of data and constants are plain again and tables of constants are closed under
+//    mul/pow (one() = 2^64 mod p).  The Montgomery reduction for this prime needs no multiply
+//    (p^-1 = 1 + 2^32 mod 2^64) and, for a canonical second operand, returns a CANONICAL value
+//    for free: with V = a*b < 2^64 * p the exact quotient (V - t*p) / 2^64 lies in (-p, p).
+//  * add()/sub() take a loose first and a canonical second operand -- exactly the shape of a
+//    radix-2 DIT butterfly (u loose, t = v*w canonical) -- and return loose values; this saves
+//    the conditional subtraction on every add/sub.  tight() makes a loose value a legal second
+//    operand.  2^64 = 2^32 - 1 =: EPS (mod p), 2^96 = -1 (mod p).
 #pragma once
 #include "../util/hd.cuh"
 
@@ -14,14 +21,15 @@ struct gl64 {
     static constexpr uint64_t P = 0xffffffff00000001ULL;
     static constexpr uint64_t EPS = 0xffffffffULL;
     static constexpr int MAX_LG = 32;
-    static constexpr uint32_t NTT_MAX_LG_R = 12;   // largest sub-NTT per tile
+    static constexpr uint32_t NTT_MAX_LG_R = 12;   // largest sub-NTT per tile (block-tile kernel)
     static constexpr uint32_t NTT_MAX_THREADS = 1024;
     static constexpr uint32_t LG_EPT = 4;          // NTT: elements per thread per register step
     static constexpr int LG_BYTES = 3;
 
     static HD T canon(T a) { return a >= P ? a - P : a; }
+    static HD T tight(T a) { return canon(a); }             // loose -> legal second operand of add/sub
     static HD T load(T a) { return a; }     // memory -> register (accepts non-canonical input)
-    static HD T one() { return 1; }
+    static HD T one() { return EPS; }       // 2^64 mod p: the Montgomery form of 1
 
     // a loose, b canonical -> loose
     static HD T add(T a, T b)
@@ -56,58 +64,56 @@ struct gl64 {
         return a < b ? d - EPS : d;           // borrowed: -2^64 == -EPS; cannot borrow twice as b < p
 #endif
     }
-    static HD T reduce128(T lo, T hi)
+    // (hi:lo) * 2^-64 mod p, hi:lo < 2^64 * p  ->  canonical
+    static HD T mont_reduce(T lo, T hi)
     {
-        // lo + hi_lo*2^64 + hi_hi*2^96 == lo - hi_hi + hi_lo*EPS
-        T hh = hi >> 32, hl = hi & EPS;
-        T t = lo - hh;
-        if (lo < hh) t -= EPS;
-        T m = hl * EPS;                       // < 2^64
-        T r = t + m;
-        if (r < t) r += EPS;
-        return canon(r);
+        // t = lo * p^-1 mod 2^64 = lo + (lo << 32);  result = hi - ceil(t*p / 2^64) (+p if negative),
+        // written with wrapping arithmetic
+        T t = lo + (lo << 32);
+        T e = t < lo;
+        T b = t - (t >> 32) - e;
+        T r = hi - b;
+        return hi < b ? r - EPS : r;
     }
-    // loose x loose -> canonical
+    // loose x canonical (Montgomery-form constant) -> canonical, = a * b * 2^-64 mod p
     static HD T mul(T a, T b)
     {
 #if defined(__CUDA_ARCH__)
-        // 4 wide products (each mad.lo.cc/madc.hi.cc pair is one IMAD.WIDE.U32) -> r3:r2:r1:r0,
-        // then r0 + r1*2^32 + r2*EPS - r3, one conditional +-EPS per wrap, final canonical fix
-        uint32_t r0, r1;
-        asm("{ .reg .u32 a0, a1, b0, b1, r2, r3, t;\n\t"
-            ".reg .pred q;\n\t"
+        // 128-bit product (ptxas fuses the mad.lo.cc/madc.hi pairs into IMAD.WIDE.U32), then the
+        // multiplication-free Montgomery step above on 32-bit halves
+        uint32_t s0, s1;
+        asm("{ .reg .u32 a0, a1, b0, b1, r0, r1, r2, r3, e, m, x1, y0, y1;\n\t"
             "mov.b64 {a0, a1}, %2; mov.b64 {b0, b1}, %3;\n\t"
-            "mul.lo.u32 %0, a0, b0; mul.hi.u32 %1, a0, b0;\n\t"
-            "mul.lo.u32 r2, a1, b1; mul.hi.u32 r3, a1, b1;\n\t"
-            "mad.lo.cc.u32 %1, a0, b1, %1; madc.hi.cc.u32 r2, a0, b1, r2; addc.u32 r3, r3, 0;\n\t"
-            "mad.lo.cc.u32 %1, a1, b0, %1; madc.hi.cc.u32 r2, a1, b0, r2; addc.u32 r3, r3, 0;\n\t"
-            "sub.cc.u32 %0, %0, r3; subc.cc.u32 %1, %1, 0; subc.u32 t, 0, 0;\n\t"      // - r3*2^96
-            "sub.cc.u32 %0, %0, t; subc.u32 %1, %1, 0;\n\t"
-            "mad.lo.cc.u32 %0, r2, 0xffffffff, %0; madc.hi.cc.u32 %1, r2, 0xffffffff, %1; addc.u32 t, 0, 0;\n\t"
-            "neg.s32 t, t;\n\t"
-            "add.cc.u32 %0, %0, t; addc.u32 %1, %1, 0;\n\t"
-            "setp.eq.u32 q, %1, 0xffffffff;\n\t"
-            "@q setp.ne.u32 q, %0, 0;\n\t"
-            "@q sub.u32 %0, %0, 1;\n\t"
-            "@q mov.u32 %1, 0; }"
-            : "=r"(r0), "=r"(r1) : "l"(a), "l"(b));
-        return ((T)r1 << 32) | r0;
+            "mul.lo.u32 r0, a0, b0; mul.hi.u32 r1, a0, b0;\n\t"
+            "mad.lo.cc.u32 r1, a0, b1, r1; madc.hi.u32 r2, a0, b1, 0;\n\t"
+            "mad.lo.cc.u32 r1, a1, b0, r1; madc.hi.cc.u32 r2, a1, b0, r2; addc.u32 r3, 0, 0;\n\t"
+            "mad.lo.cc.u32 r2, a1, b1, r2; madc.hi.u32 r3, a1, b1, r3;\n\t"
+            "add.cc.u32 x1, r1, r0; addc.u32 e, 0, 0;\n\t"              // t = (x1:r0), carry e
+            "sub.cc.u32 y0, r0, x1; subc.u32 y1, x1, 0;\n\t"            // b = t - (t >> 32) - e
+            "sub.cc.u32 y0, y0, e;  subc.u32 y1, y1, 0;\n\t"
+            "sub.cc.u32 %0, r2, y0; subc.cc.u32 %1, r3, y1; subc.u32 m, 0, 0;\n\t"   // hi - b, m = 0 / EPS
+            "sub.cc.u32 %0, %0, m; subc.u32 %1, %1, 0; }"
+            : "=r"(s0), "=r"(s1) : "l"(a), "l"(b));
+        return ((T)s1 << 32) | s0;
 #else
         unsigned __int128 x = (unsigned __int128)a * b;
-        return reduce128((T)x, (T)(x >> 64));
+        return mont_reduce((T)x, (T)(x >> 64));
 #endif
     }
+    static HD T to_mont(T a) { return mul(canon(a), 0xfffffffe00000001ULL); }   // * 2^128 mod p
     static HD T pow(T b, uint64_t e)
     {
-        T r = 1;
+        T r = one();
         b = canon(b);
         for (; e; e >>= 1, b = mul(b, b))
             if (e & 1) r = mul(r, b);
         return r;
     }
     // parameters: ntt/parameters/goldilocks.h:84-160 (default, non-PLONKY2 branch):
-    // group_gen = 7, w_(2^32) = 7^((p-1)/2^32); values re-derived, pinned by tests/test_params_pin.py
-    static HD T group_gen() { return 7; }
-    static HD T root_of_unity_max() { return 0x185629dcda58878cULL; }   // order 2^32
+    // group_gen = 7, w_(2^32) = 7^((p-1)/2^32) = 0x185629dcda58878c; the constants below are these
+    // values times 2^64 mod p (tests/test_params_pin.py pins the plain values, tests/test_emu.py
+    // the Montgomery forms)
+    static HD T group_gen() { return 0x6fffffff9ULL; }
+    static HD T root_of_unity_max() { return 0xda58878b0d514e98ULL; }   // order 2^32
     static HD T inv(T a) { return pow(a, P - 2); }
 };

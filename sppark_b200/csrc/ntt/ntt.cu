@@ -24,14 +24,18 @@ static bool try_static(const Pass& d, const Tables<F>& tb, const typename F::T* 
         (d.in_rev != 0) != IREV || (d.out_rev != 0) != OREV || d.tw_mode != TW)
         return false;
     typedef KStat<R, W, IRF, ORF, IREV, OREV, TW> K;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(pass_kernel_static<F, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_done = true;
+    // function attributes are per device (context): one flag per CUDA device and instantiation
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    static bool attr_done[64];
+    if (!attr_done[dev & 63]) {
+        CUDA_OK(cudaFuncSetAttribute(pass_kernel_static<F, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done[dev & 63] = true;
     }
     // one CTA per SM (a tile fills the shared memory), each walking ntiles / grid tiles
-    static int sms = 0;
-    if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    static int sms_of[64];
+    if (!sms_of[dev & 63]) CUDA_OK(cudaDeviceGetAttribute(&sms_of[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+    const int sms = sms_of[dev & 63];
     uint32_t per_sm = smem <= 48 * 1024 ? 4 : smem <= 100 * 1024 ? 2 : 1;
     uint32_t grid = ntiles < (uint32_t)sms * per_sm ? ntiles : (uint32_t)sms * per_sm;
     pass_kernel_static<F, K><<<grid, tile_threads<F>(d), smem, stream>>>(d, tb, in, out, ntiles);
@@ -73,6 +77,7 @@ template<class F> bool launch_static(const Pass& d, const Tables<F>& tb, const t
 
 template bool launch_static<gl64>(const Pass&, const Tables<gl64>&, const uint64_t*, uint64_t*, uint32_t, size_t, cudaStream_t);
 template bool launch_static<bb31>(const Pass&, const Tables<bb31>&, const uint32_t*, uint32_t*, uint32_t, size_t, cudaStream_t);
+
 
 template bool launch_static<ff::bls12_381_fr_ntt>(const Pass&, const Tables<ff::bls12_381_fr_ntt>&, const ff::bls12_381_fr_ntt::T*, ff::bls12_381_fr_ntt::T*, uint32_t, size_t, cudaStream_t);
 template bool launch_static<ff::pallas_fr_ntt>(const Pass&, const Tables<ff::pallas_fr_ntt>&, const ff::pallas_fr_ntt::T*, ff::pallas_fr_ntt::T*, uint32_t, size_t, cudaStream_t);

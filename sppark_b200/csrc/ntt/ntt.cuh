@@ -6,6 +6,7 @@
 #pragma once
 #include "../util/gpu.cuh"
 #include "ntt_plan.hpp"
+#include "ntt_warp.cuh"
 
 namespace ntt {
 
@@ -63,6 +64,9 @@ pass_kernel_static(const Pass d, const Tables<F> tb, const typename F::T* in, ty
 // launcher table for the statically shaped passes; returns false if (d) has no static twin
 template<class F> bool launch_static(const Pass& d, const Tables<F>& tb, const typename F::T* in,
                                      typename F::T* out, uint32_t ntiles, size_t smem, cudaStream_t stream);
+// warp-autonomous pass (ntt_warp.cuh) for 4 <= d.lg_r <= 8, single-word fields; false otherwise
+template<class F> bool launch_warp(const gpu_t& gpu, const Pass& d, const Tables<F>& tb, const typename F::T* in,
+                                   typename F::T* out, uint32_t ncols, cudaStream_t stream);
 
 // ---- one-time table generation (role of NTTParameters, ntt/parameters.cuh:147-337) ----
 template<class F>
@@ -86,6 +90,22 @@ __global__ void gen_tables_kernel(typename F::T* dense, typename F::T* tlo, type
     T wn = F::pow(w_max, 1ull << (F::MAX_LG - lg_n));
     if (i < (1u << LG_TLO)) tlo[i] = F::pow(wn, i);
     if (i < n_hi) thi[i] = F::pow(wn, (uint64_t)i << LG_TLO);
+}
+
+// twist tables of the warp-autonomous passes (ntt_warp.cuh): for R = 5..8,
+// mid[mid_offset(R) + k0 * L + b] = w_(2^R)^(b * k0), L = 2^(R-4), k0 < 16, b < L
+template<class F>
+__global__ void gen_mid_kernel(typename F::T* mid, bool inverse)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= MID_WORDS) return;
+    uint32_t R = 5;
+    while (R < WARP_MAX_LG_R && i >= mid_offset(R + 1)) R++;
+    if ((uint32_t)F::MAX_LG < R) { mid[i] = F::one(); return; }
+    const uint32_t L = 1u << (R - 4), e = i - mid_offset(R), k0 = e / L, b = e % L;
+    typename F::T w_max = F::root_of_unity_max();
+    if (inverse) w_max = F::inv(w_max);
+    mid[i] = F::pow(F::pow(w_max, 1ull << (F::MAX_LG - R)), (uint64_t)b * k0);
 }
 
 // coset: x[i] *= g^nat(i)   (reference: LDE_distribute_powers, ntt/kernels.cu:131-153)
@@ -167,18 +187,27 @@ private:
         if (it != cache.end()) return *reinterpret_cast<Tables<F>*>(it->second);
 
         const uint32_t n_hi = lg_n > LG_TLO ? 1u << (lg_n - LG_TLO) : 1;
-        const size_t total = (1u << LG_DENSE) + (1u << LG_TLO) + n_hi;
+        const size_t total = (1u << LG_DENSE) + (1u << LG_TLO) + n_hi + MID_WORDS;
         T* blob;
         CUDA_OK(cudaMalloc(&blob, total * sizeof(T)));
-        T *dense = blob, *tlo = blob + (1u << LG_DENSE), *thi = tlo + (1u << LG_TLO);
+        T *dense = blob, *tlo = blob + (1u << LG_DENSE), *thi = tlo + (1u << LG_TLO), *mid = thi + n_hi;
         uint32_t nthr = n_hi > 4096 ? n_hi : 4096;
         gen_tables_kernel<F><<<(nthr + 255) / 256, 256, 0, stream>>>(dense, tlo, thi, n_hi, lg_n, inverse);
+        COUNT_LAUNCH();
+        gen_mid_kernel<F><<<(MID_WORDS + 255) / 256, 256, 0, stream>>>(mid, inverse);
         COUNT_LAUNCH();
         CUDA_OK(cudaGetLastError());
         CUDA_OK(cudaStreamSynchronize(stream));      // one-time: other streams may use it next
         T half = F::inv(F::add(F::one(), F::one())), ninv = F::one();
         for (uint32_t i = 0; i < lg_n; i++) ninv = F::mul(ninv, half);
-        auto* tb = new Tables<F>{dense, tlo, thi, ninv};
+        auto* tb = new Tables<F>{dense, tlo, thi, ninv, mid, {}};
+        if ((uint32_t)F::MAX_LG >= 4) {
+            T w_max = F::root_of_unity_max();
+            if (inverse) w_max = F::inv(w_max);
+            const T w16 = F::pow(w_max, 1ull << (F::MAX_LG - 4));
+            tb->w16[0] = F::one();
+            for (uint32_t i = 1; i < 8; i++) tb->w16[i] = F::mul(tb->w16[i - 1], w16);
+        }
         cache[key(0, lg_n, inverse)] = tb;
         return *tb;
     }
@@ -213,6 +242,13 @@ private:
         CUDA_OK(cudaGetLastError());
     }
 
+    static bool use_warp_path(uint32_t lg_n)
+    {
+        if (F::LG_EPT != 4 || lg_n < WARP_MIN_LG_R) return false;
+        const char* env = getenv("SPPARK_B200_NTT_BLOCK");
+        return !(env && env[0] == '1');
+    }
+
 public:
     // device-resident transform, enqueued on `stream`, no synchronisation
     static void NTT_internal(const gpu_t& gpu, T* d_inout, uint32_t lg_n, InputOutputOrder order,
@@ -231,13 +267,20 @@ public:
             coset_scale(gpu, d_inout, lg_n, in_rev, false, stream);
 
         const Tables<F>& tb = tables(gpu, lg_n, inverse, stream);
-        // 2^14-element tiles fill one SM's shared memory; below 2^22 elements shrink the tile so
-        // that there are still >= 256 of them for the 148 SMs
+        // single-word fields: warp-autonomous passes of 2^4..2^8-point sub-NTTs (ntt_warp.cuh);
+        // 256-bit fields (and SPPARK_B200_NTT_BLOCK=1): block-tile passes of up to 2^12 points
+        const bool warp_path = use_warp_path(lg_n);
         uint32_t lg_tile = FieldId<F>::lg_tile;
-        if (lg_n < lg_tile + 8) lg_tile = lg_n > 18 ? lg_n - 8 : 10;
-        if (const char* env = getenv("SPPARK_B200_NTT_LG_TILE")) lg_tile = (uint32_t)atoi(env);
-        if (lg_tile > FieldId<F>::lg_tile) lg_tile = FieldId<F>::lg_tile;
-        Plan plan = make_plan(lg_n, (int)order, inverse, lg_tile, 6, F::NTT_MAX_LG_R);
+        if (warp_path) {
+            lg_tile = WARP_MAX_LG_R + 6;                  // up to 64 adjacent columns per tile
+        } else {
+            // 2^14-element tiles fill one SM's shared memory; below 2^22 elements shrink the tile so
+            // that there are still >= 256 of them for the 148 SMs
+            if (lg_n < lg_tile + 8) lg_tile = lg_n > 18 ? lg_n - 8 : 10;
+            if (const char* env = getenv("SPPARK_B200_NTT_LG_TILE")) lg_tile = (uint32_t)atoi(env);
+            if (lg_tile > FieldId<F>::lg_tile) lg_tile = FieldId<F>::lg_tile;
+        }
+        Plan plan = make_plan(lg_n, (int)order, inverse, lg_tile, 6, warp_path ? WARP_MAX_LG_R : F::NTT_MAX_LG_R);
 
         T* scratch = nullptr;
         if (plan.needs_scratch)
@@ -255,7 +298,10 @@ public:
             g_profile.mark("pass", stream);
             uint32_t ntiles = 1u << (lg_n - d.lg_r - d.lg_w);
             size_t smem = smem_elems(d) * sizeof(T);
-            if (!launch_static<F>(d, tb, buf[d.src], buf[d.dst], ntiles, smem, stream))
+            bool done = false;
+            if constexpr (F::LG_EPT == 4)
+                done = warp_path && launch_warp<F>(gpu, d, tb, buf[d.src], buf[d.dst], 1u << (lg_n - d.lg_r), stream);
+            if (!done && !launch_static<F>(d, tb, buf[d.src], buf[d.dst], ntiles, smem, stream))
                 pass_kernel<F><<<ntiles, tile_threads<F>(d), smem, stream>>>(d, tb, buf[d.src], buf[d.dst]);
             COUNT_LAUNCH();
             CUDA_OK(cudaGetLastError());

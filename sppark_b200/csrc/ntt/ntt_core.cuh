@@ -63,6 +63,10 @@ template<class F> struct Tables {
     const typename F::T* tlo;            // tlo[i] = w_N^i,            i < 2^LG_TLO
     const typename F::T* thi;            // thi[i] = w_N^(i << LG_TLO)
     typename F::T ninv;                  // 2^-n
+    // warp-autonomous passes (ntt_warp.cuh): twist tables of the 2^5..2^8-point sub-NTTs,
+    // mid[mid_offset(R) + k0 * 2^(R-4) + b] = w_(2^R)^(b * k0), and the powers of w_16
+    const typename F::T* mid;
+    typename F::T w16[8];
 };
 
 // ---- compile-time / run-time views of the shape of a pass ------------------------------

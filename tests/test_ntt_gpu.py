@@ -324,3 +324,93 @@ def test_lde_matches_reference_gpu_golden():
     g = np.load(path)
     for lg, lb in ((1, 1), (3, 1), (6, 2), (10, 1), (12, 3)):
         assert np.array_equal(ntt.LDE(0, g[f"in_{lg}_{lb}"], lb), g[f"out_{lg}_{lb}"]), (lg, lb)
+
+
+def _word_selftest(field, op, a, b):
+    from sppark_b200 import _lib
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    r = np.zeros_like(a)
+    _lib.check(_lib.lib().sppark_b200_selftest_word_field(field, op, a.size, r.ctypes.data, a.ctypes.data, b.ctypes.data))
+    return r
+
+
+def _gl64_operands(seed, n):
+    """Pairs (a loose, b canonical) with every carry / borrow / wrap corner of p = 2^64 - 2^32 + 1."""
+    edge = [0, 1, 2, 0xFFFFFFFE, 0xFFFFFFFF, 0x100000000, 0x100000001, 2**63 - 1, 2**63, 2**63 + 1,
+            0xFFFFFFFE00000000, 0xFFFFFFFEFFFFFFFF, 0xFFFFFFFF00000000, GL_P - 1, GL_P, GL_P + 1,
+            0xFFFFFFFF00000002, 0xFFFFFFFFFFFFFFFE, 0xFFFFFFFFFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF00000001 - 0xFFFFFFFF]
+    a = [x for x in edge for _ in edge]
+    b = [y % GL_P for _ in edge for y in edge]
+    rng = np.random.default_rng(seed)
+    ra = rng.integers(0, 2**64, size=n, dtype=np.uint64)
+    rb = rng.integers(0, GL_P, size=n, dtype=np.uint64)
+    # operands with saturated halves hit the +-EPS corrections far more often than uniform ones
+    ra[: n // 4] |= np.uint64(0xFFFFFFFF00000000)
+    rb[n // 8: n // 4] = (rb[n // 8: n // 4] | np.uint64(0xFFFFFFFE00000000)) % np.uint64(GL_P)
+    return (np.concatenate([np.array(a, dtype=np.uint64), ra]), np.concatenate([np.array(b, dtype=np.uint64), rb]))
+
+
+def test_gl64_device_field_arithmetic_known_answers():
+    """The PTX field arithmetic against Python integers: add / sub keep the value mod p for a loose
+    first and a canonical second operand; mul is the Montgomery product a*b*2^-64 and is canonical;
+    tight / canon reduce below p."""
+    a, b = _gl64_operands(11, 1 << 16)
+    ai = [int(v) for v in a]
+    bi = [int(v) for v in b]
+    rinv = pow(2**64, -1, GL_P)
+    got = _word_selftest(0, 1, a, b)
+    assert all(int(g) % GL_P == (x + y) % GL_P for g, x, y in zip(got, ai, bi))
+    got = _word_selftest(0, 2, a, b)
+    assert all(int(g) % GL_P == (x - y) % GL_P for g, x, y in zip(got, ai, bi))
+    got = _word_selftest(0, 0, a, b)
+    assert all(int(g) == x * y * rinv % GL_P for g, x, y in zip(got, ai, bi))
+    for op in (3, 4):
+        got = _word_selftest(0, op, a, b)
+        assert all(int(g) == x % GL_P for g, x in zip(got, ai))
+
+
+def test_bb31_device_field_arithmetic_known_answers():
+    rng = np.random.default_rng(12)
+    edge = np.array([0, 1, 2, BB_P - 1, BB_P - 2, BB_P // 2, BB_P // 2 + 1, 0x0FFFFFFE], dtype=np.uint32)
+    a = np.concatenate([np.repeat(edge, len(edge)), rng.integers(0, BB_P, size=1 << 14, dtype=np.uint32)])
+    b = np.concatenate([np.tile(edge, len(edge)), rng.integers(0, BB_P, size=1 << 14, dtype=np.uint32)])
+    ai = a.astype(np.uint64)
+    bi = b.astype(np.uint64)
+    assert np.array_equal(_word_selftest(1, 1, a, b), ((ai + bi) % BB_P).astype(np.uint32))
+    assert np.array_equal(_word_selftest(1, 2, a, b), ((ai + BB_P - bi) % BB_P).astype(np.uint32))
+    rinv = pow(2**32, -1, BB_P)
+    want = np.array([int(x) * int(y) * rinv % BB_P for x, y in zip(a, b)], dtype=np.uint32)
+    assert np.array_equal(_word_selftest(1, 0, a, b), want)
+
+
+@pytest.mark.parametrize("field", ["gl64", "bb31"])
+@pytest.mark.parametrize("split", ["4,4,4", "5,5,5", "6,6", "7,7,7", "8,8", "8,4,6", "4,5,4,5"])
+def test_warp_pass_every_subntt_size(oracle, field, split, monkeypatch):
+    """Every sub-NTT size of the warp-autonomous pass (2^4..2^8), in every position of a plan and
+    in every order / direction, against the oracle."""
+    from sppark_b200 import ntt
+    monkeypatch.setenv("SPPARK_B200_NTT_SPLIT", split)
+    lg = sum(int(v) for v in split.split(","))
+    x = _rand(field, 1 << lg, 900 + lg)
+    ofn = oracle.ntt_gl64 if field == "gl64" else oracle.ntt_bb31
+    for order in (ntt.NN, ntt.NR, ntt.RN, ntt.RR):
+        for inverse in (False, True):
+            y = x.copy()
+            (ntt.iNTT if inverse else ntt.NTT)(0, y, order)
+            assert np.array_equal(y, ofn(x, order, inverse, nthreads=8)), (field, split, order, inverse)
+
+
+@pytest.mark.parametrize("cpt", ["1", "2"])
+@pytest.mark.parametrize("field", ["gl64", "bb31"])
+def test_warp_pass_columns_per_lane(oracle, field, cpt, monkeypatch):
+    from sppark_b200 import ntt
+    monkeypatch.setenv("SPPARK_B200_NTT_CPT", cpt)
+    ofn = oracle.ntt_gl64 if field == "gl64" else oracle.ntt_bb31
+    for lg in (4, 5, 9, 13, 16, 19):
+        x = _rand(field, 1 << lg, 70 + lg)
+        for order in (ntt.NN, ntt.NR, ntt.RN):
+            for inverse in (False, True):
+                y = x.copy()
+                (ntt.iNTT if inverse else ntt.NTT)(0, y, order)
+                assert np.array_equal(y, ofn(x, order, inverse, nthreads=8)), (field, cpt, lg, order, inverse)
