@@ -242,11 +242,19 @@ private:
         CUDA_OK(cudaGetLastError());
     }
 
+    // Which pass kernel: below 2^20 elements the warp-autonomous passes (ntt_warp.cuh: no block
+    // barrier, any number of warps busy) win -- 2^16: 23 us against 37 us; from 2^20 on the two
+    // 12-stage block-tile passes move a third less data and are ahead by 5-10 % (B200, round 2:
+    // gpurun_out/r2_probe_ntt6.txt, summarised in profiles/).  SPPARK_B200_NTT_WARP=1 /
+    // SPPARK_B200_NTT_BLOCK=1 force one or the other (experiments, tests).
     static bool use_warp_path(uint32_t lg_n)
     {
         if (F::LG_EPT != 4 || lg_n < WARP_MIN_LG_R) return false;
-        const char* env = getenv("SPPARK_B200_NTT_BLOCK");
-        return !(env && env[0] == '1');
+        const char* b = getenv("SPPARK_B200_NTT_BLOCK");
+        const char* w = getenv("SPPARK_B200_NTT_WARP");
+        if (b && b[0] == '1') return false;
+        if (w && w[0] == '1') return true;
+        return lg_n < 20;
     }
 
 public:

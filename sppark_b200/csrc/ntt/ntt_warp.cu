@@ -7,19 +7,37 @@
 
 namespace ntt {
 // ---- warp-autonomous passes (ntt_warp.cuh) ---------------------------------------------------
+template<class F, uint32_t R, uint32_t CPT, uint32_t TW>
+static void launch_warp_tw(const gpu_t& gpu, const Pass& d, const Tables<F>& tb, const typename F::T* in,
+                              typename F::T* out, uint32_t ncols, cudaStream_t stream)
+{
+    constexpr uint32_t WARPS = 8, SPW = 32u >> (R - 4);
+    const size_t smem = (size_t)cta_smem_words(R, CPT, WARPS) * sizeof(typename F::T);
+    // per device (function attributes and occupancy are per context): resident CTAs per SM
+    static int per_sm[64];
+    int& ctas = per_sm[gpu.cid() & 63];
+    if (ctas == 0) {
+        CUDA_OK(cudaFuncSetAttribute(pass_kernel_warp<F, R, CPT, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, pass_kernel_warp<F, R, CPT, TW>, WARPS * 32, smem));
+        if (ctas < 1) throw cuda_error(-(int)cudaErrorLaunchOutOfResources, "NTT warp pass does not fit an SM");
+    }
+    // persistent warps: at most one resident wave, every warp walks units with the grid's stride
+    const uint32_t units = (ncols + SPW * CPT - 1) / (SPW * CPT);
+    uint32_t grid = (units + WARPS - 1) / WARPS;
+    const uint32_t wave = (uint32_t)gpu.sm_count() * (uint32_t)ctas;
+    if (grid > wave) grid = wave;
+    pass_kernel_warp<F, R, CPT, TW><<<grid, WARPS * 32, smem, stream>>>(d, tb, in, out, ncols);
+}
+
 template<class F, uint32_t R, uint32_t CPT>
 static void launch_warp_shape(const gpu_t& gpu, const Pass& d, const Tables<F>& tb, const typename F::T* in,
                               typename F::T* out, uint32_t ncols, cudaStream_t stream)
 {
-    constexpr uint32_t WARPS = 8, SPW = 32u >> (R - 4);
-    const size_t smem = (size_t)WARPS * CPT * warp_xchg_words(R) * sizeof(typename F::T);
-    static bool attr_done[64];                       // per device: function attributes are per context
-    if (smem > 48 * 1024 && !attr_done[gpu.cid() & 63]) {
-        CUDA_OK(cudaFuncSetAttribute(pass_kernel_warp<F, R, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done[gpu.cid() & 63] = true;
+    switch (d.tw_mode) {
+    case TW_LOAD: launch_warp_tw<F, R, CPT, TW_LOAD>(gpu, d, tb, in, out, ncols, stream); break;
+    case TW_STORE: launch_warp_tw<F, R, CPT, TW_STORE>(gpu, d, tb, in, out, ncols, stream); break;
+    default: launch_warp_tw<F, R, CPT, TW_NONE>(gpu, d, tb, in, out, ncols, stream); break;
     }
-    const uint32_t units = (ncols + SPW * CPT - 1) / (SPW * CPT);
-    pass_kernel_warp<F, R, CPT><<<(units + WARPS - 1) / WARPS, WARPS * 32, smem, stream>>>(d, tb, in, out, ncols);
 }
 
 template<class F, uint32_t CPT>

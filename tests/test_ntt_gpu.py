@@ -391,6 +391,7 @@ def test_warp_pass_every_subntt_size(oracle, field, split, monkeypatch):
     in every order / direction, against the oracle."""
     from sppark_b200 import ntt
     monkeypatch.setenv("SPPARK_B200_NTT_SPLIT", split)
+    monkeypatch.setenv("SPPARK_B200_NTT_WARP", "1")
     lg = sum(int(v) for v in split.split(","))
     x = _rand(field, 1 << lg, 900 + lg)
     ofn = oracle.ntt_gl64 if field == "gl64" else oracle.ntt_bb31
@@ -406,6 +407,7 @@ def test_warp_pass_every_subntt_size(oracle, field, split, monkeypatch):
 def test_warp_pass_columns_per_lane(oracle, field, cpt, monkeypatch):
     from sppark_b200 import ntt
     monkeypatch.setenv("SPPARK_B200_NTT_CPT", cpt)
+    monkeypatch.setenv("SPPARK_B200_NTT_WARP", "1")
     ofn = oracle.ntt_gl64 if field == "gl64" else oracle.ntt_bb31
     for lg in (4, 5, 9, 13, 16, 19):
         x = _rand(field, 1 << lg, 70 + lg)
@@ -414,3 +416,20 @@ def test_warp_pass_columns_per_lane(oracle, field, cpt, monkeypatch):
                 y = x.copy()
                 (ntt.iNTT if inverse else ntt.NTT)(0, y, order)
                 assert np.array_equal(y, ofn(x, order, inverse, nthreads=8)), (field, cpt, lg, order, inverse)
+
+
+@pytest.mark.parametrize("field", ["gl64", "bb31"])
+@pytest.mark.parametrize("knob,sizes", [("SPPARK_B200_NTT_BLOCK", [4, 9, 13, 17]), ("SPPARK_B200_NTT_WARP", [20, 22])])
+def test_both_pass_kernels_at_every_size_class(oracle, field, knob, sizes, monkeypatch):
+    """The library picks the warp-autonomous passes below 2^20 and the block-tile passes above;
+    each kernel is also correct on the other side of that line."""
+    from sppark_b200 import ntt
+    monkeypatch.setenv(knob, "1")
+    ofn = oracle.ntt_gl64 if field == "gl64" else oracle.ntt_bb31
+    for lg in sizes:
+        x = _rand(field, 1 << lg, 300 + lg)
+        for order in (ntt.NN, ntt.NR, ntt.RN):
+            for inverse in (False, True):
+                y = x.copy()
+                (ntt.iNTT if inverse else ntt.NTT)(0, y, order)
+                assert np.array_equal(y, ofn(x, order, inverse, nthreads=8)), (field, knob, lg, order, inverse)

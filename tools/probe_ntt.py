@@ -1,6 +1,8 @@
 """GPU probe: time our NTT (device-resident) against the reference's own kernels built for
-sm_100a (oracle/_ref), over the kernel variants selected by environment knobs.  Development
-tool, not the bench."""
+sm_100a (oracle/_ref), over the kernel variants selected by environment knobs.  Two clocks per
+case: `call` = one call between two events (includes the host-side launch path while the GPU is
+idle), `b2b` = 20 calls back to back divided by 20 (the GPU never waits for the host: kernel time).
+Development tool, not the bench."""
 import ctypes as C
 import os
 import sys
@@ -13,9 +15,10 @@ sys.path.insert(0, ROOT)
 from sppark_b200 import ntt, _lib  # noqa: E402
 
 GL_P = 2**64 - 2**32 + 1
+BB_P = 0x78000001
 
 
-def time_fn(fn, stream, iters=20, warm=3, flush=None):
+def time_fn(fn, stream, iters=10, warm=3, flush=None, batch=20):
     for _ in range(warm):
         fn()
     stream.synchronize()
@@ -23,6 +26,7 @@ def time_fn(fn, stream, iters=20, warm=3, flush=None):
     for _ in range(iters):
         if flush is not None:
             flush.add_(1)
+            torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         fn()
@@ -30,11 +34,19 @@ def time_fn(fn, stream, iters=20, warm=3, flush=None):
         e1.synchronize()
         ts.append(e0.elapsed_time(e1))
     ts.sort()
-    return ts[len(ts) // 2], ts[0]
+    bs = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(batch):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        bs.append(e0.elapsed_time(e1) / batch)
+    return ts[len(ts) // 2], min(bs)
 
 
-VARIANTS = [("warp cpt1", {"SPPARK_B200_NTT_CPT": "1"}), ("warp cpt2", {"SPPARK_B200_NTT_CPT": "2"}),
-            ("block", {"SPPARK_B200_NTT_BLOCK": "1"})]
 KNOBS = ["SPPARK_B200_NTT_CPT", "SPPARK_B200_NTT_BLOCK", "SPPARK_B200_NTT_SPLIT"]
 
 
@@ -43,49 +55,63 @@ def main():
     print(torch.cuda.get_device_name(0))
     cur = torch.cuda.current_stream()
     flush = torch.zeros(64 << 20, dtype=torch.int32, device="cuda")      # 256 MiB > L2
-    sizes = [int(a) for a in sys.argv[1:]] or [16, 20, 22, 24]
-    for lg in sizes:
-        n = 1 << lg
-        rng = np.random.default_rng(lg)
-        host = rng.integers(0, GL_P, size=n, dtype=np.uint64)
-        bytes_alg = 2 * n * 8
-        extra = []
-        if lg == 20:
-            extra = [("warp 7,7,6", {"SPPARK_B200_NTT_SPLIT": "7,7,6"}), ("warp 8,8,4", {"SPPARK_B200_NTT_SPLIT": "8,8,4"}),
-                     ("warp 8,6,6", {"SPPARK_B200_NTT_SPLIT": "8,6,6"}), ("warp 5,5,5,5", {"SPPARK_B200_NTT_SPLIT": "5,5,5,5"})]
-        for vname, env in VARIANTS + extra:
+    args = sys.argv[1:]
+    fields = ["gl64"]
+    if args and args[0] in ("gl64", "bb31", "both"):
+        fields = ["gl64", "bb31"] if args[0] == "both" else [args[0]]
+        args = args[1:]
+    sizes = [int(a) for a in args] or [16, 20, 22, 24]
+    l = _lib.lib()
+    for field in fields:
+        for lg in sizes:
+            n = 1 << lg
+            rng = np.random.default_rng(lg)
+            if field == "gl64":
+                host = rng.integers(0, GL_P, size=n, dtype=np.uint64)
+                view, fid, esz = np.int64, 0, 8
+            else:
+                host = rng.integers(0, BB_P, size=n, dtype=np.uint32)
+                view, fid, esz = np.int32, 1, 4
+            bytes_alg = 2 * n * esz
+            variants = [("warp", {}), ("block", {"SPPARK_B200_NTT_BLOCK": "1"})]
+            if lg == 20:
+                variants += [("warp 7,7,6", {"SPPARK_B200_NTT_SPLIT": "7,7,6"})]
+            for vname, env in variants:
+                for k in KNOBS:
+                    os.environ.pop(k, None)
+                os.environ.update(env)
+                for order, name in ((ntt.NN, "NN"), (ntt.NR, "NR"), (ntt.RN, "RN")):
+                    d = torch.from_numpy(host.view(view)).cuda()
+                    ptr, s = d.data_ptr(), cur.cuda_stream
+                    med, b2b = time_fn(lambda: l.sppark_b200_ntt_dev(fid, ptr, lg, order, 0, 0, s), cur,
+                                       flush=flush if lg >= 22 else None)
+                    print(f"ours[{vname}] {field} 2^{lg} {name}: call {med*1e3:.1f} us  b2b {b2b*1e3:.1f} us  "
+                          f"-> {bytes_alg/ (b2b*1e-3) / 1e9:.0f} GB/s algorithmic", flush=True)
             for k in KNOBS:
                 os.environ.pop(k, None)
-            os.environ.update(env)
-            for order, name in ((ntt.NN, "NN"), (ntt.NR, "NR"), (ntt.RN, "RN")):
-                d = torch.from_numpy(host.view(np.int64)).cuda()
-                med, best = time_fn(lambda: ntt.ntt_dev(d, order), cur, flush=flush if lg >= 22 else None)
-                print(f"ours[{vname}] gl64 2^{lg} {name}: median {med*1e3:.1f} us  min {best*1e3:.1f} us  "
-                      f"-> {bytes_alg/ (med*1e-3) / 1e9:.0f} GB/s algorithmic", flush=True)
-        for k in KNOBS:
-            os.environ.pop(k, None)
-        # reference kernels, same box, data resident
-        p = os.path.join(ROOT, "oracle", "_ref", "libref_ntt_gl64_gpu.so")
-        if os.path.exists(p):
-            ref = C.CDLL(p)
-            ref.ref_ntt_stream.restype = C.c_void_p
-            ref.ref_ntt_dev_async.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int]
-            rs = torch.cuda.ExternalStream(ref.ref_ntt_stream())
-            for order, name in ((0, "NN"), (1, "NR"), (2, "RN")):
-                d = torch.from_numpy(host.view(np.int64)).cuda()
-                torch.cuda.synchronize()
-                med, best = time_fn(lambda: ref.ref_ntt_dev_async(d.data_ptr(), lg, order, 0, 0), rs,
-                                    flush=flush if lg >= 22 else None)
-                print(f"REF   gl64 2^{lg} {name}: median {med*1e3:.1f} us  min {best*1e3:.1f} us  "
-                      f"-> {bytes_alg/ (med*1e-3) / 1e9:.0f} GB/s algorithmic", flush=True)
-            # parity of ours vs the reference GPU implementation at this size
-            d1 = torch.from_numpy(host.view(np.int64)).cuda()
-            d2 = d1.clone()
-            ntt.ntt_dev(d1, ntt.NN)
-            torch.cuda.synchronize()
-            ref.ref_ntt_dev_async(d2.data_ptr(), lg, 0, 0, 0)
-            rs.synchronize()
-            print(f"ours == reference-GPU at 2^{lg} NN:", bool(torch.equal(d1, d2)), flush=True)
+            # reference kernels, same box, data resident
+            p = os.path.join(ROOT, "oracle", "_ref", f"libref_ntt_{field}_gpu.so")
+            if os.path.exists(p):
+                ref = C.CDLL(p)
+                ref.ref_ntt_stream.restype = C.c_void_p
+                ref.ref_ntt_dev_async.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int]
+                rs = torch.cuda.ExternalStream(ref.ref_ntt_stream())
+                for order, name in ((0, "NN"), (1, "NR"), (2, "RN")):
+                    d = torch.from_numpy(host.view(view)).cuda()
+                    torch.cuda.synchronize()
+                    ptr = d.data_ptr()
+                    med, b2b = time_fn(lambda: ref.ref_ntt_dev_async(ptr, lg, order, 0, 0), rs,
+                                       flush=flush if lg >= 22 else None)
+                    print(f"REF   {field} 2^{lg} {name}: call {med*1e3:.1f} us  b2b {b2b*1e3:.1f} us  "
+                          f"-> {bytes_alg/ (b2b*1e-3) / 1e9:.0f} GB/s algorithmic", flush=True)
+                if field == "gl64":
+                    d1 = torch.from_numpy(host.view(view)).cuda()
+                    d2 = d1.clone()
+                    ntt.ntt_dev(d1, ntt.NN)
+                    torch.cuda.synchronize()
+                    ref.ref_ntt_dev_async(d2.data_ptr(), lg, 0, 0, 0)
+                    rs.synchronize()
+                    print(f"ours == reference-GPU at 2^{lg} NN:", bool(torch.equal(d1, d2)), flush=True)
     print("launches:", _lib.launch_count())
 
 
