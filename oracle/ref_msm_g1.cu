@@ -2,7 +2,7 @@
  * oracle/ref_msm_g1.cu -- TEST INFRASTRUCTURE ONLY.
  *
  * The G1 half of the reference's poc/msm-cuda/cuda/pippenger_inf.cu (:20-34) for the crate's
- * bn254 / bls12_377 features, around the reference's OWN templates included from where they lie
+ * bn254 / bls12_377 features (and for the Pasta curves of ff/pasta.hpp), around the reference's OWN templates included from where they lie
  * under $(REF).  The file itself cannot be built for these features with the blst stand-in
  * (oracle/shim/blst_t.hpp): its G2 half needs blst's 256-bit vector API for the host fp2_t, and
  * its G2 entry point has the host/device layout mismatch described in ref_msm_g2.cu anyway.
@@ -13,8 +13,12 @@
 # include <ff/alt_bn128.hpp>
 #elif defined(FEATURE_BLS12_377)
 # include <ff/bls12-377.hpp>
+#elif defined(FEATURE_PALLAS) || defined(FEATURE_VESTA)
+/* the Pasta cycle (ff/pasta.hpp:82-103): the reference has no PoC boundary for these curves, its
+ * templates are instantiated here exactly as for the other features; host field = shim/pasta_t.hpp */
+# include <ff/pasta.hpp>
 #else
-# error "FEATURE_BN254 or FEATURE_BLS12_377"
+# error "FEATURE_BN254, FEATURE_BLS12_377, FEATURE_PALLAS or FEATURE_VESTA"
 #endif
 #include <ec/jacobian_t.hpp>
 #include <ec/xyzz_t.hpp>

@@ -8,6 +8,7 @@
   msm_g2_ref_gpu.npz  the reference's mult_pippenger_fp2_inf (BLS12-381 G2) and mult_pippenger_inf
                     (G1, arkworks layout with infinity flags): `... make_golden.py g2` on a GPU.
   msm_curves2_ref_gpu.npz  the reference's CUDA MSM for BN254 and BLS12-377 G1: `... make_golden.py curves2`.
+  msm_pasta_ref_gpu.npz    the reference's CUDA MSM templates for Pallas and Vesta: `... make_golden.py pasta`.
   msm_ref_cpu.npz   the reference's CPU msm/pippenger.hpp (oracle/_ref/libref_msm_cpu.so);
                     runs anywhere: `python tests/golden/make_golden.py cpu`.
 
@@ -71,27 +72,34 @@ def gen_cpu(outdir):
     print("wrote msm_ref_cpu.npz")
 
 
-def gen_gpu(outdir):
+# Every reference library is loaded in a process of its own: the reference's NTT keeps its
+# parameter tables in function-local / template statics, which g++ emits as STB_GNU_UNIQUE symbols;
+# the dynamic loader then shares ONE copy between all libraries of a process even under
+# RTLD_LOCAL, so a BabyBear library loaded after the Goldilocks one computes with Goldilocks
+# tables (this is what made the round-1 BabyBear / 256-bit recordings look self-inconsistent).
+def gen_ntt_word(outdir, field):
+    dtype, p, so = {"gl64": (np.uint64, GL_P, "libref_ntt_gl64_gpu.so"),
+                    "bb31": (np.uint32, BB_P, "libref_ntt_bb31_gpu.so")}[field]
     out = {}
-    for field, dtype, p, so in (("gl64", np.uint64, GL_P, "libref_ntt_gl64_gpu.so"),
-                                ("bb31", np.uint32, BB_P, "libref_ntt_bb31_gpu.so")):
-        lib = C.CDLL(o.ref_path(so))
-        lib.compute_ntt.restype = RE
-        lib.compute_ntt.argtypes = [C.c_size_t, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int]
-        rng = np.random.default_rng(7)
-        for lg in range(1, 11):
-            x = rng.integers(0, p, size=1 << lg, dtype=dtype)
-            out[f"{field}_in_{lg}"] = x
-            for order in range(4):
-                for direction in range(2):
-                    for typ in range(2):
-                        y = x.copy()
-                        e = lib.compute_ntt(0, y.ctypes.data, lg, order, direction, typ)
-                        assert e.code == 0
-                        out[f"{field}_out_{lg}_{order}{direction}{typ}"] = y
-    np.savez_compressed(os.path.join(outdir, "ntt_ref_gpu.npz"), **out)
-    print("wrote ntt_ref_gpu.npz")
+    lib = C.CDLL(o.ref_path(so))
+    lib.compute_ntt.restype = RE
+    lib.compute_ntt.argtypes = [C.c_size_t, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int]
+    rng = np.random.default_rng(7 if field == "gl64" else 8)
+    for lg in range(1, 13 if field == "bb31" else 11):
+        x = rng.integers(0, p, size=1 << lg, dtype=dtype)
+        out[f"{field}_in_{lg}"] = x
+        for order in range(4):
+            for direction in range(2):
+                for typ in range(2):
+                    y = x.copy()
+                    e = lib.compute_ntt(0, y.ctypes.data, lg, order, direction, typ)
+                    assert e.code == 0
+                    out[f"{field}_out_{lg}_{order}{direction}{typ}"] = y
+    np.savez_compressed(os.path.join(outdir, f"ntt_{field}_ref_gpu.npz"), **out)
+    print(f"wrote ntt_{field}_ref_gpu.npz")
 
+
+def gen_lde(outdir):
     # low-degree extension, Goldilocks (NTT::LDE)
     lib = C.CDLL(o.ref_path("libref_ntt_gl64_gpu.so"))
     lib.ref_lde.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
@@ -107,15 +115,16 @@ def gen_gpu(outdir):
     np.savez_compressed(os.path.join(outdir, "lde_ref_gpu.npz"), **out)
     print("wrote lde_ref_gpu.npz")
 
+
+def gen_ntt256(outdir):
     # 256-bit "wide" NTT: BLS12-381 scalar field, Montgomery residues
     lib = C.CDLL(o.ref_path("libref_ntt_bls12_381_gpu.so"))
     lib.compute_ntt.restype = RE
     lib.compute_ntt.argtypes = [C.c_size_t, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int]
     import random
     rnd = random.Random(11)
-    R = 1 << 256
     out = {}
-    for lg in range(1, 9):
+    for lg in range(1, 11):
         x = np.array([o.int_to_limbs(rnd.randrange(R_BLS), 4) for _ in range(1 << lg)], dtype=np.uint64)
         out[f"in_{lg}"] = x
         for order in range(4):
@@ -128,6 +137,8 @@ def gen_gpu(outdir):
     np.savez_compressed(os.path.join(outdir, "ntt256_ref_gpu.npz"), **out)
     print("wrote ntt256_ref_gpu.npz")
 
+
+def gen_msm(outdir):
     lib = C.CDLL(o.ref_path("libref_msm_gpu.so"))
     lib.mult_pippenger.restype = RE
     lib.mult_pippenger.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -141,6 +152,21 @@ def gen_gpu(outdir):
         out[f"affine_{n}"] = o.jac_to_affine("bls12_381", jac)
     np.savez_compressed(os.path.join(outdir, "msm_ref_gpu.npz"), **out)
     print("wrote msm_ref_gpu.npz")
+
+
+def gen_gpu(outdir):
+    """all GPU goldens, one process per reference library; ntt_ref_gpu.npz = Goldilocks + BabyBear"""
+    import subprocess
+    for mode in ("ntt_gl64", "ntt_bb31", "lde", "ntt256", "msm"):
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), mode])
+    merged = {}
+    for field in ("gl64", "bb31"):
+        part = os.path.join(outdir, f"ntt_{field}_ref_gpu.npz")
+        with np.load(part) as g:
+            merged.update({k: g[k] for k in g.files})
+        os.remove(part)
+    np.savez_compressed(os.path.join(outdir, "ntt_ref_gpu.npz"), **merged)
+    print("wrote ntt_ref_gpu.npz")
 
 
 def g2_inputs():
@@ -239,6 +265,41 @@ def gen_curves2(outdir):
     print("wrote msm_curves2_ref_gpu.npz")
 
 
+def gen_pasta(outdir):
+    """msm_pasta_ref_gpu.npz: the reference's CUDA MSM templates instantiated for the Pasta curves
+    (oracle/ref_msm_g1.cu with FEATURE_PALLAS / FEATURE_VESTA over ff/pasta.hpp; host field types from
+    oracle/shim/pasta_t.hpp): rows x, y, infinity flag; scalars are integers below the group order."""
+    out = {}
+    orders = {"pallas": 0x40000000000000000000000000000000224698fc0994a8dd8c46eb2100000001,
+              "vesta": 0x40000000000000000000000000000000224698fc094cf91b992d30ed00000001}
+    for curve, lib in (("pallas", "libref_msm_pallas_gpu.so"), ("vesta", "libref_msm_vesta_gpu.so")):
+        r = orders[curve]
+        ref = C.CDLL(o.ref_path(lib))
+        ref.mult_pippenger_inf.restype = RE
+        ref.mult_pippenger_inf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        nl = o.CURVE_LIMBS[o.CURVES[curve]]
+        rng = np.random.default_rng(100 + nl)
+        base = o.gen_points(curve, 64)
+        k = 0
+        for n in (1, 2, 33, 200, 1000, 5000):
+            pts = np.zeros((n, 2 * nl + 1), dtype=np.uint64)
+            pts[:, :2 * nl] = base[rng.integers(0, 64, size=n)]
+            sc = np.array([o.int_to_limbs(int.from_bytes(rng.bytes(32), "little") % r, 4) for _ in range(n)], dtype=np.uint64)
+            if n > 10:
+                pts[3, 2 * nl] = 1
+                pts[4, :2 * nl] = 0
+                sc[5] = 0
+                sc[7] = o.int_to_limbs(r - 1, 4)
+                pts[9], sc[9] = pts[8], sc[8]
+            jac = np.zeros(3 * nl, dtype=np.uint64)
+            ok(ref.mult_pippenger_inf(jac.ctypes.data, pts.ctypes.data, n, sc.ctypes.data, pts.strides[0]), f"{curve} n={n}")
+            out[f"{curve}_points{k}"], out[f"{curve}_scalars{k}"], out[f"{curve}_out{k}"] = pts, sc, jac
+            k += 1
+        out[f"{curve}_ncases"] = np.int64(k)
+    np.savez_compressed(os.path.join(outdir, "msm_pasta_ref_gpu.npz"), **out)
+    print("wrote msm_pasta_ref_gpu.npz")
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "cpu"
     if mode == "cpu":
@@ -250,5 +311,15 @@ if __name__ == "__main__":
             gen_g2(outdir)
         elif mode == "curves2":
             gen_curves2(outdir)
+        elif mode == "pasta":
+            gen_pasta(outdir)
+        elif mode in ("ntt_gl64", "ntt_bb31"):
+            gen_ntt_word(outdir, mode[4:])
+        elif mode == "lde":
+            gen_lde(outdir)
+        elif mode == "ntt256":
+            gen_ntt256(outdir)
+        elif mode == "msm":
+            gen_msm(outdir)
         else:
             gen_gpu(outdir)

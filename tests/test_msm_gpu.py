@@ -121,6 +121,14 @@ def test_pasta_msm_matches_oracle(oracle, curve, cid):
     got = msm.msm(cid, pts, sc)
     want = oracle.msm(curve, pts, sc, "pippenger", ncpus=8)
     assert _same_point(oracle, curve, got, want)
+    # ... and against the reference's own CUDA MSM templates instantiated for this curve, recorded
+    # on a B200 (tests/golden/make_golden.py pasta: ff/pasta.hpp through oracle/ref_msm_g1.cu):
+    # arkworks-style rows with infinity flags, scalars below the group order incl. 0 and r - 1
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "msm_pasta_ref_gpu.npz"))
+    for k in range(int(g[f"{curve}_ncases"])):
+        got = msm.msm(cid, np.ascontiguousarray(g[f"{curve}_points{k}"]), np.ascontiguousarray(g[f"{curve}_scalars{k}"]))
+        assert _same_point(oracle, curve, got, g[f"{curve}_out{k}"]), k
 
 
 @pytest.mark.parametrize("curve,cid,fr", [("bn254", 4, "bn254_fr"), ("bls12_377", 5, "bls12_377_fr")])

@@ -110,19 +110,23 @@ def test_bad_arguments_return_errors():
 def test_matches_reference_gpu_golden():
     """Bit-exact against outputs of the reference's own CUDA NTT recorded on a B200
     (tests/golden/ntt_ref_gpu.npz, made by tests/golden/make_golden.py): every order x direction
-    x type, lg 1..10, Goldilocks."""
+    x type; Goldilocks lg 1..10 through compute_ntt, BabyBear lg 1..12 through sppark_b200_ntt."""
     import os
     from sppark_b200 import _lib
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ntt_ref_gpu.npz"))
     l = _lib.lib()
-    for lg in range(1, 11):
-        x = g[f"gl64_in_{lg}"]
-        for order in range(4):
-            for d in range(2):
-                for t in range(2):
-                    y = x.copy()
-                    _lib.check(l.compute_ntt(0, y.ctypes.data, lg, order, d, t))
-                    assert np.array_equal(y, g[f"gl64_out_{lg}_{order}{d}{t}"]), (lg, order, d, t)
+    for field, top in (("gl64", 10), ("bb31", 12)):
+        for lg in range(1, top + 1):
+            x = g[f"{field}_in_{lg}"]
+            for order in range(4):
+                for d in range(2):
+                    for t in range(2):
+                        y = x.copy()
+                        if field == "gl64":
+                            _lib.check(l.compute_ntt(0, y.ctypes.data, lg, order, d, t))
+                        else:
+                            _lib.check(l.sppark_b200_ntt(1, 0, y.ctypes.data, lg, order, d, t))
+                        assert np.array_equal(y, g[f"{field}_out_{lg}_{order}{d}{t}"]), (field, lg, order, d, t)
 
 
 @pytest.mark.parametrize("field", ["gl64", "bb31"])
@@ -186,17 +190,19 @@ def test_ntt_256bit_fields_match_oracle(oracle, fid, name):
 
 
 def test_ntt_256bit_matches_reference_gpu_golden():
-    """lg = 1 only: the reference's own sm_100a build of this field is self-inconsistent beyond
-    that (see tests/test_oracle.py::test_oracle_matches_reference_gpu_golden_ntt256)."""
+    """BLS12-381 scalar field, lg 1..10, every order x direction x type, against the recording of
+    the reference's own 256-bit ("wide") CUDA kernels."""
     import os
     from sppark_b200 import ntt
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ntt256_ref_gpu.npz"))
-    x = g["in_1"]
-    for order in range(4):
-        for d in range(2):
-            y = x.copy()
-            ntt._run(0, y, order, d, 0, field=ntt.BLS12_381_FR)
-            assert np.array_equal(y, g[f"out_1_{order}{d}0"]), (order, d)
+    for lg in range(1, 11):
+        x = g[f"in_{lg}"]
+        for order in range(4):
+            for d in range(2):
+                for t in range(2):
+                    y = x.copy()
+                    ntt._run(0, y, order, d, t, field=ntt.BLS12_381_FR)
+                    assert np.array_equal(y, g[f"out_{lg}_{order}{d}{t}"]), (lg, order, d, t)
 
 
 def test_ntt_256bit_2pow22_roundtrip():

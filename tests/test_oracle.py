@@ -84,6 +84,23 @@ def test_bn254_bls12_377_oracle(oracle, curve):
         assert np.array_equal(got, oracle.jac_to_affine(curve, g[f"{curve}_out{k}"])), k
 
 
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_pasta_oracle_matches_reference_gpu_golden(oracle, curve):
+    """The oracle's Pallas / Vesta MSM against the reference's own CUDA MSM templates run for these
+    curves on a B200 (ff/pasta.hpp:82-103 through oracle/ref_msm_g1.cu with the host field types of
+    oracle/shim/pasta_t.hpp; tests/golden/make_golden.py pasta) -- this is what pins the Pasta
+    oracle to the reference rather than to its own definition."""
+    nl = oracle.CURVE_LIMBS[oracle.CURVES[curve]]
+    g = np.load(os.path.join(GOLD, "msm_pasta_ref_gpu.npz"))
+    assert int(g[f"{curve}_ncases"]) >= 5
+    for k in range(int(g[f"{curve}_ncases"])):
+        p = g[f"{curve}_points{k}"].copy()
+        p[p[:, 2 * nl] != 0, :2 * nl] = 0                    # flagged rows are infinity
+        got = oracle.jac_to_affine(curve, oracle.msm(curve, np.ascontiguousarray(p[:, :2 * nl]), g[f"{curve}_scalars{k}"]))
+        want = oracle.jac_to_affine(curve, g[f"{curve}_out{k}"])
+        assert np.array_equal(got, want) and oracle.on_curve(curve, want), k
+
+
 def _sc(n, seed, r=R_BLS):
     rnd = random.Random(seed)
     return np.array([[(v >> (64 * i)) & (2**64 - 1) for i in range(4)]
@@ -161,17 +178,18 @@ def test_ntt_small_known_answers(oracle):
 
 
 def test_oracle_matches_reference_gpu_golden_ntt(oracle):
+    """Goldilocks (lg 1..10) and BabyBear (lg 1..12): every order x direction x type of the
+    reference's own CUDA NTT, recorded on a B200 with ONE reference library per process
+    (tests/golden/make_golden.py explains why that matters), bit for bit."""
     path = os.path.join(GOLD, "ntt_ref_gpu.npz")
     if not os.path.exists(path):
         pytest.skip("reference-GPU golden not recorded yet")
     g = np.load(path)
-    # BabyBear: the reference's sm_100a build fails its OWN self-consistency check (NN != RR in
-    # the recorded outputs, see DESIGN.md "parity pinning"), so only Goldilocks pins the oracle here.
-    for lg in range(2, 11):
-        assert not np.array_equal(g[f"bb31_out_{lg}_000"], g[f"bb31_out_{lg}_300"])
-    for field, fn in (("gl64", oracle.ntt_gl64),):
-        for lg in range(1, 11):
+    for field, fn, top in (("gl64", oracle.ntt_gl64, 10), ("bb31", oracle.ntt_bb31, 12)):
+        for lg in range(1, top + 1):
             x = g[f"{field}_in_{lg}"]
+            # the reference's own protocol holds in the recording: NN == RR
+            assert np.array_equal(g[f"{field}_out_{lg}_000"], g[f"{field}_out_{lg}_300"])
             for order in range(4):
                 for d in range(2):
                     for t in range(2):
@@ -180,21 +198,22 @@ def test_oracle_matches_reference_gpu_golden_ntt(oracle):
 
 
 def test_oracle_matches_reference_gpu_golden_ntt256(oracle):
-    """BLS12-381 scalar-field NTT (the reference's 256-bit "wide" kernels) recorded on a B200.
-    Like its BabyBear build, the reference's sm_100a build of this field fails its own
-    self-consistency check beyond lg = 1 (NN != RR in the recorded outputs), so only the
-    twiddle-free size pins anything; the oracle is pinned by the definition, the parameter tables
-    (tests/test_params_pin.py) and by sharing every line of the transform with Goldilocks."""
+    """BLS12-381 scalar-field NTT (the reference's 256-bit "wide" kernels) recorded on a B200,
+    lg 1..10, every order x direction x type."""
     path = os.path.join(GOLD, "ntt256_ref_gpu.npz")
     if not os.path.exists(path):
         pytest.skip("reference-GPU golden not recorded yet")
     g = np.load(path)
-    for lg in range(2, 9):
-        assert not np.array_equal(g[f"out_{lg}_000"], g[f"out_{lg}_300"])     # reference: NN != RR (!)
-    x = g["in_1"]
-    for order in range(4):
-        for d in range(2):
-            assert np.array_equal(oracle.ntt_ff("bls12_381_fr", x, order, bool(d)), g[f"out_1_{order}{d}0"])
+    for lg in range(1, 11):
+        x = g[f"in_{lg}"]
+        assert np.array_equal(g[f"out_{lg}_000"], g[f"out_{lg}_300"])          # reference: NN == RR
+        for order in range(4):
+            for d in range(2):
+                for t in range(2):
+                    if lg > 8 and t == 1 and order in (1, 2):
+                        continue                                          # keep the CPU suite short
+                    assert np.array_equal(oracle.ntt_ff("bls12_381_fr", x, order, bool(d), bool(t)),
+                                          g[f"out_{lg}_{order}{d}{t}"]), (lg, order, d, t)
 
 
 @pytest.mark.parametrize("field", ["bls12_381_fr", "pallas_fp", "vesta_fp"])

@@ -124,3 +124,32 @@ def test_256bit_ntt_roots():
         for lg in range(S + 1):
             assert t["forward_roots_of_unity"][lg] == pow(w, 1 << (S - lg), p) * R % p
             assert t["domain_size_inverse"][lg] == pow(2, -lg, p) * R % p
+
+
+def test_pasta_shim_constants():
+    """oracle/shim/pasta_t.hpp (host field types for the reference's Pasta MSM build) vs the
+    device-side tables of ff/pasta.hpp:12-50, and the Montgomery factors vs -p^-1 mod 2^64."""
+    shim = open(os.path.join(os.path.dirname(__file__), "..", "oracle", "shim", "pasta_t.hpp")).read()
+    theirs = open(f"{REF}/ff/pasta.hpp").read().split("namespace device")[1]
+
+    def shim_words(name):
+        m = re.search(r"static const vec256 %s = \{(.*?)\};" % name, shim, re.S)
+        words = []
+        for v in re.findall(r"TO_LIMB_T\((0x[0-9a-f]+)\)", m.group(1)):
+            v = int(v, 16)
+            words += [v & 0xFFFFFFFF, v >> 32]
+        return words
+
+    def ref_words(name):
+        m = re.search(r"%s\[8\] = \{(.*?)\};" % name, theirs, re.S)
+        return [int(v, 16) for v in re.findall(r"0x[0-9a-f]{8}", m.group(1))]
+
+    for ours, ref in (("Pallas_P", "Pallas_P"), ("Pallas_RR", "Pallas_RR"), ("Pallas_ONE", "Pallas_one"),
+                      ("Vesta_P", "Vesta_P"), ("Vesta_RR", "Vesta_RR"), ("Vesta_ONE", "Vesta_one")):
+        assert shim_words(ours) == ref_words(ref), ours
+    for name, m0 in (("Pallas_P", 0x992d30ecffffffff), ("Vesta_P", 0x8c46eb20ffffffff)):
+        w = shim_words(name)
+        p = sum(v << (32 * i) for i, v in enumerate(w))
+        assert (-pow(p, -1, 2**64)) % 2**64 == m0
+        assert "0x%016xu" % m0 in shim
+        assert m0 & 0xFFFFFFFF == 0xFFFFFFFF        # ff/pasta.hpp:51: Pasta_M0 = 0xffffffff
