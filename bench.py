@@ -120,8 +120,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 200"}
 
 
-def fold_scalars(sc, m):
+def fold_scalars(sc, m, r=None):
     """sum of scalars per residue class i mod m, reduced mod r -> (m, 4) uint64."""
+    r = R_BLS if r is None else r
     n = sc.shape[0]
     v = sc.reshape(n // m, m, 4)
     lo = (v & np.uint64(0xFFFFFFFF)).sum(axis=0, dtype=np.uint64)       # < 2^32 * n/m
@@ -131,7 +132,7 @@ def fold_scalars(sc, m):
         t = 0
         for k in range(4):
             t += (int(lo[j, k]) + (int(hi[j, k]) << 32)) << (64 * k)
-        t %= R_BLS
+        t %= r
         for k in range(4):
             out[j, k] = (t >> (64 * k)) & 0xFFFFFFFFFFFFFFFF
     return out
@@ -213,6 +214,8 @@ def main():
     ap.add_argument("--lg-cpu-sample", type=int, default=22)
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-ref-gpu", action="store_true")
+    ap.add_argument("--lg-pallas", type=int, default=24)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -328,11 +331,14 @@ def main():
 
     # ---- self-check at full size (size-independent property, no oracle): folding the scalars of
     # the replicated points onto the m distinct points must give the same group element
-    check = None
-    if world == 1:
-        folded = fold_scalars(sc_host, m)
-        small = msm.msm_dev(msm.BLS12_381_G1, base_dev, torch.from_numpy(folded.view(np.int64)).cuda())
-        check = "folded-msm " + ("ok" if _jac_equal(result, small, msm) else "MISMATCH")
+    folded = fold_scalars(sc_host, m)
+    if world > 1:
+        # every rank holds the same m distinct points: the sharded MSM equals the m-point MSM whose
+        # scalars are the folded scalars of ALL ranks, summed mod r
+        parts = parallel.all_gather_partials(folded.reshape(-1), "cuda").reshape(world, m, 4)
+        folded = fold_scalars(np.ascontiguousarray(parts.reshape(world * m, 4)), m)
+    small = msm.msm_dev(msm.BLS12_381_G1, base_dev, torch.from_numpy(folded.view(np.int64)).cuda())
+    check = f"folded-msm over {world} rank(s) " + ("ok" if _jac_equal(result, small, msm) else "MISMATCH")
 
     # ---------------------------------------------------------------- e2e through the C-ABI
     e2e = None
@@ -347,6 +353,7 @@ def main():
         e2e = {"value": 1.0 / dt, "unit": "MSM/s", "h2d_bytes_per_step": int(n * 128),
                "d2h_bytes_per_step": 144, "ms_per_step": dt * 1e3, "api": "mult_pippenger (host pointers, pinned)",
                "same_result": bool(_jac_equal(r2, result, msm))}
+        e2e_result = r2
     elif world > 1 and not args.skip_e2e:
         # N > 1: every rank pushes its shard through mult_pippenger from pinned host buffers (its
         # own PCIe link), then the same all-gather + combine as the device-resident step.  All
@@ -400,6 +407,14 @@ def main():
     # ---------------------------------------------------------------- Goldilocks NTT (second half of the metric)
     ntt_res = bench_ntt(args, torch, ntt, _lib, peak, peak_src, barrier, max_over_ranks, world)
 
+    # ---------------------------------------------------------------- config 4: Pallas MSM, sharded like the headline
+    pallas = bench_pallas(args, torch, msm, parallel, barrier, max_over_ranks, rank, world)
+
+    # ---------------------------------------------------------------- the reference's own sm_100a kernels (N = 1)
+    ref_gpu = None
+    if world == 1 and need_host and not args.skip_ref_gpu:
+        ref_gpu = bench_reference_gpu(args, torch, msm, ntt, _lib, pts_host, sc_host, e2e_result, e2e)
+
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -422,7 +437,8 @@ def main():
                            "scalars": "uniform < 2^254, seed 42+rank", "sharding": f"point-chunk x{world}, all-gather of partials",
                            "l2": "inputs (8.6 GB at 2^26) exceed L2; no flush needed"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
-                "cpu_baseline": cpu, "check": check, "ntt": ntt_res}
+                "cpu_baseline": cpu, "check": check, "ntt": ntt_res, "pallas_msm": pallas,
+                "reference_gpu": ref_gpu}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -439,20 +455,194 @@ def phases_entries(n, world):
     return best[1] * n
 
 
-def _jac_equal(a, b, msm):
+def _jac_equal(a, b, msm, field=0, nl=6):
     """Equality of two Jacobian points as group elements, by cross-multiplied coordinates
     (X1*Z2^2 == X2*Z1^2, Y1*Z2^3 == Y2*Z1^3), using the library's own field multiply (no oracle
-    on this path)."""
+    on this path).  field / nl: selftest field id and 64-bit limbs per coordinate (0 / 6 =
+    BLS12-381 fp, 2 / 4 = Pallas fp)."""
     a = np.asarray(a, dtype=np.uint64)
     b = np.asarray(b, dtype=np.uint64)
-    za, zb = a[12:], b[12:]
+    za, zb = a[2 * nl:], b[2 * nl:]
     if not za.any() or not zb.any():
         return (not za.any()) and (not zb.any())
-    mul = lambda x, y: msm.selftest_field(0, "mul", x.reshape(1, 6), y.reshape(1, 6))[0]   # noqa: E731
+    mul = lambda x, y: msm.selftest_field(field, "mul", x.reshape(1, nl), y.reshape(1, nl))[0]   # noqa: E731
     za2, zb2 = mul(za, za), mul(zb, zb)
-    if not np.array_equal(mul(a[:6], zb2), mul(b[:6], za2)):
+    if not np.array_equal(mul(a[:nl], zb2), mul(b[:nl], za2)):
         return False
-    return np.array_equal(mul(a[6:12], mul(zb2, zb)), mul(b[6:12], mul(za2, za)))
+    return np.array_equal(mul(a[nl:2 * nl], mul(zb2, zb)), mul(b[nl:2 * nl], mul(za2, za)))
+
+
+R_PALLAS = 0x40000000000000000000000000000000224698fc0994a8dd8c46eb2100000001   # order of the Pallas group
+
+
+def bench_pallas(args, torch, msm, parallel, barrier, max_over_ranks, rank, world):
+    """BASELINE.json config 4: Pallas MSM over 2^24 points, sharded by point-chunk over the ranks
+    (2^21 points per GPU at N = 8), one all-gather of the 96-byte partial results + combine.
+    Device-resident, strong scaling; checked by folding every rank's scalars onto the distinct
+    points (same size-independent property as the headline)."""
+    try:
+        lg = args.lg_pallas
+        n = (1 << lg) // world
+        m = 1 << min(LG_DISTINCT, lg - (world.bit_length() - 1))
+        base_dev = msm.generate_points_dev(msm.PALLAS, m)
+        rng = np.random.default_rng(4242 + rank)
+        sc = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
+        sc[:, 3] >>= np.uint64(2)                                      # < 2^254 < group order
+        d_points = base_dev.repeat(n // m, 1).contiguous()
+        d_scalars = torch.from_numpy(sc.view(np.int64)).cuda()
+
+        def step():
+            return parallel.msm_sharded(lambda: msm.msm_dev(msm.PALLAS, d_points, d_scalars),
+                                        lambda parts: msm.combine(msm.PALLAS, parts) if world > 1 else parts[0],
+                                        12, device="cuda")
+        for _ in range(max(3, args.warmup)):
+            result = step()
+        barrier()
+        iters = max(3, args.steps)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            result = step()
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1) / iters)
+        folded = fold_scalars(sc, m, R_PALLAS)
+        if world > 1:
+            parts = parallel.all_gather_partials(folded.reshape(-1), "cuda").reshape(world * m, 4)
+            folded = fold_scalars(np.ascontiguousarray(parts), m, R_PALLAS)
+        small = msm.msm_dev(msm.PALLAS, base_dev, torch.from_numpy(folded.view(np.int64)).cuda())
+        ok = _jac_equal(result, small, msm, field=2, nl=4)
+        del d_points, d_scalars
+        torch.cuda.empty_cache()
+        return {"metric": f"Pallas MSM/s @2^{lg} points", "value": 1e3 / ms, "unit": "MSM/s", "ms_per_step": ms,
+                "scaling": "strong", "n_gpus": world, "points_per_gpu": n,
+                "sharding": f"point-chunk x{world}, all-gather of 96-byte partials + combine",
+                "check": f"folded-msm over {world} rank(s) " + ("ok" if ok else "MISMATCH")}
+    except Exception as e:                                             # never take the headline down
+        return {"metric": "Pallas MSM/s", "value": None, "error": f"{type(e).__name__}: {e}"}
+
+
+class _RustError(C.Structure):
+    _fields_ = [("code", C.c_int), ("message", C.c_void_p)]
+
+
+def bench_reference_gpu(args, torch, msm, ntt, _lib, pts_host, sc_host, ours_result, ours_e2e):
+    """The kernels to beat: the REFERENCE's own CUDA code (poc/msm-cuda/cuda/pippenger.cu and
+    poc/ntt-cuda/cuda/ntt_api.cu) compiled for sm_100a into oracle/_ref by oracle/Makefile, called
+    through the identical host-pointer entry points on the same buffers, pinned and pageable, and
+    (NTT) on device-resident data.  Runs after the repository's own timed regions; rank 0, N = 1."""
+    out = {"source": "oracle/_ref/*.so = the reference's sources built with nvcc -arch sm_100a (oracle/Makefile)"}
+    refdir = os.path.join(ROOT, "oracle", "_ref")
+    n = pts_host.shape[0]
+    try:
+        path = os.path.join(refdir, "libref_msm_gpu.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        ref = C.CDLL(path)
+        ref.mult_pippenger.restype = _RustError
+        ref.mult_pippenger.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+
+        def ref_msm(p, s_):
+            o_ = np.zeros(18, dtype=np.uint64)
+            e = ref.mult_pippenger(o_.ctypes.data, p.ctypes.data, n, s_.ctypes.data)
+            if e.code != 0:
+                raise RuntimeError(f"reference mult_pippenger returned {e.code}")
+            return o_
+
+        def clock(fn, reps):
+            fn()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                r_ = fn()
+            return (time.perf_counter() - t0) / reps, r_
+
+        reps = max(1, min(2, args.steps))
+        dt_ref_pin, r_ref = clock(lambda: ref_msm(pts_host, sc_host), reps)
+        pts_pg, sc_pg = np.array(pts_host), np.array(sc_host)            # pageable copies (a Rust Vec is pageable)
+        dt_ref_pg, _ = clock(lambda: ref_msm(pts_pg, sc_pg), reps)
+        dt_our_pg, r_our = clock(lambda: msm.multi_scalar_mult(pts_pg, sc_pg), reps)
+        del pts_pg, sc_pg
+        out["msm"] = {"workload": f"bls12_381_g1_msm_2^{args.lg_msm}, mult_pippenger(host pointers)",
+                      "reference_ms": {"pinned": dt_ref_pin * 1e3, "pageable": dt_ref_pg * 1e3},
+                      "ours_ms": {"pinned": ours_e2e["ms_per_step"], "pageable": dt_our_pg * 1e3},
+                      "speedup": {"pinned": dt_ref_pin * 1e3 / ours_e2e["ms_per_step"], "pageable": dt_ref_pg / dt_our_pg},
+                      "same_group_element": bool(_jac_equal(r_ref, ours_result, msm) and _jac_equal(r_our, r_ref, msm))}
+    except Exception as e:
+        out["msm"] = {"error": f"{type(e).__name__}: {e}"}
+    try:
+        path = os.path.join(refdir, "libref_ntt_gl64_gpu.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        ref = C.CDLL(path)
+        ref.ref_ntt_stream.restype = C.c_void_p
+        ref.ref_ntt_dev_async.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int]
+        ref.compute_ntt.restype = _RustError
+        ref.compute_ntt.argtypes = [C.c_size_t, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int]
+        rs = torch.cuda.ExternalStream(ref.ref_ntt_stream())
+        cur = torch.cuda.current_stream()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        l = _lib.lib()
+        res = {}
+        for lg in sorted({20, args.lg_ntt}):
+            nn = 1 << lg
+            rng = np.random.default_rng(70 + lg)
+            host = rng.integers(0, GL_P, size=nn, dtype=np.uint64)
+            row = {}
+            for order, name in ((0, "NN"), (1, "NR"), (2, "RN")):
+                d1 = torch.from_numpy(host.view(np.int64)).cuda()
+                d2 = d1.clone()
+                p1, p2 = d1.data_ptr(), d2.data_ptr()
+
+                def timed(fn, stream, iters=10):
+                    for _ in range(3):
+                        fn()
+                    torch.cuda.synchronize()
+                    tot = 0.0
+                    for _ in range(iters):
+                        flush.zero_()
+                        torch.cuda.synchronize()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(stream)
+                        fn()
+                        e1.record(stream)
+                        e1.synchronize()
+                        tot += e0.elapsed_time(e1)
+                    return tot / iters * 1e3
+                ours_us = timed(lambda: l.sppark_b200_ntt_dev(0, p1, lg, order, 0, 0, cur.cuda_stream), cur)
+                ref_us = timed(lambda: ref.ref_ntt_dev_async(p2, lg, order, 0, 0), rs)
+                d1.copy_(torch.from_numpy(host.view(np.int64)))
+                d2.copy_(d1)
+                torch.cuda.synchronize()
+                l.sppark_b200_ntt_dev(0, p1, lg, order, 0, 0, cur.cuda_stream)
+                ref.ref_ntt_dev_async(p2, lg, order, 0, 0)
+                torch.cuda.synchronize()
+                row[name] = {"ours_us": ours_us, "reference_us": ref_us, "speedup": ref_us / ours_us,
+                             "bit_identical": bool(torch.equal(d1, d2))}
+            res[f"lg{lg}_device_resident"] = row
+        # host-pointer compute_ntt at the metric size: pinned and pageable
+        nn = 1 << args.lg_ntt
+        pin_t = torch.empty(nn, dtype=torch.int64, pin_memory=True)
+        pin = pin_t.numpy().view(np.uint64)
+        pin[:] = np.random.default_rng(9).integers(0, GL_P, size=nn, dtype=np.uint64)
+        pg = np.array(pin)
+
+        def host_ms(fn, buf, reps=3):
+            fn(buf)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn(buf)
+            return (time.perf_counter() - t0) / reps * 1e3
+
+        def ref_host(buf):
+            e = ref.compute_ntt(0, buf.ctypes.data, args.lg_ntt, 0, 0, 0)
+            assert e.code == 0
+        res[f"lg{args.lg_ntt}_compute_ntt_host_ms"] = {
+            "ours": {"pinned": host_ms(lambda b: ntt.NTT(0, b, ntt.NN), pin), "pageable": host_ms(lambda b: ntt.NTT(0, b, ntt.NN), pg)},
+            "reference": {"pinned": host_ms(ref_host, pin), "pageable": host_ms(ref_host, pg)}}
+        out["ntt"] = res
+    except Exception as e:
+        out["ntt"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
 
 
 def bench_ntt(args, torch, ntt, _lib, peak, peak_src, barrier, max_over_ranks, world):
