@@ -153,6 +153,13 @@ RustError sppark_b200_ntt_slab_pass(int field, int which, const void *d_in, void
 RustError sppark_b200_ntt_slab_pass_p2p(int field, const void *d_in, void *const *peer_recv,
                                         uint32_t lg_domain_size, uint32_t lg_g, uint32_t rank,
                                         int ntt_direction, void *stream);
+/* The same transform with every rank inside ONE process (a Rust / Go / C++ host needs no process
+ * group): `inout` is a host array of 2^lg elements in natural order (order NN); chunk r runs on
+ * device_ids[r], ndev = 1, 2, 4 or 8.  The exchange is fused into stage 1 (NVLink peer stores) when
+ * the devices are distinct and can access each other, block copies otherwise. */
+RustError sppark_b200_ntt_sharded(int field, void *inout, uint32_t lg_domain_size, int ntt_direction,
+                                  const int *device_ids, size_t ndev);
+
 /* Peer buffers (one process per GPU): cudaMalloc + CUDA IPC handle (64 bytes) on the owner,
  * cudaIpcOpenMemHandle / cudaIpcCloseMemHandle on the other ranks of the same node. */
 RustError sppark_b200_peer_alloc(size_t bytes, void **d_ptr, void *ipc_handle_64);
@@ -169,6 +176,14 @@ RustError sppark_b200_msm(int curve, void *out_jacobian, const void *points_affi
 RustError sppark_b200_msm_ex(int curve, void *out_jacobian, const void *points_affine,
                              size_t npoints, const void *scalars, size_t ffi_affine_sz,
                              int scalars_mont);
+/* One MSM sharded by point-chunk over GPUs of this process: chunk i of the points /
+ * scalars runs on device_ids[i] through the host-pointer pipeline of that device, the ndev partial
+ * results are added on the first device.  ndev = 1..64; ids may repeat (chunks of one device run
+ * one after the other).  The multi-process route (one rank per GPU, NCCL all-gather of the
+ * partials) is sppark_b200/parallel.py. */
+RustError sppark_b200_msm_sharded(int curve, void *out_jacobian, const void *points_affine, size_t npoints,
+                                  const void *scalars, size_t ffi_affine_sz, int scalars_mont,
+                                  const int *device_ids, size_t ndev);
 /* Preloaded points: the reference's msm_t{points, npoints} constructor + invoke(out, scalars)
  * (msm/pippenger.cuh:377-390,582-601) -- a fixed SRS stays on the device (of the calling thread's
  * current GPU), each invoke moves only the scalars (host pointer; npoints <= preloaded count). */

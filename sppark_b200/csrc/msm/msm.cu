@@ -1,5 +1,7 @@
 // Curve dispatch for the extended MSM entry points (include/sppark_b200.h).
 #include "../util/gpu.cuh"
+#include <thread>
+#include <vector>
 
 RustError msm_host_bls12_381(void*, const void*, size_t, const void*, size_t, bool, bool);
 RustError msm_dev_bls12_381(void*, const void*, size_t, const void*, void*);
@@ -107,6 +109,84 @@ extern "C" RustError sppark_b200_msm_dev(int curve, void* out, const void* d_poi
     case SPPARK_CURVE_BLS12_377_G1: return msm_dev_bls12_377(out, d_points, npoints, d_scalars, stream);
     default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_msm_dev: unknown curve");
     }
+}
+
+// ---- one MSM sharded by point-chunk over several GPUs of this process --------
+// chunk i of the points / scalars runs on device_ids[i] (one host thread per distinct device, the
+// chunks of a device one after the other; the host-pointer pipeline of msm_host on each device's
+// own PCIe link), the partial results -- one Jacobian point each -- are added on the first device.
+// No collective library is needed inside one process: the "all-gather" of the multi-process
+// route (sppark_b200/parallel.py over NCCL) is a host array here.
+static size_t jacobian_bytes(int curve)
+{
+    switch (curve) {
+    case SPPARK_CURVE_BLS12_381_G1: case SPPARK_CURVE_BLS12_377_G1: return 144;
+    case SPPARK_CURVE_BLS12_381_G2: return 288;
+    default: return 96;
+    }
+}
+static size_t packed_affine_bytes(int curve)
+{
+    switch (curve) {
+    case SPPARK_CURVE_BLS12_381_G1: case SPPARK_CURVE_BLS12_377_G1: return 96;
+    case SPPARK_CURVE_BLS12_381_G2: return 192;
+    default: return 64;
+    }
+}
+
+extern "C" RustError sppark_b200_msm_sharded(int curve, void* out, const void* points, size_t npoints,
+                                             const void* scalars, size_t ffi_affine_sz, int scalars_mont,
+                                             const int* device_ids, size_t ndev)
+{
+    if (curve < 0 || curve > SPPARK_CURVE_BLS12_377_G1)
+        return rust_err(-(int)cudaErrorInvalidValue, "msm_sharded: unknown curve");
+    if (out == nullptr || ndev == 0 || ndev > 64 || device_ids == nullptr)
+        return rust_err(-(int)cudaErrorInvalidValue, "msm_sharded: need 1..64 device ids");
+    const size_t jb = jacobian_bytes(curve), stride = ffi_affine_sz ? ffi_affine_sz : packed_affine_bytes(curve);
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return rust_err(-(int)cudaErrorNoDevice, "msm_sharded: no CUDA device");
+    for (size_t i = 0; i < ndev; i++)
+        if (device_ids[i] < 0 || device_ids[i] >= count)
+            return rust_err(-(int)cudaErrorInvalidDevice, "msm_sharded: no such device");
+    int home = 0;
+    (void)cudaGetDevice(&home);
+
+    std::vector<uint8_t> partials(ndev * jb, 0);
+    std::vector<RustError> status(ndev, rust_ok());
+    const size_t chunk = (npoints + ndev - 1) / ndev;
+    auto run_device = [&](int dev) {
+        if (cudaSetDevice(dev) != cudaSuccess) {
+            for (size_t i = 0; i < ndev; i++)
+                if (device_ids[i] == dev) status[i] = rust_err(-(int)cudaErrorInvalidDevice, "msm_sharded: cudaSetDevice failed");
+            return;
+        }
+        for (size_t i = 0; i < ndev; i++) {
+            if (device_ids[i] != dev) continue;
+            const size_t first = i * chunk < npoints ? i * chunk : npoints;
+            const size_t n = npoints - first < chunk ? npoints - first : chunk;
+            status[i] = msm_any(curve, partials.data() + i * jb, (const uint8_t*)points + first * stride, n,
+                                (const uint8_t*)scalars + first * 32, ffi_affine_sz, scalars_mont != 0);
+        }
+    };
+    std::vector<int> distinct;
+    for (size_t i = 0; i < ndev; i++) {
+        bool seen = false;
+        for (int d : distinct) seen |= d == device_ids[i];
+        if (!seen) distinct.push_back(device_ids[i]);
+    }
+    std::vector<std::thread> workers;
+    for (size_t k = 1; k < distinct.size(); k++) workers.emplace_back(run_device, distinct[k]);
+    run_device(distinct[0]);
+    for (auto& t : workers) t.join();
+    (void)cudaSetDevice(distinct[0]);
+    RustError result = rust_ok();
+    for (size_t i = 0; i < ndev; i++) {
+        if (status[i].code != 0 && result.code == 0) result = status[i];
+        else if (status[i].message) free(status[i].message);
+    }
+    if (result.code == 0) result = sppark_b200_msm_combine(curve, out, partials.data(), ndev);
+    (void)cudaSetDevice(home);
+    return result;
 }
 
 // ---- preloaded points (the reference's msm_t{points, npoints} + invoke(out, scalars),

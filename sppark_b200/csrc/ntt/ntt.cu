@@ -3,6 +3,8 @@
 #include "../ff/bb31.cuh"
 #include "../ff/mont_ntt.cuh"
 #include "ntt.cuh"
+#include <memory>
+#include <vector>
 
 namespace ntt {
 // lg_tile: log2(elements) of one CTA's shared-memory tile: 128 KiB of data for either field
@@ -202,6 +204,147 @@ extern "C" RustError sppark_b200_ntt_slab_pass_p2p(int field, const void* d_in, 
     case SPPARK_FIELD_BN254_FR: return ntt_slab<ff::bn254_fr_ntt>(1, d_in, nullptr, lg, lg_g, rank, direction, stream, peer_recv);
     case SPPARK_FIELD_BLS12_377_FR: return ntt_slab<ff::bls12_377_fr_ntt>(1, d_in, nullptr, lg, lg_g, rank, direction, stream, peer_recv);
     default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_ntt_slab_pass_p2p: unknown field");
+    }
+}
+
+// ---- one transform slab-sharded over several GPUs of THIS process -----------
+// Host array in natural order in and out (order NN).  Chunk r of the plan (ntt_plan.hpp:
+// make_slab_plan) runs on device_ids[r]: strided upload of its column slab, local stage 1, the one
+// exchange, local stage 2, strided download of its slab of the result.  The exchange is either
+// fused into stage 1 -- every row is stored straight into the receiving GPU over NVLink, all devices
+// being mapped into one address space by cudaDeviceEnablePeerAccess (no IPC handles inside one
+// process) -- or, when the devices cannot see each other (or an id repeats: single-GPU tests),
+// G^2 block copies (cudaMemcpyPeerAsync) between the staging and the receive buffers.  Ordering
+// between devices is by events only; the host waits once, for the downloads.
+template<class F>
+static RustError ntt_sharded(void* inout, uint32_t lg, int direction, const int* ids, size_t ndev)
+{
+    typedef typename F::T T;
+    typedef ntt::NTT<F> N;
+    uint32_t lg_g = 0;
+    while ((1u << lg_g) < ndev) lg_g++;
+    if (ndev == 0 || (1u << lg_g) != ndev || lg_g > 3)
+        return rust_err(-(int)cudaErrorInvalidValue, "ntt_sharded: 1, 2, 4 or 8 chunks");
+    if (direction < 0 || direction > 1 || lg > (uint32_t)F::MAX_LG || lg > 30 || lg < 2 * lg_g || lg == 0)
+        return rust_err(-(int)cudaErrorInvalidValue, "ntt_sharded: bad direction / lg_domain_size");
+    int home = 0;
+    (void)cudaGetDevice(&home);
+    const uint32_t s1 = ntt::slab_first_digit(lg, F::NTT_MAX_LG_R), s2 = lg - s1;
+    if (s1 < lg_g || s2 < lg_g) return rust_err(-(int)cudaErrorInvalidValue, "ntt_sharded: transform too small for this many chunks");
+    const size_t n1 = (size_t)1 << s1, n2 = (size_t)1 << s2, G = ndev, c = n2 / G, dd = n1 / G;
+    const size_t nloc = ((size_t)1 << lg) / G, blk = c * dd;
+    std::vector<T*> d_in(G, nullptr), d_stage(G, nullptr), d_recv(G, nullptr);
+    RustError result = rust_ok();
+    try {
+        bool distinct = true;
+        for (size_t a = 0; a < G; a++)
+            for (size_t b = a + 1; b < G; b++) distinct &= ids[a] != ids[b];
+        bool fused = distinct && G > 1 && getenv("SPPARK_B200_NTT_EXCHANGE_COPY") == nullptr;
+        for (size_t a = 0; a < G && fused; a++)
+            for (size_t b = 0; b < G && fused; b++) {
+                int ok = 0;
+                if (a != b) { CUDA_OK(cudaDeviceCanAccessPeer(&ok, ids[a], ids[b])); fused &= ok != 0; }
+            }
+        std::vector<const gpu_t*> gpus(G);
+        for (size_t r = 0; r < G; r++) gpus[r] = &select_gpu(ids[r]);
+        std::vector<std::unique_ptr<event_t>> staged(G), landed(G);
+        for (size_t r = 0; r < G; r++) {
+            gpus[r]->select();
+            if (fused)
+                for (size_t q = 0; q < G; q++)
+                    if (q != r) {
+                        cudaError_t e = cudaDeviceEnablePeerAccess(ids[q], 0);
+                        if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+                        else CUDA_OK(e);
+                    }
+            const stream_t& st = (*gpus[r])[0];
+            // plain cudaMalloc: allocations of the stream-ordered pool are not visible to peers
+            CUDA_OK(cudaMalloc((void**)&d_in[r], nloc * sizeof(T)));
+            CUDA_OK(cudaMalloc((void**)&d_recv[r], nloc * sizeof(T)));
+            if (!fused) CUDA_OK(cudaMalloc((void**)&d_stage[r], nloc * sizeof(T)));
+            staged[r].reset(new event_t());
+            landed[r].reset(new event_t());
+            // column slab r of the [N1][N2] matrix -> dense [N1][N2/G]
+            st.HtoD2D(d_in[r], c * sizeof(T), (const T*)inout + r * c, n2 * sizeof(T), c * sizeof(T), n1);
+        }
+        if (fused) {
+            // receive buffers must exist before any peer writes into them
+            for (size_t r = 0; r < G; r++) { gpus[r]->select(); landed[r]->record((*gpus[r])[0]); }
+            std::vector<void*> peers(G);
+            for (size_t q = 0; q < G; q++) peers[q] = d_recv[q];
+            for (size_t r = 0; r < G; r++) {
+                gpus[r]->select();
+                const stream_t& st = (*gpus[r])[0];
+                for (size_t q = 0; q < G; q++) if (q != r) landed[q]->wait(st);
+                N::slab_pass(*gpus[r], 1, d_in[r], nullptr, lg, lg_g, (uint32_t)r, (typename N::Direction)direction, st, peers.data());
+                staged[r]->record(st);
+            }
+        } else {
+            for (size_t r = 0; r < G; r++) {
+                gpus[r]->select();
+                const stream_t& st = (*gpus[r])[0];
+                N::slab_pass(*gpus[r], 1, d_in[r], d_stage[r], lg, lg_g, (uint32_t)r, (typename N::Direction)direction, st);
+                staged[r]->record(st);
+            }
+            // block q of sender g's staging -> block g of receiver q, on the receiver's stream
+            for (size_t q = 0; q < G; q++) {
+                gpus[q]->select();
+                const stream_t& st = (*gpus[q])[0];
+                for (size_t g = 0; g < G; g++) {
+                    staged[g]->wait(st);
+                    if (ids[g] == ids[q])
+                        CUDA_OK(cudaMemcpyAsync(d_recv[q] + g * blk, d_stage[g] + q * blk, blk * sizeof(T), cudaMemcpyDeviceToDevice, st));
+                    else
+                        CUDA_OK(cudaMemcpyPeerAsync(d_recv[q] + g * blk, ids[q], d_stage[g] + q * blk, ids[g], blk * sizeof(T), st));
+                }
+            }
+        }
+        for (size_t q = 0; q < G; q++) {
+            gpus[q]->select();
+            const stream_t& st = (*gpus[q])[0];
+            if (fused) for (size_t g = 0; g < G; g++) if (g != q) staged[g]->wait(st);
+            // the input slab is dead by now: it is the scratch of a multi-pass second stage
+            N::slab_pass(*gpus[q], 2, d_recv[q], d_in[q], lg, lg_g, (uint32_t)q, (typename N::Direction)direction, st);
+            // [N2][N1/G] -> columns q*N1/G.. of the [N2][N1] result, i.e. X[k1 + N1*k2]
+            CUDA_OK(cudaMemcpy2DAsync((T*)inout + q * dd, n1 * sizeof(T), d_recv[q], dd * sizeof(T), dd * sizeof(T), n2,
+                                      cudaMemcpyDeviceToHost, st));
+        }
+        for (size_t r = 0; r < G; r++) { gpus[r]->select(); (*gpus[r])[0].sync(); }
+    } catch (const cuda_error& e) {
+        result = rust_err(e.code(), e.what());
+    } catch (const std::exception& e) {
+        result = rust_err(-1, e.what());
+    }
+    for (size_t r = 0; r < G; r++) {
+        if (cudaSetDevice(ids[r]) != cudaSuccess) continue;
+        if (result.code != 0) (void)cudaDeviceSynchronize();
+        (void)cudaFree(d_in[r]);
+        (void)cudaFree(d_stage[r]);
+        (void)cudaFree(d_recv[r]);
+    }
+    (void)cudaSetDevice(home);
+    return result;
+}
+
+extern "C" RustError sppark_b200_ntt_sharded(int field, void* inout, uint32_t lg_domain_size, int ntt_direction,
+                                             const int* device_ids, size_t ndev)
+{
+    if (inout == nullptr || device_ids == nullptr)
+        return rust_err(-(int)cudaErrorInvalidValue, "ntt_sharded: null argument");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return rust_err(-(int)cudaErrorNoDevice, "ntt_sharded: no CUDA device");
+    for (size_t i = 0; i < ndev; i++)
+        if (device_ids[i] < 0 || device_ids[i] >= count)
+            return rust_err(-(int)cudaErrorInvalidDevice, "ntt_sharded: no such device");
+    switch (field) {
+    case SPPARK_FIELD_GL64: return ntt_sharded<gl64>(inout, lg_domain_size, ntt_direction, device_ids, ndev);
+    case SPPARK_FIELD_BB31: return ntt_sharded<bb31>(inout, lg_domain_size, ntt_direction, device_ids, ndev);
+    case SPPARK_FIELD_BLS12_381_FR: return ntt_sharded<ff::bls12_381_fr_ntt>(inout, lg_domain_size, ntt_direction, device_ids, ndev);
+    case SPPARK_FIELD_PALLAS_FR: return ntt_sharded<ff::pallas_fr_ntt>(inout, lg_domain_size, ntt_direction, device_ids, ndev);
+    case SPPARK_FIELD_VESTA_FR: return ntt_sharded<ff::vesta_fr_ntt>(inout, lg_domain_size, ntt_direction, device_ids, ndev);
+    case SPPARK_FIELD_BN254_FR: return ntt_sharded<ff::bn254_fr_ntt>(inout, lg_domain_size, ntt_direction, device_ids, ndev);
+    case SPPARK_FIELD_BLS12_377_FR: return ntt_sharded<ff::bls12_377_fr_ntt>(inout, lg_domain_size, ntt_direction, device_ids, ndev);
+    default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_ntt_sharded: unknown field");
     }
 }
 

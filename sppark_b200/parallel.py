@@ -243,3 +243,31 @@ def ntt_slab_p2p(local, lg_n, field, rank, peers, scratch, inverse=False):
     _lib.check(_lib.lib().sppark_b200_ntt_slab_pass(field, 2, recv.data_ptr(), scratch.data_ptr(), lg_n, lg_g, rank,
                                                      int(inverse), stream))
     return recv
+
+
+# ------------------------------------------------------- single-process entry points of the C ABI
+def msm_sharded_c(curve, points, scalars, device_ids, mont=False):
+    """sppark_b200_msm_sharded: one MSM cut into len(device_ids) point-chunks, chunk i on GPU
+    device_ids[i] of THIS process (host arrays in, Jacobian words out)."""
+    import ctypes as C
+    from . import _lib, msm
+    points = np.ascontiguousarray(points)
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
+    ids = (C.c_int * len(device_ids))(*device_ids)
+    out = np.zeros(3 * msm._LIMBS[curve], dtype=np.uint64)
+    stride = points.strides[0]
+    _lib.check(_lib.lib().sppark_b200_msm_sharded(curve, out.ctypes.data, points.ctypes.data, points.shape[0],
+                                                  scalars.ctypes.data, stride, int(mont), ids, len(device_ids)))
+    return out
+
+
+def ntt_sharded_c(inout, device_ids, inverse=False, field=None):
+    """sppark_b200_ntt_sharded: in-place NN transform of a host array, slab-sharded over the GPUs
+    device_ids of THIS process (1, 2, 4 or 8 of them)."""
+    import ctypes as C
+    from . import _lib, ntt
+    if field is None:
+        field = ntt._field_of(inout)
+    n = inout.size if field in (ntt.GL64, ntt.BB31) else inout.shape[0]
+    ids = (C.c_int * len(device_ids))(*device_ids)
+    _lib.check(_lib.lib().sppark_b200_ntt_sharded(field, inout.ctypes.data, n.bit_length() - 1, int(inverse), ids, len(device_ids)))

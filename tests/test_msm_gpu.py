@@ -396,3 +396,24 @@ def test_no_serialised_buckets(oracle, kind):
     folded = np.array([_limbs(v % R_BLS, 4) for v in ints], dtype=np.uint64)
     want = oracle.msm("bls12_381", base.cpu().numpy().view(np.uint64), folded, "pippenger", ncpus=8)
     assert _same_point(oracle, "bls12_381", got, want)
+
+
+@pytest.mark.parametrize("curve,cid", [("bls12_381", 0), ("pallas", 1)])
+def test_msm_sharded_c_abi(oracle, curve, cid):
+    """sppark_b200_msm_sharded (single process, C ABI): chunks on device 0 one after the other, and
+    on every visible device when there are several; same group element as the one-device call."""
+    import torch
+    from sppark_b200 import msm, parallel
+    n = 50000
+    r = R_BLS if curve == "bls12_381" else oracle.ff_consts("vesta_fp")["p"]
+    base = oracle.gen_points(curve, 512)
+    pts = base[np.arange(n) % 512].copy()
+    pts[7] = 0
+    sc = _scalars(n, 77, r)
+    want = msm.msm(cid, pts, sc)
+    for ids in ([0], [0, 0, 0], list(range(torch.cuda.device_count()))):
+        got = parallel.msm_sharded_c(cid, pts, sc, ids)
+        assert _same_point(oracle, curve, got, want), ids
+    # ragged: fewer points than chunks
+    got = parallel.msm_sharded_c(cid, pts[:2], sc[:2], [0, 0, 0, 0])
+    assert _same_point(oracle, curve, got, msm.msm(cid, pts[:2], sc[:2]))

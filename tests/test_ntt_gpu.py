@@ -439,3 +439,38 @@ def test_both_pass_kernels_at_every_size_class(oracle, field, knob, sizes, monke
                 y = x.copy()
                 (ntt.iNTT if inverse else ntt.NTT)(0, y, order)
                 assert np.array_equal(y, ofn(x, order, inverse, nthreads=8)), (field, knob, lg, order, inverse)
+
+
+@pytest.mark.parametrize("field", ["gl64", "bb31"])
+@pytest.mark.parametrize("chunks", [1, 2, 4, 8])
+def test_ntt_sharded_c_abi_on_one_device(oracle, field, chunks):
+    """sppark_b200_ntt_sharded (single process, C ABI): every chunk on device 0, so the exchange
+    runs as block copies; bit-exact against the oracle, forward and inverse, including sizes whose
+    second stage takes several passes."""
+    from sppark_b200 import parallel
+    ofn = oracle.ntt_gl64 if field == "gl64" else oracle.ntt_bb31
+    for lg in (6, 13, 20) + ((25,) if chunks == 8 and field == "bb31" else ()):
+        x = _rand(field, 1 << lg, 40 + lg)
+        y = x.copy()
+        parallel.ntt_sharded_c(y, [0] * chunks)
+        assert np.array_equal(y, ofn(x, 0, False, nthreads=8)), (field, chunks, lg)
+        parallel.ntt_sharded_c(y, [0] * chunks, inverse=True)
+        assert np.array_equal(y, x), (field, chunks, lg, "inverse")
+
+
+def test_ntt_sharded_c_abi_across_devices(oracle):
+    """Fused exchange (NVLink peer stores) when this box has at least two GPUs that see each other."""
+    import torch
+    from sppark_b200 import parallel
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("one GPU")
+    g = 1 << (min(ndev, 8).bit_length() - 1)
+    for field, ofn in (("gl64", oracle.ntt_gl64), ("bb31", oracle.ntt_bb31)):
+        for lg in (13, 22):
+            x = _rand(field, 1 << lg, 60 + lg)
+            y = x.copy()
+            parallel.ntt_sharded_c(y, list(range(g)))
+            assert np.array_equal(y, ofn(x, 0, False, nthreads=8)), (field, lg)
+            parallel.ntt_sharded_c(y, list(range(g)), inverse=True)
+            assert np.array_equal(y, x)
