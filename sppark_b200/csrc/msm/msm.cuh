@@ -320,6 +320,14 @@ public:
         size_t pair_bound;          // most pair sums one slice can produce
         uint32_t pair_threads;      // threads per forward/backward launch (PAIR_K outputs each)
         uint32_t *counts1, *off1, *wintotal, *winbase, *sums, *pre, *totals;
+        // the scratch blob (several GB at 2^26) is released on every exit path, also when a CUDA
+        // call between begin() and finish() throws
+        cudaStream_t owner;
+        Job() : blob(nullptr), owner(nullptr) {}
+        Job(const Job&) = delete;
+        Job& operator=(const Job&) = delete;
+        Job(Job&& o) noexcept { memcpy((void*)this, (const void*)&o, sizeof(Job)); o.blob = nullptr; }
+        ~Job() { if (blob) (void)cudaFreeAsync(blob, owner); }
     };
 
     // total_points fixes the window width; slice_cap is the most points one slice() call may carry
@@ -362,6 +370,7 @@ public:
             o_tot = take((size_t)j.pair_threads * F::N * 4);
         }
         CUDA_OK(cudaMallocAsync((void**)&j.blob, off, stream));
+        j.owner = stream;
         auto U32 = [&](size_t o) { return reinterpret_cast<uint32_t*>(j.blob + o); };
         j.counts = U32(o_counts); j.offsets = U32(o_offsets); j.cursor = U32(o_cursor);
         j.ctrl = U32(o_ctrl); j.heavy_list = U32(o_heavy); j.chunk_map = U32(o_cmap);

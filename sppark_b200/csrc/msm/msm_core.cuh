@@ -57,6 +57,11 @@ struct Digits {
 #else
         for (int i = 0; i < 8; i++) s[i] = p[i];
 #endif
+        // Bit 255 is ignored, as the reference ignores every bit from `nbits` up
+        // (msm/pippenger.cuh:33-70, nbits = 255 or less for all supported scalar fields): with it
+        // cleared the top window can never carry out, also when the window width divides 256, so
+        // un-reduced inputs give a deterministic result instead of one that depends on npoints.
+        s[7] &= 0x7fffffffu;
     }
     // windows must be requested in order w = 0, 1, ...; returns bucket (|d|-1) and sign,
     // or false for a zero digit

@@ -54,6 +54,8 @@ RustError msm_host(void* out, const void* points, size_t npoints, const void* sc
         if (npoints == 0) { memset(out, 0, JB); return rust_ok(); }
         if (!resident && stride < PB + (has_flag ? 1 : 0))
             return rust_err(-(int)cudaErrorInvalidValue, "msm: affine stride too small");
+        if (!resident && stride % 4 != 0)        // rows are packed on the device with 32-bit loads
+            return rust_err(-(int)cudaErrorInvalidValue, "msm: affine stride must be a multiple of 4 bytes");
         const stream_t &compute = gpu[0], &copy = gpu[1];
         const bool packed = resident || (stride == PB && !has_flag);
 
@@ -175,6 +177,8 @@ RustError msm_preload(const void* points, size_t npoints, size_t stride, bool ha
         gpu.select();
         if (stride < PB + (has_flag ? 1 : 0))
             return rust_err(-(int)cudaErrorInvalidValue, "msm: affine stride too small");
+        if (stride % 4 != 0)
+            return rust_err(-(int)cudaErrorInvalidValue, "msm: affine stride must be a multiple of 4 bytes");
         if (npoints >= (1ull << 31))
             return rust_err(-(int)cudaErrorInvalidValue, "msm: npoints must be < 2^31");
         const stream_t& copy = gpu[1];
@@ -222,12 +226,11 @@ RustError msm_dev(void* out, const void* d_points, size_t npoints, const void* d
     try {
         const gpu_t& gpu = gpu_of_current_device();
         cudaStream_t s = (cudaStream_t)stream;
-        uint32_t* d_out;
-        CUDA_OK(cudaMallocAsync((void**)&d_out, JB, s));
+        const stream_t borrowed(s);
+        dev_ptr_t<uint32_t> d_out(JB / 4, borrowed);           // released on every exit path
         msm::msm_t<F> m(gpu);
         m.invoke_dev(d_out, (const uint32_t*)d_points, npoints, (const uint32_t*)d_scalars, s);
         CUDA_OK(cudaMemcpyAsync(out, d_out, JB, cudaMemcpyDeviceToHost, s));
-        CUDA_OK(cudaFreeAsync(d_out, s));
         CUDA_OK(cudaStreamSynchronize(s));
     } catch (const cuda_error& e) {
         memset(out, 0, JB);

@@ -41,7 +41,7 @@ def msm_sharded(local_msm, combine, partial_words, device=None):
 
 
 # ---------------------------------------------------------------------------------- NTT
-_MAX_LG_R = {0: 12, 1: 12, 2: 11, 3: 11, 4: 11}       # F::NTT_MAX_LG_R per field id (csrc/ff/*.cuh)
+_MAX_LG_R = {0: 12, 1: 12, 2: 11, 3: 11, 4: 11, 5: 11, 6: 11}       # F::NTT_MAX_LG_R per field id (csrc/ff/*.cuh)
 
 
 def slab_first_digit(lg_n, field=0, s1=None):

@@ -417,3 +417,25 @@ def test_msm_sharded_c_abi(oracle, curve, cid):
     # ragged: fewer points than chunks
     got = parallel.msm_sharded_c(cid, pts[:2], sc[:2], [0, 0, 0, 0])
     assert _same_point(oracle, curve, got, msm.msm(cid, pts[:2], sc[:2]))
+
+
+def test_scalar_bit_255_is_ignored_and_odd_strides_are_rejected(oracle):
+    """Bits from nbits = 255 up are ignored, as in the reference's digit extraction
+    (msm/pippenger.cuh:33-70): a scalar with bit 255 set gives the result of the scalar without it,
+    whatever window width npoints selects.  Row strides that are not a multiple of 4 bytes are an
+    argument error, not a device fault."""
+    from sppark_b200 import _lib, msm
+    for n in (100, 1 << 20):                          # c = 16 divides 256 around 2^20 points
+        base = oracle.gen_points("bls12_381", 64)
+        pts = base[np.arange(n) % 64].copy()
+        sc = _scalars(n, 5 + n)
+        hi = sc.copy()
+        hi[::3, 3] |= np.uint64(1 << 63)
+        assert _same_point(oracle, "bls12_381", msm.multi_scalar_mult(pts, hi), msm.multi_scalar_mult(pts, sc)), n
+    raw = np.zeros(97 * 8 + 8, dtype=np.uint8)
+    out = np.zeros(18, dtype=np.uint64)
+    sc = _scalars(8, 1)
+    err = _lib.lib().mult_pippenger_inf(out.ctypes.data, raw.ctypes.data, 8, sc.ctypes.data, 97)
+    assert err.code != 0
+    if err.message:
+        _lib.lib().drop_error_message(err.message)
