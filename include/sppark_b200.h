@@ -132,6 +132,15 @@ RustError sppark_b200_ntt_dev(int field, void *d_inout, uint32_t lg_domain_size,
 RustError sppark_b200_lde(int field, size_t device_id, void *inout, uint32_t lg_domain_size,
                           uint32_t lg_blowup, void *aux_out);
 
+/* The device-pointer halves of the same step, NTT::LDE_powers / NTT::LDE_expand
+ * (ntt/ntt.cuh:352-365), enqueued on `stream`, not synchronised:
+ *   lde_powers: d_inout[i] *= group_gen^bitrev(i), i < 2^lg (coefficients in bit-reversed order);
+ *   lde_expand: d_out[i << lg_blowup] = d_in[i], zero elsewhere (no coset shift); d_in may be the
+ *               tail of d_out, as the reference allows. */
+RustError sppark_b200_lde_powers_dev(int field, void *d_inout, uint32_t lg_domain_size, void *stream);
+RustError sppark_b200_lde_expand_dev(int field, void *d_out, const void *d_in, uint32_t lg_domain_size,
+                                     uint32_t lg_blowup, void *stream);
+
 /* Slab-sharded NTT over G = 2^lg_g GPUs with ONE all-to-all (new; the reference has no multi-GPU
  * path).  N = N1 x N2, N1 = 2^ceil(lg/2).  Rank r owns input columns x[j1*N2 + j2],
  * j2 in [r*N2/G, (r+1)*N2/G), as a row-major [N1][N2/G] device array, and ends with the output

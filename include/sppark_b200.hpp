@@ -8,7 +8,7 @@
 //                               ec/xyzz_t.hpp:14-101)
 //   mult_pippenger<bucket_t>() msm/pippenger.cuh:730-747
 //   msm_t<...>::invoke()       msm/pippenger.cuh:351-395,448-571 (host-pointer overloads)
-//   NTT::Base / Base_dev_ptr / LDE / LDE_aux, InputOutputOrder, Direction, Type
+//   NTT::Base / Base_dev_ptr / LDE / LDE_aux / LDE_powers / LDE_expand, InputOutputOrder, Direction, Type
 //                              ntt/ntt.cuh:33-36,216-244,283-350
 //   gpu_t, stream_t, select_gpu(), ngpus(), cuda_available()   util/gpu_t.cuh:20-24,57-267
 // The value types are LAYOUT types (the bytes that cross the boundary); arithmetic happens on the
@@ -238,5 +238,10 @@ public:
     }
     static RustError LDE(const gpu_t& gpu, fr_t* inout, uint32_t lg_domain_size, uint32_t lg_blowup)
     {   return LDE_aux(gpu, inout, lg_domain_size, lg_blowup);   }
+    // device-pointer halves (ntt/ntt.cuh:352-365; errors are returned, not thrown)
+    static RustError LDE_powers(stream_t& stream, fr_t* d_inout, uint32_t lg_domain_size)
+    {   return sppark_b200_lde_powers_dev(fr_t::ntt_field, d_inout, lg_domain_size, (void*)stream);   }
+    static RustError LDE_expand(stream_t& stream, fr_t* d_out, fr_t* d_in, uint32_t lg_domain_size, uint32_t lg_blowup)
+    {   return sppark_b200_lde_expand_dev(fr_t::ntt_field, d_out, d_in, lg_domain_size, lg_blowup, (void*)stream);   }
 };
 #endif

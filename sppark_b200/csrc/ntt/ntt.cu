@@ -31,7 +31,7 @@ static bool try_static(const Pass& d, const Tables<F>& tb, const typename F::T* 
     CUDA_OK(cudaGetDevice(&dev));
     static bool attr_done[64];
     if (!attr_done[dev & 63]) {
-        CUDA_OK(cudaFuncSetAttribute(pass_kernel_static<F, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CUDA_OK(cudaFuncSetAttribute(pass_kernel_static<F, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));   // + the static mbarrier word <= 227 KiB
         attr_done[dev & 63] = true;
     }
     // one CTA per SM (a tile fills the shared memory), each walking ntiles / grid tiles
@@ -161,6 +161,39 @@ static RustError lde_host(size_t device_id, void* inout, uint32_t lg, uint32_t l
         return rust_err(-1, e.what());
     }
 }
+
+template<class F>
+static RustError lde_dev(int what, void* d_out, const void* d_in, uint32_t lg, uint32_t lg_blowup, void* stream)
+{
+    try {
+        const gpu_t& gpu = gpu_of_current_device();
+        if (what == 0) ntt::NTT<F>::LDE_powers(gpu, (cudaStream_t)stream, (typename F::T*)d_out, lg);
+        else ntt::NTT<F>::LDE_expand(gpu, (cudaStream_t)stream, (typename F::T*)d_out, (const typename F::T*)d_in, lg, lg_blowup);
+        return rust_ok();
+    } catch (const cuda_error& e) {
+        return rust_err(e.code(), e.what());
+    } catch (const std::exception& e) {
+        return rust_err(-1, e.what());
+    }
+}
+static RustError lde_dev_any(int field, int what, void* d_out, const void* d_in, uint32_t lg, uint32_t lb, void* stream)
+{
+    switch (field) {
+    case SPPARK_FIELD_GL64: return lde_dev<gl64>(what, d_out, d_in, lg, lb, stream);
+    case SPPARK_FIELD_BB31: return lde_dev<bb31>(what, d_out, d_in, lg, lb, stream);
+    case SPPARK_FIELD_BLS12_381_FR: return lde_dev<ff::bls12_381_fr_ntt>(what, d_out, d_in, lg, lb, stream);
+    case SPPARK_FIELD_PALLAS_FR: return lde_dev<ff::pallas_fr_ntt>(what, d_out, d_in, lg, lb, stream);
+    case SPPARK_FIELD_VESTA_FR: return lde_dev<ff::vesta_fr_ntt>(what, d_out, d_in, lg, lb, stream);
+    case SPPARK_FIELD_BN254_FR: return lde_dev<ff::bn254_fr_ntt>(what, d_out, d_in, lg, lb, stream);
+    case SPPARK_FIELD_BLS12_377_FR: return lde_dev<ff::bls12_377_fr_ntt>(what, d_out, d_in, lg, lb, stream);
+    default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_lde_*_dev: unknown field");
+    }
+}
+extern "C" RustError sppark_b200_lde_powers_dev(int field, void* d_inout, uint32_t lg, void* stream)
+{   return lde_dev_any(field, 0, d_inout, nullptr, lg, 0, stream);   }
+extern "C" RustError sppark_b200_lde_expand_dev(int field, void* d_out, const void* d_in, uint32_t lg,
+                                                uint32_t lg_blowup, void* stream)
+{   return lde_dev_any(field, 1, d_out, d_in, lg, lg_blowup, stream);   }
 
 extern "C" RustError sppark_b200_lde(int field, size_t device_id, void* inout, uint32_t lg, uint32_t lg_blowup, void* aux_out)
 {

@@ -43,11 +43,19 @@ pass_kernel_static(const Pass d, const Tables<F> tb, const typename F::T* in, ty
     constexpr uint32_t nthreads = (R >= LG_EPT ? (1u << (R - LG_EPT)) : 1u) << K::lg_w();
     const K k(d);
 
-    // persistent CTAs: the sub-NTT twiddles are staged into shared memory once per CTA, not
-    // once per tile (they are a quarter of a tile's bytes)
-    phase_twiddles<F>(k, tb, smem, tid, nthreads);
+    // persistent CTAs: the sub-NTT twiddles (2^R words, a quarter of a tile's bytes) are staged into
+    // shared memory once per CTA, by ONE bulk asynchronous copy (TMA, cp.async.bulk) that runs
+    // while the first tile is being loaded; every thread waits on the copy's mbarrier before the
+    // first butterfly step
+    __shared__ uint64_t tw_bar;
+    typename F::T* tw_dst = smem + (col_stride(R) << K::lg_w());
+    if (tid == 0) mbar_init(&tw_bar, 1);
+    __syncthreads();
+    if (tid == 0) tma_load_1d(tw_dst, tb.dense, (uint32_t)(sizeof(typename F::T) << R), &tw_bar);
+    bool tw_pending = true;
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         phase_load<F>(k, d, tb, in, smem, t, tid, nthreads);
+        if (tw_pending) { mbar_wait(&tw_bar, 0); tw_pending = false; }
         __syncthreads();
 #pragma unroll
         for (uint32_t s = 0; s < step_count<F>(R); s++) {
@@ -141,9 +149,19 @@ __global__ void coset_kernel(typename F::T* data, uint32_t lg_n, bool bitrev,
 // bit-reversed order (the output of an NR inverse transform); out[i << lg_blowup] = in[i] *
 // g^bitrev(i), every other slot of the (n << lg_blowup)-element array is zero -- i.e. the
 // coefficients of P(g*x) in the bit-reversed order of the extended domain.
+// out[brev(i)] = in[i]: the natural-order copy of a bit-reversed array (LDE_aux's coefficients)
+template<class F>
+__global__ void bitrev_copy_kernel(typename F::T* out, const typename F::T* in, uint32_t lg_n)
+{
+    const size_t n = (size_t)1 << lg_n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[brev32((uint32_t)i, lg_n)] = in[i];
+}
+
 template<class F>
 __global__ void lde_spread_kernel(typename F::T* out, const typename F::T* in, uint32_t lg_n, uint32_t lg_blowup,
-                                  const typename F::T* g0, const typename F::T* g1, const typename F::T* g2)
+                                  const typename F::T* g0, const typename F::T* g1, const typename F::T* g2,
+                                  bool shift = true)
 {
     typedef typename F::T T;
     const size_t n_ext = (size_t)1 << (lg_n + lg_blowup);
@@ -153,9 +171,12 @@ __global__ void lde_spread_kernel(typename F::T* out, const typename F::T* in, u
         T x = zero;
         if ((i & mask) == 0) {
             uint32_t src = (uint32_t)(i >> lg_blowup), e = brev32(src, lg_n);
-            x = F::mul(F::load(in[src]), g0[e & 4095]);
-            if (e >> 12) x = F::mul(x, g1[(e >> 12) & 4095]);
-            if (e >> 24) x = F::mul(x, g2[e >> 24]);
+            x = F::load(in[src]);
+            if (shift) {
+                x = F::mul(x, g0[e & 4095]);
+                if (e >> 12) x = F::mul(x, g1[(e >> 12) & 4095]);
+                if (e >> 24) x = F::mul(x, g2[e >> 24]);
+            }
             x = F::canon(x);
         }
         out[i] = x;
@@ -187,10 +208,11 @@ private:
         if (it != cache.end()) return *reinterpret_cast<Tables<F>*>(it->second);
 
         const uint32_t n_hi = lg_n > LG_TLO ? 1u << (lg_n - LG_TLO) : 1;
-        const size_t total = (1u << LG_DENSE) + (1u << LG_TLO) + n_hi + MID_WORDS;
+        const size_t total = (1u << LG_DENSE) + (1u << LG_TLO) + 512 + n_hi;
         T* blob;
         CUDA_OK(cudaMalloc(&blob, total * sizeof(T)));
-        T *dense = blob, *tlo = blob + (1u << LG_DENSE), *thi = tlo + (1u << LG_TLO), *mid = thi + n_hi;
+        // mid sits before thi: its sub-tables are sources of 16-byte aligned bulk copies
+        T *dense = blob, *tlo = blob + (1u << LG_DENSE), *mid = tlo + (1u << LG_TLO), *thi = mid + 512;
         uint32_t nthr = n_hi > 4096 ? n_hi : 4096;
         gen_tables_kernel<F><<<(nthr + 255) / 256, 256, 0, stream>>>(dense, tlo, thi, n_hi, lg_n, inverse);
         COUNT_LAUNCH();
@@ -395,12 +417,14 @@ public:
             dev_ptr_t<T> d_in(n, s), d_ext(n_ext, s);
             s.HtoD(d_in, inout, n * sizeof(T));
             NTT_internal(gpu, d_in, lg_n, InputOutputOrder::NR, Direction::inverse, Type::standard, s);
-            if (aux_out) {                                 // natural-order coefficients
+            if (aux_out) {
+                // natural-order coefficients = the bit-reversal of the NR inverse just computed
+                // (the reference: bit_rev(aux_data, domain_data), ntt/ntt.cuh:312-315)
                 dev_ptr_t<T> d_aux(n, s);
-                CUDA_OK(cudaMemcpyAsync(d_aux, d_in, n * sizeof(T), cudaMemcpyDeviceToDevice, s));
-                // bit-reversed -> natural = an RN round trip is overkill; redo the inverse as NN
-                s.HtoD(d_aux, inout, n * sizeof(T));
-                NTT_internal(gpu, d_aux, lg_n, InputOutputOrder::NN, Direction::inverse, Type::standard, s);
+                uint32_t bl = (uint32_t)std::min<size_t>((n + 255) / 256, (size_t)gpu.sm_count() * 16);
+                bitrev_copy_kernel<F><<<bl, 256, 0, s>>>(d_aux, d_in, lg_n);
+                COUNT_LAUNCH();
+                CUDA_OK(cudaGetLastError());
                 s.DtoH(aux_out, d_aux, n * sizeof(T));
                 s.sync();
             }
@@ -417,6 +441,38 @@ public:
             return rust_err(e.code(), e.what());
         }
         return rust_ok();
+    }
+
+    // NTT::LDE_powers (ntt/ntt.cuh:352-356): d_inout[i] *= group_gen^bitrev(i), device memory,
+    // enqueued on `stream`
+    static void LDE_powers(const gpu_t& gpu, cudaStream_t stream, T* d_inout, uint32_t lg_n)
+    {
+        if (lg_n > (uint32_t)F::MAX_LG || lg_n > 30)
+            throw cuda_error(-(int)cudaErrorInvalidValue, "LDE_powers: lg_domain_size out of range");
+        coset_scale(gpu, d_inout, lg_n, true, false, stream);
+    }
+    // NTT::LDE_expand (ntt/ntt.cuh:358-365): d_out[i << lg_blowup] = d_in[i], zero elsewhere, no
+    // coset shift; d_in is in bit-reversed order and may be the tail of d_out (then it is moved
+    // aside first: the reference reads everything before a grid-wide barrier, same effect)
+    static void LDE_expand(const gpu_t& gpu, cudaStream_t stream, T* d_out, const T* d_in, uint32_t lg_n,
+                           uint32_t lg_blowup)
+    {
+        const uint32_t lg_ext = lg_n + lg_blowup;
+        if (lg_ext > (uint32_t)F::MAX_LG || lg_ext > 30)
+            throw cuda_error(-(int)cudaErrorInvalidValue, "LDE_expand: lg_domain_size + lg_blowup out of range");
+        const size_t n = (size_t)1 << lg_n, n_ext = (size_t)1 << lg_ext;
+        const stream_t st(stream);
+        const bool overlap = d_in < d_out + n_ext && d_out < d_in + n;
+        std::unique_ptr<dev_ptr_t<T>> tmp;
+        if (overlap) {
+            tmp.reset(new dev_ptr_t<T>(n, st));
+            CUDA_OK(cudaMemcpyAsync(tmp->get(), d_in, n * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+            d_in = tmp->get();
+        }
+        uint32_t blocks = (uint32_t)std::min<size_t>((n_ext + 255) / 256, (size_t)gpu.sm_count() * 16);
+        lde_spread_kernel<F><<<blocks, 256, 0, stream>>>(d_out, d_in, lg_n, lg_blowup, nullptr, nullptr, nullptr, false);
+        COUNT_LAUNCH();
+        CUDA_OK(cudaGetLastError());
     }
 
     static void Base_dev_ptr(const gpu_t& gpu, cudaStream_t stream, T* d_inout, uint32_t lg_n,

@@ -133,6 +133,34 @@ HD uint32_t tw_column_value(const Pass& d, uint64_t pos0)
     return (d.tw_brev ? brev32(v, d.tw_bits) : v) + d.tw_col_offset;
 }
 
+#if defined(__CUDACC__)
+// ---- TMA (bulk asynchronous copy) of a twiddle table into shared memory -------------------------
+// One thread arms an mbarrier with the byte count and issues ONE cp.async.bulk (SASS: UBLKCP): the
+// copy engine of the SM moves the table while all threads go on (here: into the first tile load);
+// consumers wait on the barrier's phase before their first table read.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "MBAR_WAIT:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra MBAR_DONE;\n\t"
+                 "bra MBAR_WAIT;\n\t"
+                 "MBAR_DONE:\n\t}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
+
 // ---- phase 0: per-CTA copy of the sub-NTT twiddles into shared memory -------------
 template<class F, class K>
 HD void phase_twiddles(const K k, const Tables<F>& tb, typename F::T* smem,

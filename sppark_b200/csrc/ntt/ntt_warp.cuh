@@ -128,9 +128,13 @@ pass_kernel_warp(const Pass d, const Tables<F> tb, const typename F::T* __restri
     T* const xb = midsh + 16 * L + warp * warp_smem_words(R, CPT) + s * SS + l;
     T* const sb = midsh + 16 * L + warp * warp_smem_words(R, CPT) + CPT * XW + lane * CPT;
     if (R1 > 0) {
-        // twist table w_(2^R)^(l * k0) of this pass: once per persistent CTA
-        for (uint32_t i = threadIdx.x; i < 16 * L; i += blockDim.x) midsh[i] = tb.mid[mid_offset(R) + i];
+        // twist table w_(2^R)^(l * k0) of this pass: once per persistent CTA, one bulk asynchronous
+        // copy (TMA) signalled through an mbarrier
+        __shared__ uint64_t mid_bar;
+        if (threadIdx.x == 0) mbar_init(&mid_bar, 1);
         __syncthreads();
+        if (threadIdx.x == 0) tma_load_1d(midsh, tb.mid + mid_offset(R), (uint32_t)(16 * L * sizeof(T)), &mid_bar);
+        mbar_wait(&mid_bar, 0);
     }
 
     const uint32_t nunits = (ncols + SPW * CPT - 1) / (SPW * CPT);

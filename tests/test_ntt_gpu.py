@@ -474,3 +474,33 @@ def test_ntt_sharded_c_abi_across_devices(oracle):
             assert np.array_equal(y, ofn(x, 0, False, nthreads=8)), (field, lg)
             parallel.ntt_sharded_c(y, list(range(g)), inverse=True)
             assert np.array_equal(y, x)
+
+
+@pytest.mark.parametrize("field", ["gl64", "bb31"])
+def test_lde_device_entries_compose_to_the_host_lde(oracle, field):
+    """NTT::LDE_powers / LDE_expand on device memory (ntt/ntt.cuh:352-365): iNTT(NR), powers,
+    expand (in place: the coefficients sit at the tail of the extended buffer), NTT(RN) must equal
+    the one-call LDE, which is pinned against the reference's own recording."""
+    import torch
+    from sppark_b200 import _lib, ntt
+    l = _lib.lib()
+    fid, tdt = (0, torch.int64) if field == "gl64" else (1, torch.int32)
+    for lg, lb in ((5, 1), (10, 2), (14, 3)):
+        n, n_ext = 1 << lg, 1 << (lg + lb)
+        x = _rand(field, n, 500 + lg)
+        want, coeffs = ntt.LDE(0, x, lb, want_coefficients=True)
+        ext = torch.zeros(n_ext, dtype=tdt, device="cuda")
+        tail = ext[n_ext - n:]
+        tail.copy_(torch.from_numpy(x.view(np.int64 if field == "gl64" else np.int32)))
+        s = torch.cuda.current_stream().cuda_stream
+        _lib.check(l.sppark_b200_ntt_dev(fid, tail.data_ptr(), lg, ntt.NR, ntt.INVERSE, 0, s))
+        _lib.check(l.sppark_b200_lde_powers_dev(fid, tail.data_ptr(), lg, s))
+        _lib.check(l.sppark_b200_lde_expand_dev(fid, ext.data_ptr(), tail.data_ptr(), lg, lb, s))
+        _lib.check(l.sppark_b200_ntt_dev(fid, ext.data_ptr(), lg + lb, ntt.RN, ntt.FORWARD, 0, s))
+        torch.cuda.synchronize()
+        got = ext.cpu().numpy().view(x.dtype)
+        assert np.array_equal(got, want), (field, lg, lb)
+        # the natural-order coefficients of LDE_aux: inverse transform of the evaluations
+        y = x.copy()
+        ntt.iNTT(0, y, ntt.NN)
+        assert np.array_equal(coeffs, y), (field, lg, lb)
