@@ -8,6 +8,8 @@
 # include <ff/goldilocks.hpp>
 #elif defined(FEATURE_BABY_BEAR)
 # include <ff/baby_bear.hpp>
+#elif defined(FEATURE_BLS12_381)
+# include <ff/bls12-381.hpp>
 #endif
 #include <ntt/ntt.cuh>
 

@@ -439,3 +439,69 @@ def test_scalar_bit_255_is_ignored_and_odd_strides_are_rejected(oracle):
     assert err.code != 0
     if err.message:
         _lib.lib().drop_error_message(err.message)
+
+
+def test_bls12_381_msm_2pow26_equals_reference_gpu():
+    """BASELINE config 3 at full size: the same group element as the reference's own CUDA
+    mult_pippenger (oracle/_ref/libref_msm_gpu.so, its sources built for sm_100a) on 2^26 points,
+    compared with the library's own field arithmetic (cross-multiplied coordinates)."""
+    import ctypes as C
+    import os
+    import sys
+    import torch
+    from sppark_b200 import msm
+    path = os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libref_msm_gpu.so")
+    if not os.path.exists(path):
+        pytest.skip("reference GPU build not present")
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    import bench
+
+    class RE(C.Structure):
+        _fields_ = [("code", C.c_int), ("message", C.c_void_p)]
+    ref = C.CDLL(path)
+    ref.mult_pippenger.restype = RE
+    ref.mult_pippenger.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    n, m = 1 << 26, 1 << 16
+    base = msm.generate_points_dev(msm.BLS12_381_G1, m).cpu().numpy().view(np.uint64)
+    pts = np.empty((n, 12), dtype=np.uint64)
+    pts.reshape(n // m, m, 12)[:] = base
+    rng = np.random.default_rng(26)
+    sc = np.empty((n, 4), dtype=np.uint64)
+    for s in range(0, n, 1 << 22):
+        sc[s:s + (1 << 22)] = rng.integers(0, 2**64, size=(1 << 22, 4), dtype=np.uint64)
+    sc[:, 3] >>= np.uint64(2)
+    ours = msm.multi_scalar_mult(pts, sc)
+    theirs = np.zeros(18, dtype=np.uint64)
+    e = ref.mult_pippenger(theirs.ctypes.data, pts.ctypes.data, n, sc.ctypes.data)
+    assert e.code == 0
+    assert bench._jac_equal(ours, theirs, msm)
+    # and the size-independent property: folding the scalars onto the 2^16 distinct points
+    folded = bench.fold_scalars(sc, m)
+    small = msm.multi_scalar_mult(np.ascontiguousarray(base), folded)
+    assert bench._jac_equal(ours, small, msm)
+    del pts, sc
+    torch.cuda.empty_cache()
+
+
+def test_two_rank_nccl_bench_legs():
+    """One process per GPU over NCCL (the launch the driver uses), when this box has two GPUs:
+    sharded BLS12-381 and Pallas MSMs and the slab-sharded NTTs at reduced sizes; every leg's
+    self-check must say ok."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU")
+    root = os.path.join(os.path.dirname(__file__), "..")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "bench.py"),
+           "--gpus", "2", "--steps", "1", "--warmup", "3", "--lg-msm", "20", "--lg-ntt", "20", "--lg-pallas", "18", "--skip-cpu"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["n_gpus"] == 2 and line["check"].endswith("ok"), line["check"]
+    assert line["pallas_msm"]["check"].endswith("ok"), line["pallas_msm"]
+    assert line["e2e"]["same_result"] is True
+    assert line["ntt"]["value"] > 0 and line["ntt"]["babybear_2pow27"]["value"] > 0

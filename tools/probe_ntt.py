@@ -57,8 +57,14 @@ def main():
     flush = torch.zeros(64 << 20, dtype=torch.int32, device="cuda")      # 256 MiB > L2
     args = sys.argv[1:]
     fields = ["gl64"]
-    if args and args[0] in ("gl64", "bb31", "both"):
-        fields = ["gl64", "bb31"] if args[0] == "both" else [args[0]]
+    if args and args[0] in ("gl64", "bb31", "both", "bls12_381"):
+        if args[0] == "both":
+            # one reference library per process (their parameter statics are STB_GNU_UNIQUE symbols)
+            import subprocess
+            for f in ("gl64", "bb31"):
+                subprocess.check_call([sys.executable, os.path.abspath(__file__), f] + args[1:])
+            return
+        fields = [args[0]]
         args = args[1:]
     sizes = [int(a) for a in args] or [16, 20, 22, 24]
     l = _lib.lib()
@@ -69,9 +75,12 @@ def main():
             if field == "gl64":
                 host = rng.integers(0, GL_P, size=n, dtype=np.uint64)
                 view, fid, esz = np.int64, 0, 8
-            else:
+            elif field == "bb31":
                 host = rng.integers(0, BB_P, size=n, dtype=np.uint32)
                 view, fid, esz = np.int32, 1, 4
+            else:
+                host = rng.integers(0, 2**62, size=(n, 4), dtype=np.uint64)      # valid residues of BLS12-381 fr
+                view, fid, esz = np.int64, 2, 32
             bytes_alg = 2 * n * esz
             variants = [("warp", {}), ("block", {"SPPARK_B200_NTT_BLOCK": "1"})]
             if lg == 20:
