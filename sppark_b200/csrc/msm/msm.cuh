@@ -286,6 +286,176 @@ __global__ void finish_kernel(const Config cfg, const uint32_t* winR, uint32_t* 
     if (blockIdx.x == 0 && threadIdx.x == 0) finish_body<F>(cfg, winR, out);
 }
 
+// ---- finish on four lanes -------------------------------------------------------------------------
+// The Horner combination of the window sums is one dependent chain of nwins*c doublings; what can
+// run side by side are the multiplications INSIDE a point operation: a doubling (dbl-2008-s-1) is
+// three rounds of independent products {V = U^2, Q = X^2}, {W = UV, S = XV, M^2}, {M(S-X3), WY,
+// ZZ*V, ZZZ*W}, a full addition four.  Lanes 0..3 of one warp execute the shared ladder in
+// lock-step on different operands (one instruction stream, SIMD), values travel through a few
+// shared-memory slots: 3 ladder latencies per doubling instead of 9, 4 per addition instead of
+// 14 (2.4 ms -> under 1 ms at 2^26; the same group element as finish_body, which the CPU
+// single-stepper keeps running).
+template<class F> struct Par4 {
+    enum { sX, sY, sZZZ, sZZ, sA, sB, sC, sD, sE, sF, sG, sH, NS };
+    // slot i of the accumulator: its four coordinates first, then eight scratch values that
+    // several accumulators of one lane group may share
+    struct Slots {
+        F* pt;
+        F* tmp;
+        __device__ F& operator[](uint32_t i) const { return i < 4 ? pt[i] : tmp[i - 4]; }
+    };
+    Slots s;
+    uint32_t lane;
+    unsigned mask;                                          // the four lanes of this group
+    __device__ Par4(F* pt, F* tmp, uint32_t lane_, unsigned mask_ = 0xFu) : s{pt, tmp}, lane(lane_), mask(mask_) {}
+    __device__ void sync() const { __syncwarp(mask); }
+    __device__ ec::xyzz_t<F> get() const
+    {
+        ec::xyzz_t<F> p;
+        p.X = s[sX]; p.Y = s[sY]; p.ZZZ = s[sZZZ]; p.ZZ = s[sZZ];
+        return p;
+    }
+    __device__ void set_inf()
+    {
+        if (lane == 0) { s[sX] = F::zero(); s[sY] = F::zero(); s[sZZZ] = F::zero(); s[sZZ] = F::zero(); }
+        sync();
+    }
+    __device__ bool is_inf() const { return s[sZZZ].is_zero() && s[sZZ].is_zero(); }
+
+    // lane-wise choice of an operand: every lane then makes THE SAME call of the shared ladder (one
+    // instruction stream for the four products; a branch per lane would serialise them)
+    __device__ F pick(const F& a0, const F& a1, const F& a2, const F& a3) const
+    {
+        F r;
+#pragma unroll
+        for (int i = 0; i < F::N; i++)
+            r.l[i] = lane == 0 ? a0.l[i] : lane == 1 ? a1.l[i] : lane == 2 ? a2.l[i] : a3.l[i];
+        return r;
+    }
+    __device__ void put(uint32_t i0, uint32_t i1, uint32_t i2, uint32_t i3, const F& r)
+    {   s[lane == 0 ? i0 : lane == 1 ? i1 : lane == 2 ? i2 : i3] = r;   }
+
+    __device__ void dbl()
+    {
+        if (is_inf()) return;                               // same decision on all four lanes
+        const F U = s[sY].dbl(), X = s[sX];
+        F r = F::mul_shared(pick(U, X, X, X), pick(U, X, X, X));
+        put(sA, sB, sB, sB, r);                             // sA = V = U^2, sB = Q = X^2
+        sync();
+        const F V = s[sA];
+        F M = s[sB];
+        M = M.dbl() + M;
+        r = F::mul_shared(pick(U, X, M, M), pick(V, V, M, M));
+        put(sC, sD, sE, sE, r);                             // sC = W, sD = S, sE = M^2
+        sync();
+        const F W = s[sC], S = s[sD];
+        const F X3 = s[sE] - S - S;
+        const F Y = s[sY], ZZ = s[sZZ], ZZZ = s[sZZZ];
+        sync();                                             // everyone has read the old point
+        r = F::mul_shared(pick(M, W, ZZ, ZZZ), pick(S - X3, Y, V, W));
+        put(sF, sG, sZZ, sZZZ, r);
+        sync();
+        if (lane == 0) { s[sY] = s[sF] - s[sG]; s[sX] = X3; }
+        sync();
+    }
+
+    // point += p2 (both XYZZ); p2 in registers of every lane
+    __device__ void add(const ec::xyzz_t<F>& p2)
+    {
+        if (p2.is_inf()) return;
+        if (is_inf()) {
+            if (lane == 0) { s[sX] = p2.X; s[sY] = p2.Y; s[sZZZ] = p2.ZZZ; s[sZZ] = p2.ZZ; }
+            sync();
+            return;
+        }
+        const F X1 = s[sX], Y1 = s[sY], ZZZ1 = s[sZZZ], ZZ1 = s[sZZ];
+        F r = F::mul_shared(pick(X1, Y1, p2.X, p2.Y), pick(p2.ZZ, p2.ZZZ, ZZ1, ZZZ1));
+        put(sA, sB, sC, sD, r);                             // sA = U1, sB = S1, sC = U2, sD = S2
+        sync();
+        const F U1 = s[sA], S1 = s[sB];
+        const F P = s[sC] - U1, R = s[sD] - S1;
+        sync();
+        if (P.is_zero()) {                                  // same decision on all four lanes
+            if (R.is_zero()) dbl();
+            else { if (lane == 0) { s[sZZZ] = F::zero(); s[sZZ] = F::zero(); } sync(); }
+            return;
+        }
+        r = F::mul_shared(pick(P, R, ZZ1, ZZZ1), pick(P, R, p2.ZZ, p2.ZZZ));
+        put(sE, sF, sG, sH, r);                             // sE = PP, sF = RR, sG = ZZ1*ZZ2, sH = ZZZ1*ZZZ2
+        sync();
+        const F PP = s[sE], G = s[sG];
+        r = F::mul_shared(pick(P, U1, G, G), PP);
+        put(sA, sC, sZZ, sZZ, r);                           // sA = PPP, sC = Q, ZZ3
+        sync();
+        const F PPP = s[sA], Q = s[sC], H = s[sH];
+        const F X3 = s[sF] - PPP - Q - Q;
+        r = F::mul_shared(pick(R, S1, H, H), pick(Q - X3, PPP, PPP, PPP));
+        put(sD, sE, sZZZ, sZZZ, r);                         // T1, T2, ZZZ3
+        sync();
+        if (lane == 0) { s[sY] = s[sD] - s[sE]; s[sX] = X3; }
+        sync();
+    }
+};
+
+// combine level (see combine_body) with four lanes per item: the chains of a level are G x 3 full
+// additions long and there are only a few thousand items, so latency, not throughput, sets its
+// time; the additions run as four rounds of lane-parallel products
+template<class F>
+__global__ void __launch_bounds__(128)
+combine_par_kernel(const uint32_t* inR, const uint32_t* inS, uint32_t G, uint32_t lg_span,
+                   uint32_t nitems, uint32_t* outR, uint32_t* outS)
+{
+    __shared__ F sm[32][20];                                // per group: acc, weighted, rsum, 8 scratch
+    const uint32_t grp = threadIdx.x >> 2, lane = threadIdx.x & 3;
+    const uint32_t item = blockIdx.x * 32 + grp;
+    if (item >= nitems) return;                             // whole groups leave together
+    const unsigned mask = 0xFu << ((threadIdx.x & 31) & ~3u);
+    F* base = sm[grp];
+    Par4<F> acc(base, base + 12, lane, mask), weighted(base + 4, base + 12, lane, mask), rsum(base + 8, base + 12, lane, mask);
+    acc.set_inf();
+    weighted.set_inf();
+    rsum.set_inf();
+    const size_t first = (size_t)item * G;
+    for (uint32_t i = G; i-- > 0;) {
+        rsum.add(load_bucket<F>(inR, first + i));
+        acc.add(load_bucket<F>(inS, first + i));
+        if (i) weighted.add(acc.get());                     // sum_{i>=1} i*S_i
+    }
+    for (uint32_t d = 0; d < lg_span; d++) weighted.dbl();
+    rsum.add(weighted.get());
+    if (lane == 0) {
+        store_bucket<F>(outR, item, rsum.get());
+        store_bucket<F>(outS, item, acc.get());
+    }
+}
+
+template<class F>
+__global__ void __launch_bounds__(32)
+finish_par_kernel(const Config cfg, const uint32_t* winR, uint32_t* out_jacobian)
+{
+    __shared__ F slots[Par4<F>::NS];
+    if (threadIdx.x >= 4) return;
+    Par4<F> p(slots, slots + 4, threadIdx.x);
+    {
+        const ec::xyzz_t<F> top = load_bucket<F>(winR, cfg.nwins - 1);
+        if (p.lane == 0) { slots[Par4<F>::sX] = top.X; slots[Par4<F>::sY] = top.Y; slots[Par4<F>::sZZZ] = top.ZZZ; slots[Par4<F>::sZZ] = top.ZZ; }
+        p.sync();
+    }
+    for (uint32_t w = cfg.nwins - 1; w-- > 0;) {
+        for (uint32_t d = 0; d < cfg.wbits; d++) p.dbl();
+        p.add(load_bucket<F>(winR, w));
+    }
+    // XYZZ -> Jacobian (X*ZZ, Y*ZZZ, ZZ), canonical limbs; infinity -> all zero
+    const bool inf = p.is_inf();
+    const F ZZ = slots[Par4<F>::sZZ];
+    const F Yf = slots[Par4<F>::sY], ZZZf = slots[Par4<F>::sZZZ];
+    const F r = F::mul_shared(p.pick(slots[Par4<F>::sX], Yf, Yf, Yf), p.pick(ZZ, ZZZf, ZZZf, ZZZf));
+    if (p.lane < 2)
+        for (int k = 0; k < F::N; k++) out_jacobian[p.lane * F::N + k] = inf ? 0 : r.l[k];
+    if (p.lane == 2)
+        for (int k = 0; k < F::N; k++) out_jacobian[2 * F::N + k] = inf ? 0 : ZZ.l[k];
+}
+
 // host rows {X, Y, [flag]} at `stride` bytes -> packed {X, Y}; flagged rows become (0,0)
 // (reference: Affine_inf_t::mem_t, ec/affine_t.hpp:91-121; stream_t::HtoD pitch copy)
 static __global__ void pack_points_kernel(const uint8_t* in, size_t stride, uint32_t words, bool has_flag,
@@ -483,15 +653,20 @@ public:
                 uint32_t lg_g = 31 - __builtin_clz(per_win);
                 if (lg_g > 4) lg_g = 4;                         // radix 16 keeps the serial chains short
                 uint32_t G = 1u << lg_g, nitems = cfg.nwins * (per_win >> lg_g);
-                combine_kernel<F><<<(nitems + 127) / 128, 128, 0, stream>>>(j.R[cur], j.S[cur], G, lg_span, nitems,
-                                                                           j.R[cur ^ 1], j.S[cur ^ 1]);
+                if constexpr (F::N <= 12)
+                    combine_par_kernel<F><<<(nitems + 31) / 32, 128, 0, stream>>>(j.R[cur], j.S[cur], G, lg_span, nitems,
+                                                                                  j.R[cur ^ 1], j.S[cur ^ 1]);
+                else
+                    combine_kernel<F><<<(nitems + 127) / 128, 128, 0, stream>>>(j.R[cur], j.S[cur], G, lg_span, nitems,
+                                                                               j.R[cur ^ 1], j.S[cur ^ 1]);
                 COUNT_LAUNCH();
                 per_win >>= lg_g;
                 lg_span += lg_g;
                 cur ^= 1;
             }
             g_profile.mark("finish", stream);
-            finish_kernel<F><<<1, 32, 0, stream>>>(cfg, j.R[cur], d_out);
+            if constexpr (F::N <= 12) finish_par_kernel<F><<<1, 32, 0, stream>>>(cfg, j.R[cur], d_out);
+            else finish_kernel<F><<<1, 32, 0, stream>>>(cfg, j.R[cur], d_out);        // Fp2 (G2): one lane
             COUNT_LAUNCH();
             g_profile.mark("end", stream);
             CUDA_OK(cudaGetLastError());
