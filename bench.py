@@ -316,7 +316,7 @@ def main():
     # DRAM traffic of this kernel at 2^26 / c=20 from the committed `ncu --set full` capture
     # (profiles/msm_accumulate_r01.md: dram__bytes_read.sum + dram__bytes_write.sum per launch);
     # every point is gathered once per window, hence ~19x the algorithmic bytes
-    traffic = 174.7e9 if (args.lg_msm == 26 and world == 1) else None
+    traffic = 174.7e9 if (args.lg_msm == 26 and world == 1) else None      # profiles/msm_accumulate_r01.md (kernel unchanged)
     wide_mults = 2880.0 * phases_entries(n, world)          # 10 products x 288 IMAD.WIDE per mixed add
     imad_peak = 0.94 * 32 * 148 * 1.965e9                   # measured: tools/imad_bench.cu on this B200
     roofline = {"bound": "hbm", "kernel": "msm::accumulate_kernel", "achieved": achieved, "peak": peak,
@@ -683,12 +683,19 @@ def bench_ntt(args, torch, ntt, _lib, peak, peak_src, barrier, max_over_ranks, w
     worst = max(passes) if passes else ms
     res = {"metric": f"Goldilocks NTT/s @2^{lg} (NN, forward)", "value": world * 1e3 / ms, "unit": "NTT/s",
            "ms_per_ntt": ms, "scaling": "replicas", "iters": iters, "l2": "256 MiB write between iterations",
-           "roofline": {"bound": "hbm", "kernel": "ntt::pass_kernel<gl64> (slowest pass)",
+           "roofline": {"bound": "hbm", "kernel": "ntt::pass_kernel_static<gl64, 12 x 2> (slowest of the two block-tile passes)",
                         "achieved": alg / (worst * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": alg / (worst * 1e-3) / 1e9 / peak,
                         # dram__bytes_read.sum + dram__bytes_write.sum of that pass from the ncu --set full
-                        # capture (profiles/ntt_pass_r01.md: 134.5 MB + 89.4 MB), 2^24 only
-                        "traffic": 224.0e6 if lg == 24 else None, "peak_source": peak_src,
+                        # capture (profiles/ntt_block_r02.md, launch 0: 134.4 MB + 87.6 MB), 2^24 only
+                        "traffic": 222.1e6 if lg == 24 else None, "traffic_source": "profiles/ntt_block_r02.md",
+                        "peak_source": peak_src,
+                        # the binding resource is the INT32 ALU pipe, not HBM: the butterfly network alone
+                        # (tools/gl64_bfly_bench.cu, profiles/gl64_butterfly_microbench_r02.txt) needs 37.9
+                        # SMSP-cycles per butterfly at 90 % ALU-pipe utilisation
+                        "int32_alu": {"butterflies": n // 2 * lg, "dense_cycles_per_butterfly": 37.9,
+                                      "floor_ms": (n // 2 * lg / 32) * 37.9 / (148 * 4) / 1.965e6,
+                                      "frac": ((n // 2 * lg / 32) * 37.9 / (148 * 4) / 1.965e6) / ms},
                         "pass_ms": [round(p, 4) for p in passes],
                         "whole_transform_frac": alg / (ms * 1e-3) / 1e9 / peak}}
     # e2e: in place on the pinned host buffer through compute_ntt
