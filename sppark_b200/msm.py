@@ -149,18 +149,3 @@ def selftest_field(field, op, a, b):
                                                 a.shape[0], r.ctypes.data, a.ctypes.data, b.ctypes.data)
     _lib.check(err)
     return r
-
-
-def smoke():
-    """One tiny MSM on cuda:0 checked against the CPU oracle (used by __graft_entry__.smoke)."""
-    from oracle import pyoracle
-    rng = np.random.default_rng(7)
-    n = 1000
-    pts = pyoracle.gen_points("bls12_381", 64)[np.arange(n) % 64].copy()
-    sc = rng.integers(0, 2**63, size=(n, 4), dtype=np.uint64)
-    sc[:, 3] >>= np.uint64(2)
-    got = multi_scalar_mult(pts, sc)
-    want = pyoracle.msm("bls12_381", pts, sc, "pippenger", ncpus=4)
-    a = pyoracle.jac_to_affine("bls12_381", got)
-    b = pyoracle.jac_to_affine("bls12_381", want)
-    assert np.array_equal(a, b), "MSM mismatch vs oracle"
