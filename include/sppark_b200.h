@@ -141,6 +141,26 @@ RustError sppark_b200_lde_powers_dev(int field, void *d_inout, uint32_t lg_domai
 RustError sppark_b200_lde_expand_dev(int field, void *d_out, const void *d_in, uint32_t lg_domain_size,
                                      uint32_t lg_blowup, void *stream);
 
+/* ---- polynomial helpers ----------------------------------------------
+ * The reference's polynomial/ templates and ff/batch_inversion.hpp for the NTT fields above.  All
+ * arrays are DEVICE memory in the field's memory format (the format compute_ntt uses), the work is
+ * enqueued on `stream` and not synchronised; `len` is any size, not only a power of two.
+ *   prefix_op          polynomial/prefix_op.cuh:322-384: inclusive prefix, op 0 = Add, 1 = Multiply;
+ *                      d_out[i] = d_inp[0] (op) ... (op) d_inp[i]; d_out may be d_inp
+ *   div_by_x_minus_z   polynomial/div_by_x_minus_z.cuh:445-486: divide c[0] + c[1] x + ... by (x - z)
+ *                      in place; z is ONE element in HOST memory (the reference takes it by const
+ *                      reference); rotate == 0: d_inout[0] = remainder, d_inout[1..] = quotient,
+ *                      rotate != 0: d_inout[..len-2] = quotient, d_inout[len-1] = remainder
+ *   evaluate           polynomial/evaluate.cuh:308-414: d_ret[k] = sum_i d_coeffs[i] * d_x[k]^i, k < n
+ *   batch_inverse      ff/batch_inversion.hpp:14-51 over a whole array: d_out[i] = 1 / d_inp[i], and
+ *                      zero where d_inp[i] is zero; d_out may be d_inp */
+RustError sppark_b200_prefix_op_dev(int field, int op, void *d_out, const void *d_inp, size_t len, void *stream);
+RustError sppark_b200_div_by_x_minus_z_dev(int field, void *d_inout, size_t len, const void *z, int rotate,
+                                           void *stream);
+RustError sppark_b200_evaluate_dev(int field, void *d_ret, const void *d_x, size_t n, const void *d_coeffs,
+                                   size_t len, void *stream);
+RustError sppark_b200_batch_inverse_dev(int field, void *d_out, const void *d_inp, size_t len, void *stream);
+
 /* Slab-sharded NTT over G = 2^lg_g GPUs with ONE all-to-all (new; the reference has no multi-GPU
  * path).  N = N1 x N2, N1 = 2^ceil(lg/2).  Rank r owns input columns x[j1*N2 + j2],
  * j2 in [r*N2/G, (r+1)*N2/G), as a row-major [N1][N2/G] device array, and ends with the output

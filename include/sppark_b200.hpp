@@ -244,4 +244,28 @@ public:
     static RustError LDE_expand(stream_t& stream, fr_t* d_out, fr_t* d_in, uint32_t lg_domain_size, uint32_t lg_blowup)
     {   return sppark_b200_lde_expand_dev(fr_t::ntt_field, d_out, d_in, lg_domain_size, lg_blowup, (void*)stream);   }
 };
+
+// ---- polynomial/ and ff/batch_inversion.hpp -----------------------------------------------------------
+// Same names and argument order as the reference's templates (polynomial/prefix_op.cuh:17-45,322;
+// div_by_x_minus_z.cuh:445; evaluate.cuh:308,416); device arrays, enqueued on `s`.  The reference
+// returns void and throws cuda_error; the error is returned here.
+template<typename T_> struct Add { using T = T_; static constexpr int op = 0; };
+template<typename T_> struct Multiply { using T = T_; static constexpr int op = 1; };
+
+template<class Operation, typename T = typename Operation::T>
+inline RustError prefix_op(T* d_out, const T* d_inp, size_t len, stream_t& s)
+{   return sppark_b200_prefix_op_dev(T::ntt_field, Operation::op, d_out, d_inp, len, (void*)s);   }
+
+template<bool rotate = false, typename T>
+inline RustError div_by_x_minus_z(T d_inout[], size_t len, const T& z, stream_t& s)
+{   return sppark_b200_div_by_x_minus_z_dev(T::ntt_field, d_inout, len, &z, rotate, (void*)s);   }
+
+template<typename T>
+inline RustError evaluate(T d_ret[], const T d_x[], size_t n, const T d_coeffs[], size_t len, stream_t& s)
+{   return sppark_b200_evaluate_dev(T::ntt_field, d_ret, d_x, n, d_coeffs, len, (void*)s);   }
+
+// the array form of batch_inversion<T, N>() (ff/batch_inversion.hpp:14): one inversion per CTA
+template<typename T>
+inline RustError batch_inversion(T d_out[], const T d_inp[], size_t len, stream_t& s)
+{   return sppark_b200_batch_inverse_dev(T::ntt_field, d_out, d_inp, len, (void*)s);   }
 #endif

@@ -1,0 +1,142 @@
+// C-ABI entry points of the polynomial helpers (include/sppark_b200.h, "polynomial" block).
+// Device pointers in, work enqueued on the caller's stream -- the calling convention of the
+// reference's templates (polynomial/prefix_op.cuh:322, div_by_x_minus_z.cuh:445, evaluate.cuh:308),
+// which take device arrays and a stream_t.
+#include "poly.cuh"
+
+using namespace poly;
+
+template<class T> static constexpr int elems_per_thread() { return sizeof(T) >= 32 ? 4 : 8; }
+static constexpr int BS = 256;
+
+template<class F, int OP>
+static void scan(const gpu_t& gpu, cudaStream_t stream, typename F::T* out, const typename F::T* in, size_t len,
+                 const typename F::T* z_host, int rotate)
+{
+    typedef typename F::T T;
+    constexpr int E = elems_per_thread<T>();
+    constexpr size_t TILE = (size_t)BS * E;
+    if (len == 0) return;
+    if (len > ((size_t)1 << 40)) throw cuda_error(-(int)cudaErrorInvalidValue, "polynomial: length out of range");
+    const uint32_t ntiles = (uint32_t)((len + TILE - 1) / TILE);
+    const size_t flag_bytes = 16 + (((size_t)ntiles * 4 + 15) & ~(size_t)15);
+    const stream_t st(stream);
+    dev_ptr_t<uint8_t> scratch(flag_bytes + 3 * (size_t)ntiles * sizeof(T), st);
+    CUDA_OK(cudaMemsetAsync(scratch, 0, flag_bytes, stream));
+    uint32_t* counter = (uint32_t*)scratch.get();
+    uint32_t* flags = (uint32_t*)(scratch.get() + 16);
+    T* agg = (T*)(scratch.get() + flag_bytes);
+    T* incl = agg + ntiles;
+    T* edge = incl + ntiles;
+    T zk = arith<F>::zero();
+    if (OP == OP_DIV) zk = arith<F>::konst(*z_host);
+
+    int per_sm = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<F, OP, E, BS>, BS, 0));
+    const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)(gpu.sm_count() * std::max(per_sm, 1)));
+    scan_kernel<F, OP, E, BS><<<grid, BS, 0, stream>>>(out, in, len, zk, rotate, ntiles, counter, flags, agg, incl, edge);
+    COUNT_LAUNCH();
+    CUDA_OK(cudaGetLastError());
+    if (OP == OP_DIV && rotate && ntiles > 1) {
+        scan_edge_kernel<T><<<(ntiles + 255) / 256, 256, 0, stream>>>(out, edge, len, ntiles, (uint32_t)TILE);
+        COUNT_LAUNCH();
+        CUDA_OK(cudaGetLastError());
+    }
+}
+
+template<class F>
+static void evaluate(const gpu_t&, cudaStream_t stream, typename F::T* d_ret, const typename F::T* d_x, size_t n,
+                     const typename F::T* d_coeffs, size_t len)
+{
+    typedef typename F::T T;
+    constexpr int E = elems_per_thread<T>();
+    constexpr size_t TILE = (size_t)BS * E;
+    if (n == 0) return;
+    if (n > 0xffffffffu || len > ((size_t)1 << 40))
+        throw cuda_error(-(int)cudaErrorInvalidValue, "evaluate: size out of range");
+    const uint32_t nparts = (uint32_t)std::max<size_t>(1, (len + TILE - 1) / TILE);
+    const stream_t st(stream);
+    dev_ptr_t<T> partial((size_t)n * nparts, st);
+    evaluate_partial_kernel<F, E, BS><<<nparts, BS, 0, stream>>>(partial, d_x, (uint32_t)n, d_coeffs, len);
+    COUNT_LAUNCH();
+    CUDA_OK(cudaGetLastError());
+    evaluate_finish_kernel<F, BS><<<(uint32_t)n, BS, 0, stream>>>(d_ret, partial, d_x, nparts, (uint32_t)TILE);
+    COUNT_LAUNCH();
+    CUDA_OK(cudaGetLastError());
+}
+
+template<class F>
+static void batch_inverse(const gpu_t& gpu, cudaStream_t stream, typename F::T* d_out, const typename F::T* d_inp,
+                          size_t len)
+{
+    typedef typename F::T T;
+    constexpr int N = elems_per_thread<T>();
+    constexpr int IBS = sizeof(T) >= 32 ? 512 : 256;
+    if (len == 0) return;
+    const size_t nchunks = (len + (size_t)IBS * N - 1) / ((size_t)IBS * N);
+    const uint32_t grid = (uint32_t)std::min<size_t>(nchunks, (size_t)gpu.sm_count() * 8);
+    batch_inverse_kernel<F, N, IBS><<<grid, IBS, 0, stream>>>(d_out, d_inp, len);
+    COUNT_LAUNCH();
+    CUDA_OK(cudaGetLastError());
+}
+
+enum { WHAT_PREFIX_ADD, WHAT_PREFIX_MUL, WHAT_DIV, WHAT_EVAL, WHAT_INV };
+
+template<class F>
+static RustError run(int what, void* a, const void* b, size_t n, const void* c, size_t len, int flag, void* stream)
+{
+    typedef typename F::T T;
+    try {
+        const gpu_t& gpu = gpu_of_current_device();
+        cudaStream_t s = (cudaStream_t)stream;
+        switch (what) {
+        case WHAT_PREFIX_ADD: scan<F, OP_ADD>(gpu, s, (T*)a, (const T*)b, len, nullptr, 0); break;
+        case WHAT_PREFIX_MUL: scan<F, OP_MUL>(gpu, s, (T*)a, (const T*)b, len, nullptr, 0); break;
+        case WHAT_DIV: scan<F, OP_DIV>(gpu, s, (T*)a, (const T*)a, len, (const T*)c, flag); break;
+        case WHAT_EVAL: evaluate<F>(gpu, s, (T*)a, (const T*)b, n, (const T*)c, len); break;
+        default: batch_inverse<F>(gpu, s, (T*)a, (const T*)b, len); break;
+        }
+        return rust_ok();
+    } catch (const cuda_error& e) {
+        return rust_err(e.code(), e.what());
+    } catch (const std::exception& e) {
+        return rust_err(-1, e.what());
+    }
+}
+
+static RustError run_any(int field, int what, void* a, const void* b, size_t n, const void* c, size_t len, int flag,
+                         void* stream)
+{
+    switch (field) {
+    case SPPARK_FIELD_GL64: return run<gl64>(what, a, b, n, c, len, flag, stream);
+    case SPPARK_FIELD_BB31: return run<bb31>(what, a, b, n, c, len, flag, stream);
+    case SPPARK_FIELD_BLS12_381_FR: return run<ff::bls12_381_fr_ntt>(what, a, b, n, c, len, flag, stream);
+    case SPPARK_FIELD_PALLAS_FR: return run<ff::pallas_fr_ntt>(what, a, b, n, c, len, flag, stream);
+    case SPPARK_FIELD_VESTA_FR: return run<ff::vesta_fr_ntt>(what, a, b, n, c, len, flag, stream);
+    case SPPARK_FIELD_BN254_FR: return run<ff::bn254_fr_ntt>(what, a, b, n, c, len, flag, stream);
+    case SPPARK_FIELD_BLS12_377_FR: return run<ff::bls12_377_fr_ntt>(what, a, b, n, c, len, flag, stream);
+    default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200 polynomial: unknown field");
+    }
+}
+
+extern "C" RustError sppark_b200_prefix_op_dev(int field, int op, void* d_out, const void* d_inp, size_t len,
+                                               void* stream)
+{
+    if (op != 0 && op != 1) return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_prefix_op_dev: op is 0 (add) or 1 (multiply)");
+    return run_any(field, op == 0 ? WHAT_PREFIX_ADD : WHAT_PREFIX_MUL, d_out, d_inp, 0, nullptr, len, 0, stream);
+}
+
+extern "C" RustError sppark_b200_div_by_x_minus_z_dev(int field, void* d_inout, size_t len, const void* z,
+                                                      int rotate, void* stream)
+{
+    if (z == nullptr) return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_div_by_x_minus_z_dev: z is null");
+    return run_any(field, WHAT_DIV, d_inout, nullptr, 0, z, len, rotate != 0, stream);
+}
+
+extern "C" RustError sppark_b200_evaluate_dev(int field, void* d_ret, const void* d_x, size_t n,
+                                              const void* d_coeffs, size_t len, void* stream)
+{   return run_any(field, WHAT_EVAL, d_ret, d_x, n, d_coeffs, len, 0, stream);   }
+
+extern "C" RustError sppark_b200_batch_inverse_dev(int field, void* d_out, const void* d_inp, size_t len,
+                                                   void* stream)
+{   return run_any(field, WHAT_INV, d_out, d_inp, 0, nullptr, len, 0, stream);   }

@@ -9,6 +9,8 @@
                     (G1, arkworks layout with infinity flags): `... make_golden.py g2` on a GPU.
   msm_curves2_ref_gpu.npz  the reference's CUDA MSM for BN254 and BLS12-377 G1: `... make_golden.py curves2`.
   msm_pasta_ref_gpu.npz    the reference's CUDA MSM templates for Pallas and Vesta: `... make_golden.py pasta`.
+  poly_<field>_ref_gpu.npz  the reference's polynomial/ templates (prefix_op, div_by_x_minus_z,
+                    evaluate) through oracle/ref_poly.cu: `... make_golden.py poly_gl64|poly_bb31|poly_bls12_381_fr`.
   msm_ref_cpu.npz   the reference's CPU msm/pippenger.hpp (oracle/_ref/libref_msm_cpu.so);
                     runs anywhere: `python tests/golden/make_golden.py cpu`.
 
@@ -300,6 +302,77 @@ def gen_pasta(outdir):
     print("wrote msm_pasta_ref_gpu.npz")
 
 
+def gen_poly(outdir, field):
+    """poly_<field>_ref_gpu.npz: the reference's polynomial/ templates (oracle/ref_poly.cu) on
+    seeded inputs in the field's memory format.  One reference library per process.  Two limits
+    of the reference itself are stepped around (profiles/ref_poly_probe_r02.txt): its evaluate
+    faults at len = 1, and its 256-bit div_by_x_minus_z faults for len <= 5001 -- those cases are
+    not recorded.  The `big` case keeps SHA-256 digests of the outputs instead of the arrays; its
+    input is regenerated from the seed by oracle.poly.seeded_input."""
+    import hashlib
+    from oracle import poly as op
+    lib = C.CDLL(o.ref_path(f"libref_poly_{field if field != 'bls12_381_fr' else 'bls12_381'}_gpu.so"))
+    lib.ref_prefix_op.argtypes = [C.c_int, C.c_void_p, C.c_size_t]
+    lib.ref_div_by_x_minus_z.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+    lib.ref_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    f = op.FIELDS[field]
+    wide = f["words"] > 1
+    assert lib.ref_poly_elem_bytes() == f["words"] * np.dtype(f["dtype"]).itemsize
+    import random
+    rnd = random.Random({"gl64": 1, "bb31": 2, "bls12_381_fr": 3}[field])
+    lens = (1, 2, 33, 255, 1024, 1025, 3000, 5001) if wide else \
+           (1, 2, 3, 31, 32, 33, 255, 1000, 2048, 2049, 10000, 20001)
+    big = 65536 if wide else (1 << 20) + 1
+    out = {"lens": np.array(lens, dtype=np.int64), "big": np.int64(big)}
+
+    def call(e, what):
+        if e != 0:
+            raise RuntimeError(f"reference {what}: cuda error {e}")
+
+    for n in lens + (big,):
+        digest = n == big
+        if digest:
+            x = op.seeded_input(field, n, 4242)
+            vals = None
+        else:
+            vals = [rnd.randrange(f["p"]) for _ in range(n)]
+            if n > 40:
+                vals[7] = 0
+                vals[n - 2] = f["p"] - 1
+            x = op.encode(field, vals)
+            out[f"in_{n}"] = x
+
+        def keep(key, y):
+            out[key] = np.frombuffer(hashlib.sha256(y.tobytes()).digest(), dtype=np.uint8) if digest else y
+
+        for name, opc in (("add", 0), ("mul", 1)):
+            y = x.copy()
+            if name == "mul" and n > 40 and not digest:       # keep the products non-zero past index 7
+                y[7] = op.encode(field, [3])[0]
+                out[f"mulin_{n}"] = y.copy()
+            call(lib.ref_prefix_op(opc, y.ctypes.data, n), f"prefix_op {name} {n}")
+            keep(f"{name}_{n}", y)
+        zs = [rnd.randrange(f["p"])]
+        if n in (33, 1000, 1024):
+            zs += [0, 1]
+        out[f"z_{n}"] = op.encode(field, zs)
+        if not wide or digest:
+            for k, z in enumerate(zs):
+                zbuf = op.encode(field, [z])
+                for rot in (0, 1):
+                    y = x.copy()
+                    call(lib.ref_div_by_x_minus_z(y.ctypes.data, n, zbuf.ctypes.data, rot), f"div {n} {rot}")
+                    keep(f"div_{n}_{k}_{rot}", y)
+        if n > 1:
+            npts = {33: 3, 1000: 7, 1024: 7}.get(n, 2)
+            xs = op.encode(field, [rnd.randrange(f["p"]) for _ in range(npts - 1)] + [0])
+            ret = np.zeros_like(xs)
+            call(lib.ref_evaluate(ret.ctypes.data, xs.ctypes.data, npts, x.ctypes.data, n), f"evaluate {n}")
+            out[f"x_{n}"], out[f"eval_{n}"] = xs, ret
+    np.savez_compressed(os.path.join(outdir, f"poly_{field}_ref_gpu.npz"), **out)
+    print(f"wrote poly_{field}_ref_gpu.npz")
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "cpu"
     if mode == "cpu":
@@ -321,5 +394,7 @@ if __name__ == "__main__":
             gen_ntt256(outdir)
         elif mode == "msm":
             gen_msm(outdir)
+        elif mode.startswith("poly_"):
+            gen_poly(outdir, mode[5:])
         else:
             gen_gpu(outdir)
