@@ -100,6 +100,25 @@ struct gl64 {
         return mont_reduce((T)x, (T)(x >> 64));
 #endif
     }
+    // plain product of two words in the data domain: any a, b -> canonical a * b mod p
+    // (2^64 = EPS, 2^96 = -1: hi:lo = lo + hi_lo * EPS - hi_hi); used where BOTH operands are data
+    // (prefix products, batch inversion), the NTT never needs it
+    static HD T mul_plain(T a, T b)
+    {
+#if defined(__CUDA_ARCH__)
+        const T lo = a * b, hi = __umul64hi(a, b);
+#else
+        const unsigned __int128 x = (unsigned __int128)a * b;
+        const T lo = (T)x, hi = (T)(x >> 64);
+#endif
+        const T hh = hi >> 32, hl = hi & EPS;
+        T t0 = lo - hh;
+        if (lo < hh) t0 -= EPS;               // borrowed 2^64 = EPS (mod p); t0 >= 2^64 - 2^32 here
+        const T t1 = (hl << 32) - hl;         // hl * EPS <= 2^64 - 2^33 + 1
+        T r = t0 + t1;
+        if (r < t1) r += EPS;                 // wrapped: r < t1, so r + EPS cannot wrap again
+        return canon(r);
+    }
     static HD T to_mont(T a) { return mul(canon(a), 0xfffffffe00000001ULL); }   // * 2^128 mod p
     static HD T pow(T b, uint64_t e)
     {

@@ -9,6 +9,25 @@ using namespace poly;
 template<class T> static constexpr int elems_per_thread() { return sizeof(T) >= 32 ? 4 : 8; }
 static constexpr int BS = 256;
 
+template<class F, int OP, int MODE, bool REV>
+static void scan_launch(const gpu_t& gpu, cudaStream_t stream, uint32_t grid_cap, typename F::T* out,
+                        const typename F::T* in, size_t len, typename F::T z, int rotate, uint32_t ntiles,
+                        typename F::T* aggs, typename F::T* edge)
+{
+    constexpr int E = elems_per_thread<typename F::T>();
+    static int per_sm[64];                                   // occupancy per device, looked up once
+    const int dev = gpu.cid() & 63;
+    if (per_sm[dev] == 0) {
+        int n = 0;
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, scan_kernel<F, OP, E, BS, MODE, REV>, BS, 0));
+        per_sm[dev] = std::max(n, 1);
+    }
+    const uint32_t grid = std::min<uint32_t>(std::min<uint32_t>(ntiles, grid_cap), (uint32_t)(gpu.sm_count() * per_sm[dev]));
+    scan_kernel<F, OP, E, BS, MODE, REV><<<grid, BS, 0, stream>>>(out, in, len, z, rotate, ntiles, aggs, edge);
+    COUNT_LAUNCH();
+    CUDA_OK(cudaGetLastError());
+}
+
 template<class F, int OP>
 static void scan(const gpu_t& gpu, cudaStream_t stream, typename F::T* out, const typename F::T* in, size_t len,
                  const typename F::T* z_host, int rotate)
@@ -16,27 +35,30 @@ static void scan(const gpu_t& gpu, cudaStream_t stream, typename F::T* out, cons
     typedef typename F::T T;
     constexpr int E = elems_per_thread<T>();
     constexpr size_t TILE = (size_t)BS * E;
+    constexpr bool REV = OP == OP_DIV;
     if (len == 0) return;
     if (len > ((size_t)1 << 40)) throw cuda_error(-(int)cudaErrorInvalidValue, "polynomial: length out of range");
     const uint32_t ntiles = (uint32_t)((len + TILE - 1) / TILE);
-    const size_t flag_bytes = 16 + (((size_t)ntiles * 4 + 15) & ~(size_t)15);
     const stream_t st(stream);
-    dev_ptr_t<uint8_t> scratch(flag_bytes + 3 * (size_t)ntiles * sizeof(T), st);
-    CUDA_OK(cudaMemsetAsync(scratch, 0, flag_bytes, stream));
-    uint32_t* counter = (uint32_t*)scratch.get();
-    uint32_t* flags = (uint32_t*)(scratch.get() + 16);
-    T* agg = (T*)(scratch.get() + flag_bytes);
-    T* incl = agg + ntiles;
-    T* edge = incl + ntiles;
-    T zk = arith<F>::zero();
-    if (OP == OP_DIV) zk = arith<F>::konst(*z_host);
-
-    int per_sm = 0;
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<F, OP, E, BS>, BS, 0));
-    const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)(gpu.sm_count() * std::max(per_sm, 1)));
-    scan_kernel<F, OP, E, BS><<<grid, BS, 0, stream>>>(out, in, len, zk, rotate, ntiles, counter, flags, agg, incl, edge);
-    COUNT_LAUNCH();
-    CUDA_OK(cudaGetLastError());
+    dev_ptr_t<T> scratch(2 * (size_t)ntiles, st);
+    T* aggs = scratch.get();
+    T* edge = aggs + ntiles;
+    T zk = arith<F>::zero(), zt = zk;
+    if (OP == OP_DIV) {
+        zk = arith<F>::konst(*z_host);
+        zt = kpow<F>(zk, TILE);
+    }
+    if (ntiles <= 2) {
+        scan_launch<F, OP, MODE_SERIAL, REV>(gpu, stream, 1, out, in, len, zk, rotate, ntiles, aggs, edge);
+    } else {
+        const uint32_t rgrid = std::min<uint32_t>(ntiles, (uint32_t)gpu.sm_count() * 8);
+        tile_reduce_kernel<F, OP, E, BS><<<rgrid, BS, 0, stream>>>(aggs, in, len, zk, REV, ntiles);
+        COUNT_LAUNCH();
+        CUDA_OK(cudaGetLastError());
+        const uint32_t nagg_tiles = (uint32_t)((ntiles + TILE - 1) / TILE);
+        scan_launch<F, OP, MODE_SERIAL, false>(gpu, stream, 1, aggs, aggs, ntiles, zt, 0, nagg_tiles, nullptr, nullptr);
+        scan_launch<F, OP, MODE_SCAN, REV>(gpu, stream, ~0u, out, in, len, zk, rotate, ntiles, aggs, edge);
+    }
     if (OP == OP_DIV && rotate && ntiles > 1) {
         scan_edge_kernel<T><<<(ntiles + 255) / 256, 256, 0, stream>>>(out, edge, len, ntiles, (uint32_t)TILE);
         COUNT_LAUNCH();
@@ -45,22 +67,29 @@ static void scan(const gpu_t& gpu, cudaStream_t stream, typename F::T* out, cons
 }
 
 template<class F>
-static void evaluate(const gpu_t&, cudaStream_t stream, typename F::T* d_ret, const typename F::T* d_x, size_t n,
+static void evaluate(const gpu_t& gpu, cudaStream_t stream, typename F::T* d_ret, const typename F::T* d_x, size_t n,
                      const typename F::T* d_coeffs, size_t len)
 {
     typedef typename F::T T;
-    constexpr int E = elems_per_thread<T>();
-    constexpr size_t TILE = (size_t)BS * E;
     if (n == 0) return;
     if (n > 0xffffffffu || len > ((size_t)1 << 40))
         throw cuda_error(-(int)cudaErrorInvalidValue, "evaluate: size out of range");
-    const uint32_t nparts = (uint32_t)std::max<size_t>(1, (len + TILE - 1) / TILE);
+    // points that share one pass over the coefficients (accumulators in registers)
+    constexpr int MAXPTS = sizeof(T) >= 32 ? 2 : 4;
+    const int pts = n >= (size_t)MAXPTS ? MAXPTS : n >= 2 ? 2 : 1;
+    auto kernel = pts == 4 ? evaluate_partial_kernel<F, BS, MAXPTS> :
+                  pts == 2 ? evaluate_partial_kernel<F, BS, 2> : evaluate_partial_kernel<F, BS, 1>;
+    int per_sm = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BS, 0));
+    // a resident grid, but at least 8 coefficients per thread before another CTA is worth its reduction
+    const uint32_t nparts = (uint32_t)std::max<size_t>(1, std::min<size_t>((size_t)gpu.sm_count() * std::max(per_sm, 1),
+                                                                          (len + (size_t)BS * 8 - 1) / ((size_t)BS * 8)));
     const stream_t st(stream);
     dev_ptr_t<T> partial((size_t)n * nparts, st);
-    evaluate_partial_kernel<F, E, BS><<<nparts, BS, 0, stream>>>(partial, d_x, (uint32_t)n, d_coeffs, len);
+    kernel<<<nparts, BS, 0, stream>>>(partial, d_x, (uint32_t)n, d_coeffs, len);
     COUNT_LAUNCH();
     CUDA_OK(cudaGetLastError());
-    evaluate_finish_kernel<F, BS><<<(uint32_t)n, BS, 0, stream>>>(d_ret, partial, d_x, nparts, (uint32_t)TILE);
+    evaluate_finish_kernel<F, BS><<<(uint32_t)n, BS, 0, stream>>>(d_ret, partial, d_x, nparts, (uint32_t)BS);
     COUNT_LAUNCH();
     CUDA_OK(cudaGetLastError());
 }

@@ -4,16 +4,16 @@
 //
 // The reference writes each of these as ONE cooperative kernel with grid-wide barriers between a
 // local phase, a cross-block carry phase and an apply phase.  Here:
-//  * prefix_op and div_by_x_minus_z are the same single-pass scan with decoupled look-back: tiles
-//    are handed out by an atomic ticket, each tile publishes its aggregate and then its inclusive
-//    prefix next to a flag word, and a warp looks back over 32 predecessors at a time.  One read
-//    and one write of the data, no grid barrier, no cooperative launch.  Division by (x - z) is
-//    the scan of  b[i] = c[i] + z * b[i+1]  from the top coefficient down: the carry that crosses
-//    k elements is weighted by z^k, and since every level of the hierarchy (thread, lane, warp,
-//    tile) spans a fixed number of elements the weights are a handful of constants held in
-//    shared memory.
-//  * evaluate is a weighted tree reduction (Horner per thread, then  sum_t s_t * (x^E)^t  by
-//    shuffles) with one partial per CTA and a one-CTA finish per point.
+//  * prefix_op and div_by_x_minus_z are the same tiled scan in three ordinary launches (tile
+//    aggregates, a one-CTA scan of the aggregates, rescan with carries): no grid barrier, no
+//    cooperative launch, no ordering between CTAs.  Division by (x - z) is the scan of
+//    b[i] = c[i] + z * b[i+1]  from the top coefficient down: the carry that crosses k elements
+//    is weighted by z^k, and since every level of the hierarchy (thread, lane, warp, tile) spans
+//    a fixed number of elements the weights are a handful of constants held in shared memory;
+//    the scan of the tile aggregates is the same recurrence with z^TILE in the place of z.
+//  * evaluate is a strided Horner (thread g owns coefficients g, g+G, ...: one multiplication per
+//    coefficient and point, contiguous reads) followed by  sum_t s_t * x^t  over the CTA by
+//    shuffles, one partial per CTA and a one-CTA finish per point.
 //  * batch inversion shares ONE field inversion per CTA: prefix and suffix products over the CTA
 //    give every thread the inverse of its own chunk product.
 // All arithmetic is on the field's memory format (arith<F> below), the same the NTT entry points
@@ -46,12 +46,11 @@ template<class F> struct arith {                       // Montgomery fields: one
 // that data * constant is a single multiplication-free-reduction product
 template<> struct arith<gl64> {
     typedef uint64_t T;
-    static constexpr uint64_t R2 = 0xfffffffe00000001ULL;          // 2^128 mod p
     static HD T zero() { return 0; }
     static HD T one() { return 1; }
     static HD T load(T a) { return gl64::canon(a); }
     static HD T add(T a, T b) { return gl64::canon(gl64::add(a, b)); }
-    static HD T dmul(T a, T b) { return gl64::mul(gl64::mul(a, b), R2); }
+    static HD T dmul(T a, T b) { return gl64::mul_plain(a, b); }
     static HD T cmul(T a, T c) { return gl64::mul(a, c); }
     static HD T konst(T a) { return gl64::to_mont(a); }
     static HD T kone() { return gl64::one(); }
@@ -131,30 +130,88 @@ template<class F, int OP> DEV typename F::T join(const typename F::T& carry, con
     return A::add(x, A::cmul(carry, w));
 }
 
-// ---- single-pass scan ------------------------------------------------------------------------------
-// Scan order t = 0, 1, ...: OP_ADD / OP_MUL walk memory upwards, OP_DIV walks it downwards from
-// the top coefficient (memory index len-1-t).  Thread = E consecutive scan positions, warp = 32 E,
-// tile = BS E; the last tile in scan order may be ragged (its tail is identity and is not stored).
-// Tile status: flags[k] = 0 nothing yet, 1 agg[k] valid, 2 incl[k] valid.
-template<class F, int OP, int E, int BS>
+// ---- sum_t val_t * base^t over the CTA (thread 0 holds the result) ---------------------------------
+// weights base^(2^k), k < 10, once per base ...
+template<class F>
+DEV void wreduce_setup(const typename F::T& base, typename F::T* s_w /*[10]*/)
+{
+    typedef arith<F> A;
+    __syncthreads();                                            // s_w free again
+    if (threadIdx.x < 10) {
+        typename F::T b = base;
+        for (uint32_t i = 0; i < threadIdx.x; i++) b = A::kmul(b, b);
+        s_w[threadIdx.x] = b;
+    }
+    __syncthreads();
+}
+// ... then any number of reductions with them
+template<class F, int BS>
+DEV typename F::T wreduce(typename F::T val, const typename F::T* s_w, typename F::T* s_x /*[BS/32]*/)
+{
+    typedef arith<F> A;
+    typedef typename F::T T;
+    constexpr int NW = BS / 32;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (uint32_t k = 0, off = 1; off < 32; k++, off <<= 1) {
+        T t = shfl_down(val, off);
+        val = A::add(val, A::cmul(t, s_w[k]));
+    }
+    __syncthreads();                                            // s_x free again
+    if (lane == 0) s_x[warp] = val;
+    __syncthreads();
+    if (warp == 0) {
+        val = lane < NW ? s_x[lane] : A::zero();
+#pragma unroll
+        for (uint32_t k = 5, off = 1; off < NW; k++, off <<= 1) {
+            T t = shfl_down(val, off);
+            val = A::add(val, A::cmul(t, s_w[k]));
+        }
+    }
+    return val;
+}
+template<class F, int BS>
+DEV typename F::T block_wreduce(typename F::T val, const typename F::T& base, typename F::T* s_w, typename F::T* s_x)
+{
+    wreduce_setup<F>(base, s_w);
+    return wreduce<F, BS>(val, s_w, s_x);
+}
+
+// ---- scan -------------------------------------------------------------------------------------------
+// Scan order t = 0, 1, ...: memory index t, or len-1-t when `rev` (division walks down from the top
+// coefficient).  Thread = E consecutive scan positions, warp = 32 E, tile = BS E; a warp moves its
+// 32 E elements between memory and registers through a padded shared-memory transpose, so global
+// accesses are contiguous per warp in either direction.  The last tile may be ragged (its tail is
+// the identity and is not stored).
+//
+// Three launches make a scan of any length, with no ordering between CTAs:
+//   tile_reduce_kernel        every tile's aggregate -> aggs[tile]                      (reads the data once)
+//   scan_kernel MODE_SERIAL   ONE CTA scans aggs[] in place, tile after tile            (ntiles elements)
+//   scan_kernel MODE_SCAN     every tile rescanned with carry aggs[tile-1] and stored   (reads + writes the data)
+// A decoupled look-back single pass was measured first and rejected: its carry chain advances at
+// most one 32-tile window per L2 round trip, which capped 2^24 Goldilocks elements at 230 us where
+// these three launches are bandwidth bound (profiles/poly_r02.md).  Short inputs take MODE_SERIAL
+// directly on the data (one launch).
+enum { MODE_SERIAL = 1, MODE_SCAN = 2 };
+
+template<class F, int OP, int E, int BS, int MODE, bool REV>
 __global__ __launch_bounds__(BS) void scan_kernel(typename F::T* out, const typename F::T* in, size_t len,
                                                   typename F::T z, int rotate, uint32_t ntiles,
-                                                  uint32_t* counter, volatile uint32_t* flags,
-                                                  typename F::T* agg, typename F::T* incl,
-                                                  typename F::T* edge)
+                                                  typename F::T* aggs, typename F::T* edge)
 {
     typedef arith<F> A;
     typedef typename F::T T;
     constexpr int NW = BS / 32;
     constexpr uint32_t TILE = BS * E;
-    static_assert(BS >= 256 && NW <= 32, "setup below spreads the constant table over 256 threads");
+    constexpr int ROW = E + 1;       // padded row of the transpose
+    static_assert(BS >= 256 && NW <= 32 && (E & (E - 1)) == 0, "setup below spreads the constant table over 256 threads");
     __shared__ T s_wl[33];          // z^(E k): a carry crossing k threads
     __shared__ T s_ww[NW + 1];      // z^(32 E k): crossing k warps
     __shared__ T s_zp[E + 1];       // z^k
-    __shared__ T s_zt[6];           // z^(TILE 2^k): crossing 2^k tiles
+    __shared__ T s_zt;              // z^TILE
     __shared__ T s_agg[NW];
     __shared__ T s_carry;
-    __shared__ uint32_t s_tile;
+    __shared__ T s_stage[NW][32 * ROW];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const T ident = OP == OP_MUL ? A::one() : A::zero();
@@ -163,24 +220,40 @@ __global__ __launch_bounds__(BS) void scan_kernel(typename F::T* out, const type
         if (tid < 33) s_wl[tid] = kpow<F>(z, (uint64_t)E * tid);
         else if (tid >= 64 && tid < 64 + NW + 1) s_ww[tid - 64] = kpow<F>(z, (uint64_t)32 * E * (tid - 64));
         else if (tid >= 128 && tid < 128 + E + 1) s_zp[tid - 128] = kpow<F>(z, tid - 128);
-        else if (tid >= 192 && tid < 198) s_zt[tid - 192] = kpow<F>(z, (uint64_t)TILE << (tid - 192));
+        else if (tid == 192) s_zt = kpow<F>(z, TILE);
     }
+    if (tid == 0) s_carry = ident;
 
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_tile = atomicAdd(counter, 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= ntiles) break;
+    // element e = j*32 + lane of the warp's 32 E sits at stage[sidx + j * SJ] (row e / E, column e % E)
+    const uint32_t sidx = (lane / E) * ROW + lane % E;
+    constexpr uint32_t SJ = (32 / E) * ROW;
+    static_assert(E <= 32, "a warp's stripe of 32 elements covers whole rows");
 
-        const size_t base = (size_t)tile * TILE + (size_t)tid * E;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();            // constants ready; previous tile's s_agg / s_stage consumed
+        const size_t tbase = (size_t)tile * TILE;
+        const uint32_t wofs = warp * 32 * E;
+        const bool full = tbase + TILE <= len;
+        T cprev = ident;
+        if (MODE == MODE_SCAN && tid == 0 && tile) cprev = ld_cg(aggs + tile - 1);
+        T* stage = s_stage[warp];
+        if (full) {                 // scan position tbase + wofs + e  <->  memory index, no bounds to check
+            const T* src = REV ? in + (len - 1 - tbase - wofs - lane) : in + (tbase + wofs + lane);
+#pragma unroll
+            for (int j = 0; j < E; j++) stage[sidx + j * SJ] = A::load(REV ? *(src - j * 32) : src[j * 32]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < E; j++) {
+                const size_t pos = tbase + wofs + j * 32 + lane;
+                T c = ident;
+                if (pos < len) c = A::load(in[REV ? len - 1 - pos : pos]);
+                stage[sidx + j * SJ] = c;
+            }
+        }
+        __syncwarp();
         T v[E];
 #pragma unroll
-        for (int j = 0; j < E; j++) {
-            size_t pos = base + j;
-            v[j] = ident;
-            if (pos < len) v[j] = A::load(in[OP == OP_DIV ? len - 1 - pos : pos]);
-        }
+        for (int j = 0; j < E; j++) v[j] = stage[lane * ROW + j];
 #pragma unroll
         for (int j = 1; j < E; j++) v[j] = join<F, OP>(v[j - 1], v[j], z);
 
@@ -202,63 +275,110 @@ __global__ __launch_bounds__(BS) void scan_kernel(typename F::T* out, const type
                 T t = shfl_up(w, off);
                 if (lane >= off) w = join<F, OP>(t, w, s_ww[off]);
             }
-            const T tile_agg = shfl_idx(w, NW - 1);
-            T acc = ident;                                   // lane 0: everything before this tile
-            if (tile > 0) {
-                if (lane == 0) {
-                    agg[tile] = tile_agg;
-                    __threadfence();
-                    flags[tile] = 1;
-                }
-                T wacc = A::kone();                          // z^(TILE * tiles acc spans)
-                for (int64_t k0 = (int64_t)tile - 1;; k0 -= 32) {
-                    const int64_t k = k0 - lane;             // lane 0 looks at the nearest predecessor
-                    uint32_t f;
-                    do {
-                        f = k < 0 ? 2u : flags[k];
-                    } while (__any_sync(0xffffffffu, f == 0));
-                    __threadfence();
-                    T val = ident;
-                    if (k >= 0) val = f == 2 ? ld_cg(incl + k) : ld_cg(agg + k);
-                    const uint32_t m = __ballot_sync(0xffffffffu, f == 2);
-                    const uint32_t jstar = __ffs(m) - 1;     // nearest inclusive prefix (m == 0: 0xffffffff)
-                    if (lane > jstar) val = ident;
-#pragma unroll
-                    for (uint32_t kk = 0, off = 1; off < 32; kk++, off <<= 1) {
-                        T t = shfl_down(val, off);
-                        if (lane + off < 32) val = join<F, OP>(t, val, s_zt[kk]);
-                    }
-                    if (lane == 0) acc = join<F, OP>(val, acc, wacc);
-                    if (m) break;
-                    if (OP == OP_DIV) wacc = A::kmul(wacc, s_zt[5]);
-                }
-            }
-            if (lane == 0) {
-                s_carry = acc;
-                if (tile + 1 < ntiles) {
-                    incl[tile] = join<F, OP>(acc, tile_agg, s_zt[0]);
-                    __threadfence();
-                    flags[tile] = 2;
-                }
-            }
             if (lane < NW) s_agg[lane] = w;
+            if (MODE == MODE_SCAN && lane == 0) s_carry = cprev;
         }
         __syncthreads();
 
+        const T carry = s_carry;
         const T wexcl = warp ? s_agg[warp - 1] : ident;
-        const T wc = join<F, OP>(s_carry, wexcl, s_ww[warp]);          // value entering this warp
+        const T wc = join<F, OP>(carry, wexcl, s_ww[warp]);            // value entering this warp
         const T cin = join<F, OP>(wc, lane_excl, s_wl[lane]);          // value entering this thread
 #pragma unroll
-        for (int j = 0; j < E; j++) {
-            size_t pos = base + j;
-            T r = join<F, OP>(cin, v[j], s_zp[j + 1]);
-            if (pos >= len) continue;
-            if (OP != OP_DIV) out[pos] = r;
-            else if (!rotate) out[len - 1 - pos] = r;
-            else if (pos == len - 1) out[len - 1] = r;                 // the remainder goes last
-            else if (j == E - 1 && tid == BS - 1) edge[tile] = r;      // slot still unread by the next tile
-            else out[len - 2 - pos] = r;
+        for (int j = 0; j < E; j++) stage[lane * ROW + j] = join<F, OP>(cin, v[j], s_zp[j + 1]);
+        if (MODE == MODE_SERIAL) {
+            __syncthreads();                                           // every thread has read s_carry
+            if (tid == BS - 1) s_carry = stage[lane * ROW + E - 1];    // inclusive value at the tile's end
         }
+        __syncwarp();
+        if (full && !(REV && rotate)) {
+            T* dst = REV ? out + (len - 1 - tbase - wofs - lane) : out + (tbase + wofs + lane);
+#pragma unroll
+            for (int j = 0; j < E; j++) {
+                if (REV) *(dst - j * 32) = stage[sidx + j * SJ];
+                else dst[j * 32] = stage[sidx + j * SJ];
+            }
+        } else if (full && tile + 1 < ntiles) {
+            // rotate, interior tile: every quotient coefficient moves one slot down; the last one
+            // would land in the next tile's still unread first slot and is parked instead
+            T* dst = out + (len - 2 - tbase - wofs - lane);
+#pragma unroll
+            for (int j = 0; j < E; j++) {
+                const T r = stage[sidx + j * SJ];
+                if (j == E - 1 && tid == BS - 1) edge[tile] = r;
+                else *(dst - j * 32) = r;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < E; j++) {
+                const uint32_t e = j * 32 + lane;
+                const size_t pos = tbase + wofs + e;
+                if (pos >= len) continue;
+                const T r = stage[sidx + j * SJ];
+                if (!REV) out[pos] = r;
+                else if (!rotate) out[len - 1 - pos] = r;
+                else if (pos == len - 1) out[len - 1] = r;             // the remainder goes last
+                else if (e == 32 * E - 1 && warp == NW - 1) edge[tile] = r;
+                else out[len - 2 - pos] = r;
+            }
+        }
+    }
+}
+
+// MODE_REDUCE without the scan: a tile's aggregate needs no per-element prefix, so thread t takes
+// the tile's positions t, t+BS, ... (contiguous per warp, no transpose).  Add / Multiply fold them
+// in any order; division runs Horner in z^BS over its positions (mirrored, so that thread t ends up
+// weighted by z^t) and finishes with the weighted tree above: one multiplication per element.
+template<class F, int OP, int E, int BS>
+__global__ __launch_bounds__(BS) void tile_reduce_kernel(typename F::T* aggs, const typename F::T* in, size_t len,
+                                                         typename F::T z, int rev, uint32_t ntiles)
+{
+    typedef arith<F> A;
+    typedef typename F::T T;
+    constexpr int NW = BS / 32;
+    constexpr uint32_t TILE = BS * E;
+    __shared__ T s_w[10];
+    __shared__ T s_x[NW];
+    __shared__ T s_y;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const T ident = OP == OP_MUL ? A::one() : A::zero();
+    if (OP == OP_DIV) {
+        if (tid == 32) s_y = kpow<F>(z, BS);
+        wreduce_setup<F>(z, s_w);
+    }
+    const T y = OP == OP_DIV ? s_y : ident;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t base = (size_t)tile * TILE + (OP == OP_DIV ? BS - 1 - tid : tid);
+        T acc = ident;
+        if ((size_t)(tile + 1) * TILE <= len) {
+            const T* src = rev ? in + (len - 1 - base) : in + base;
+            const ptrdiff_t step = rev ? -(ptrdiff_t)BS : (ptrdiff_t)BS;
+#pragma unroll
+            for (int k = 0; k < E; k++) acc = join<F, OP>(acc, A::load(src[k * step]), y);
+        } else {
+#pragma unroll
+            for (int k = 0; k < E; k++) {
+                const size_t pos = base + (size_t)k * BS;
+                T c = ident;
+                if (pos < len) c = A::load(in[rev ? len - 1 - pos : pos]);
+                acc = join<F, OP>(acc, c, y);
+            }
+        }
+        if (OP == OP_DIV) {
+            acc = wreduce<F, BS>(acc, s_w, s_x);
+        } else {
+#pragma unroll
+            for (uint32_t off = 16; off; off >>= 1) acc = join<F, OP>(acc, shfl_down(acc, off), y);
+            __syncthreads();
+            if (lane == 0) s_x[warp] = acc;
+            __syncthreads();
+            if (warp == 0) {
+                acc = lane < NW ? s_x[lane] : ident;
+#pragma unroll
+                for (uint32_t off = NW / 2; off; off >>= 1) acc = join<F, OP>(acc, shfl_down(acc, off), y);
+            }
+        }
+        if (tid == 0) aggs[tile] = acc;
     }
 }
 
@@ -273,42 +393,11 @@ __global__ void scan_edge_kernel(T* out, const T* edge, size_t len, uint32_t nti
     out[len - 2 - pos] = edge[k];
 }
 
-// ---- sum_t val_t * base^t over the CTA (thread 0 holds the result) ---------------------------------
-template<class F, int BS>
-DEV typename F::T block_wreduce(typename F::T val, const typename F::T& base, typename F::T* s_w /*[10]*/,
-                                typename F::T* s_x /*[BS/32]*/)
-{
-    typedef arith<F> A;
-    typedef typename F::T T;
-    constexpr int NW = BS / 32;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __syncthreads();                                            // s_w / s_x free again
-    if (tid < 10) {
-        T b = base;
-        for (uint32_t i = 0; i < tid; i++) b = A::kmul(b, b);   // base^(2^tid)
-        s_w[tid] = b;
-    }
-    __syncthreads();
-#pragma unroll
-    for (uint32_t k = 0, off = 1; off < 32; k++, off <<= 1) {
-        T t = shfl_down(val, off);
-        val = A::add(val, A::cmul(t, s_w[k]));
-    }
-    if (lane == 0) s_x[warp] = val;
-    __syncthreads();
-    if (warp == 0) {
-        val = lane < NW ? s_x[lane] : A::zero();
-#pragma unroll
-        for (uint32_t k = 5, off = 1; off < NW; k++, off <<= 1) {
-            T t = shfl_down(val, off);
-            val = A::add(val, A::cmul(t, s_w[k]));
-        }
-    }
-    return val;
-}
-
-// one partial per (point, CTA): sum over the CTA's BS*E coefficients of c_i x^(i - first)
-template<class F, int E, int BS>
+// one partial per (point, CTA).  Thread g of the G = gridDim.x*BS threads owns the coefficients
+// g, g+G, g+2G, ... (a warp reads consecutive elements) and runs Horner over them in y = x^G:
+// one multiplication per coefficient and point; then  sum_t s_t x^t  over the CTA.  PTS points share
+// one pass over the coefficients.
+template<class F, int BS, int PTS>
 __global__ __launch_bounds__(BS) void evaluate_partial_kernel(typename F::T* partial, const typename F::T* x,
                                                               uint32_t npoints, const typename F::T* coeffs,
                                                               size_t len)
@@ -317,20 +406,34 @@ __global__ __launch_bounds__(BS) void evaluate_partial_kernel(typename F::T* par
     typedef typename F::T T;
     __shared__ T s_w[10];
     __shared__ T s_x[BS / 32];
-    const size_t base = ((size_t)blockIdx.x * BS + threadIdx.x) * E;
-    T c[E];
+    __shared__ T s_y[PTS], s_xk[PTS];
+    const size_t G = (size_t)gridDim.x * BS, g = (size_t)blockIdx.x * BS + threadIdx.x;
+    const size_t rows = (len + G - 1) / G;
+    for (uint32_t p0 = 0; p0 < npoints; p0 += PTS) {
+        __syncthreads();
+        if (threadIdx.x < PTS && p0 + threadIdx.x < npoints) {
+            s_xk[threadIdx.x] = A::konst(x[p0 + threadIdx.x]);
+            s_y[threadIdx.x] = kpow<F>(s_xk[threadIdx.x], G);
+        }
+        __syncthreads();
+        T y[PTS], s[PTS];
 #pragma unroll
-    for (int j = 0; j < E; j++) {
-        c[j] = A::zero();
-        if (base + j < len) c[j] = A::load(coeffs[base + j]);
-    }
-    for (uint32_t p = 0; p < npoints; p++) {
-        const T xk = A::konst(x[p]);
-        T s = c[E - 1];
+        for (int q = 0; q < PTS; q++) {
+            y[q] = s_y[p0 + q < npoints ? q : 0];
+            s[q] = A::zero();
+        }
+#pragma unroll 4
+        for (size_t k = rows; k-- > 0;) {
+            const size_t idx = k * G + g;
+            T c = A::zero();
+            if (idx < len) c = A::load(coeffs[idx]);
 #pragma unroll
-        for (int j = E - 2; j >= 0; j--) s = A::add(A::cmul(s, xk), c[j]);
-        T r = block_wreduce<F, BS>(s, kpow<F>(xk, E), s_w, s_x);
-        if (threadIdx.x == 0) partial[(size_t)p * gridDim.x + blockIdx.x] = r;
+            for (int q = 0; q < PTS; q++) s[q] = A::add(A::cmul(s[q], y[q]), c);
+        }
+        for (int q = 0; q < PTS && p0 + q < npoints; q++) {
+            T r = block_wreduce<F, BS>(s[q], s_xk[q], s_w, s_x);
+            if (threadIdx.x == 0) partial[(size_t)(p0 + q) * gridDim.x + blockIdx.x] = r;
+        }
     }
 }
 
