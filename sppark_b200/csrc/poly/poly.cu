@@ -6,26 +6,44 @@
 
 using namespace poly;
 
-template<class T> static constexpr int elems_per_thread() { return sizeof(T) >= 32 ? 4 : 8; }
-static constexpr int BS = 256;
+// scan shapes: E elements per thread, SBS threads per CTA.  The per-thread cost of carrying a scan
+// across lanes and warps (ten joins) is amortised over E, so the wide fields, whose join is a
+// 256-bit multiplication, take 8 per thread too and halve the CTA to keep the transpose buffer
+// inside the static shared-memory limit.
+template<class T> static constexpr int elems_per_thread() { return 8; }
+template<class T> static constexpr int scan_threads() { return sizeof(T) >= 32 ? 128 : 256; }
+static constexpr int BS = 256;                      // evaluate kernels
+
+template<class F, int OP, int MODE, bool REV>
+static uint32_t scan_capacity(const gpu_t& gpu)
+{
+    constexpr int E = elems_per_thread<typename F::T>(), SBS = scan_threads<typename F::T>();
+    static int per_sm[64];                                   // occupancy per device, looked up once
+    const int dev = gpu.cid() & 63;
+    if (per_sm[dev] == 0) {
+        int n = 0;
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, scan_kernel<F, OP, E, SBS, MODE, REV>, SBS, 0));
+        per_sm[dev] = std::max(n, 1);
+    }
+    return (uint32_t)(gpu.sm_count() * per_sm[dev]);
+}
 
 template<class F, int OP, int MODE, bool REV>
 static void scan_launch(const gpu_t& gpu, cudaStream_t stream, uint32_t grid_cap, typename F::T* out,
                         const typename F::T* in, size_t len, typename F::T z, int rotate, uint32_t ntiles,
                         typename F::T* aggs, typename F::T* edge)
 {
-    constexpr int E = elems_per_thread<typename F::T>();
-    static int per_sm[64];                                   // occupancy per device, looked up once
-    const int dev = gpu.cid() & 63;
-    if (per_sm[dev] == 0) {
-        int n = 0;
-        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, scan_kernel<F, OP, E, BS, MODE, REV>, BS, 0));
-        per_sm[dev] = std::max(n, 1);
+    constexpr int E = elems_per_thread<typename F::T>(), SBS = scan_threads<typename F::T>();
+    const uint32_t grid = std::min<uint32_t>(std::min<uint32_t>(ntiles, grid_cap), scan_capacity<F, OP, MODE, REV>(gpu));
+    if (MODE == MODE_COOP) {
+        void* args[] = {&out, &in, &len, &z, &rotate, &ntiles, &aggs, &edge};
+        CUDA_OK(cudaLaunchCooperativeKernel((const void*)scan_kernel<F, OP, E, SBS, MODE, REV>, dim3(grid), dim3(SBS),
+                                            args, 0, stream));
+    } else {
+        scan_kernel<F, OP, E, SBS, MODE, REV><<<grid, SBS, 0, stream>>>(out, in, len, z, rotate, ntiles, aggs, edge);
+        CUDA_OK(cudaGetLastError());
     }
-    const uint32_t grid = std::min<uint32_t>(std::min<uint32_t>(ntiles, grid_cap), (uint32_t)(gpu.sm_count() * per_sm[dev]));
-    scan_kernel<F, OP, E, BS, MODE, REV><<<grid, BS, 0, stream>>>(out, in, len, z, rotate, ntiles, aggs, edge);
     COUNT_LAUNCH();
-    CUDA_OK(cudaGetLastError());
 }
 
 template<class F, int OP>
@@ -33,8 +51,8 @@ static void scan(const gpu_t& gpu, cudaStream_t stream, typename F::T* out, cons
                  const typename F::T* z_host, int rotate)
 {
     typedef typename F::T T;
-    constexpr int E = elems_per_thread<T>();
-    constexpr size_t TILE = (size_t)BS * E;
+    constexpr int E = elems_per_thread<T>(), SBS = scan_threads<T>();
+    constexpr size_t TILE = (size_t)SBS * E;
     constexpr bool REV = OP == OP_DIV;
     if (len == 0) return;
     if (len > ((size_t)1 << 40)) throw cuda_error(-(int)cudaErrorInvalidValue, "polynomial: length out of range");
@@ -48,18 +66,22 @@ static void scan(const gpu_t& gpu, cudaStream_t stream, typename F::T* out, cons
         zk = arith<F>::konst(*z_host);
         zt = kpow<F>(zk, TILE);
     }
+    bool parked = rotate != 0;                               // rotate: are boundary coefficients in edge[]?
     if (ntiles <= 2) {
         scan_launch<F, OP, MODE_SERIAL, REV>(gpu, stream, 1, out, in, len, zk, rotate, ntiles, aggs, edge);
+    } else if (ntiles <= scan_capacity<F, OP, MODE_COOP, REV>(gpu) && !getenv("SPPARK_B200_POLY_NO_COOP")) {
+        scan_launch<F, OP, MODE_COOP, REV>(gpu, stream, ~0u, out, in, len, zk, rotate, ntiles, aggs, edge);
+        parked = false;
     } else {
         const uint32_t rgrid = std::min<uint32_t>(ntiles, (uint32_t)gpu.sm_count() * 8);
-        tile_reduce_kernel<F, OP, E, BS><<<rgrid, BS, 0, stream>>>(aggs, in, len, zk, REV, ntiles);
+        tile_reduce_kernel<F, OP, E, SBS><<<rgrid, SBS, 0, stream>>>(aggs, in, len, zk, REV, ntiles);
         COUNT_LAUNCH();
         CUDA_OK(cudaGetLastError());
         const uint32_t nagg_tiles = (uint32_t)((ntiles + TILE - 1) / TILE);
         scan_launch<F, OP, MODE_SERIAL, false>(gpu, stream, 1, aggs, aggs, ntiles, zt, 0, nagg_tiles, nullptr, nullptr);
         scan_launch<F, OP, MODE_SCAN, REV>(gpu, stream, ~0u, out, in, len, zk, rotate, ntiles, aggs, edge);
     }
-    if (OP == OP_DIV && rotate && ntiles > 1) {
+    if (OP == OP_DIV && parked && ntiles > 1) {
         scan_edge_kernel<T><<<(ntiles + 255) / 256, 256, 0, stream>>>(out, edge, len, ntiles, (uint32_t)TILE);
         COUNT_LAUNCH();
         CUDA_OK(cudaGetLastError());
@@ -99,7 +121,7 @@ static void batch_inverse(const gpu_t& gpu, cudaStream_t stream, typename F::T* 
                           size_t len)
 {
     typedef typename F::T T;
-    constexpr int N = elems_per_thread<T>();
+    constexpr int N = sizeof(T) >= 32 ? 4 : 8;
     constexpr int IBS = sizeof(T) >= 32 ? 512 : 256;
     if (len == 0) return;
     const size_t nchunks = (len + (size_t)IBS * N - 1) / ((size_t)IBS * N);

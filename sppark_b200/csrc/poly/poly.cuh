@@ -23,6 +23,9 @@
 #include "../ff/bb31.cuh"
 #include "../ff/mont_ntt.cuh"
 #include "../util/gpu.cuh"
+#if defined(__CUDACC__)
+# include <cooperative_groups.h>
+#endif
 
 namespace poly {
 
@@ -191,8 +194,46 @@ DEV typename F::T block_wreduce(typename F::T val, const typename F::T& base, ty
 // A decoupled look-back single pass was measured first and rejected: its carry chain advances at
 // most one 32-tile window per L2 round trip, which capped 2^24 Goldilocks elements at 230 us where
 // these three launches are bandwidth bound (profiles/poly_r02.md).  Short inputs take MODE_SERIAL
-// directly on the data (one launch).
-enum { MODE_SERIAL = 1, MODE_SCAN = 2 };
+// directly on the data (one launch).  Inputs whose tiles are all resident at once take MODE_COOP:
+// one cooperative launch, one tile per CTA kept in registers across a single grid barrier, after
+// which every CTA folds the aggregates of the tiles before it by itself (a few KB from L2) -- one
+// read and one write of the data and a third of the launch latency, which is what mid sizes cost.
+enum { MODE_SERIAL = 1, MODE_SCAN = 2, MODE_COOP = 3 };
+
+// MODE_COOP: what precedes tile `tile`, from the aggregates of tiles 0 .. tile-1 (thread 0 holds it).
+// Division: sum_j aggs[tile-1-j] * zt^j, thread t taking j = t, t+BS, ... by Horner in zt^BS.
+template<class F, int OP, int BS>
+DEV typename F::T carry_from_aggs(const typename F::T* aggs, uint32_t tile, const typename F::T& yt,
+                                  const typename F::T* s_w, typename F::T* s_x)
+{
+    typedef arith<F> A;
+    typedef typename F::T T;
+    constexpr int NW = BS / 32;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const T ident = OP == OP_MUL ? A::one() : A::zero();
+    T acc = ident;
+    if (OP == OP_DIV) {
+        if (tid < tile) {
+            for (uint32_t j = tid + (tile - 1 - tid) / BS * BS;; j -= BS) {      // largest j = tid (mod BS) below tile
+                acc = A::add(A::cmul(acc, yt), ld_cg(aggs + (tile - 1 - j)));
+                if (j < BS) break;
+            }
+        }
+        return wreduce<F, BS>(acc, s_w, s_x);
+    }
+    for (uint32_t i = tid; i < tile; i += BS) acc = join<F, OP>(acc, ld_cg(aggs + i), yt);
+#pragma unroll
+    for (uint32_t off = 16; off; off >>= 1) acc = join<F, OP>(acc, shfl_down(acc, off), yt);
+    __syncthreads();
+    if (lane == 0) s_x[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        acc = lane < NW ? s_x[lane] : ident;
+#pragma unroll
+        for (uint32_t off = NW / 2; off; off >>= 1) acc = join<F, OP>(acc, shfl_down(acc, off), yt);
+    }
+    return acc;
+}
 
 template<class F, int OP, int E, int BS, int MODE, bool REV>
 __global__ __launch_bounds__(BS) void scan_kernel(typename F::T* out, const typename F::T* in, size_t len,
@@ -204,7 +245,7 @@ __global__ __launch_bounds__(BS) void scan_kernel(typename F::T* out, const type
     constexpr int NW = BS / 32;
     constexpr uint32_t TILE = BS * E;
     constexpr int ROW = E + 1;       // padded row of the transpose
-    static_assert(BS >= 256 && NW <= 32 && (E & (E - 1)) == 0, "setup below spreads the constant table over 256 threads");
+    static_assert(NW <= 32 && (E & (E - 1)) == 0, "one warp scans the warp aggregates; E is a power of two");
     __shared__ T s_wl[33];          // z^(E k): a carry crossing k threads
     __shared__ T s_ww[NW + 1];      // z^(32 E k): crossing k warps
     __shared__ T s_zp[E + 1];       // z^k
@@ -212,17 +253,25 @@ __global__ __launch_bounds__(BS) void scan_kernel(typename F::T* out, const type
     __shared__ T s_agg[NW];
     __shared__ T s_carry;
     __shared__ T s_stage[NW][32 * ROW];
+    __shared__ T s_w2[10], s_x2[NW], s_yt;   // MODE_COOP: weights zt^(2^k), zt^BS
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const T ident = OP == OP_MUL ? A::one() : A::zero();
 
-    if (OP == OP_DIV) {
-        if (tid < 33) s_wl[tid] = kpow<F>(z, (uint64_t)E * tid);
-        else if (tid >= 64 && tid < 64 + NW + 1) s_ww[tid - 64] = kpow<F>(z, (uint64_t)32 * E * (tid - 64));
-        else if (tid >= 128 && tid < 128 + E + 1) s_zp[tid - 128] = kpow<F>(z, tid - 128);
-        else if (tid == 192) s_zt = kpow<F>(z, TILE);
+    if (OP == OP_DIV) {             // the table of powers of z, one entry per thread
+        for (uint32_t i = tid; i < 33 + (NW + 1) + (E + 1) + 1; i += BS) {
+            if (i < 33) s_wl[i] = kpow<F>(z, (uint64_t)E * i);
+            else if (i < 33 + NW + 1) s_ww[i - 33] = kpow<F>(z, (uint64_t)32 * E * (i - 33));
+            else if (i < 33 + NW + 1 + E + 1) s_zp[i - 33 - NW - 1] = kpow<F>(z, i - 33 - NW - 1);
+            else s_zt = kpow<F>(z, TILE);
+        }
     }
     if (tid == 0) s_carry = ident;
+    if (MODE == MODE_COOP && OP == OP_DIV) {
+        __syncthreads();
+        if (tid == 32) s_yt = kpow<F>(s_zt, BS);
+        wreduce_setup<F>(s_zt, s_w2);
+    }
 
     // element e = j*32 + lane of the warp's 32 E sits at stage[sidx + j * SJ] (row e / E, column e % E)
     const uint32_t sidx = (lane / E) * ROW + lane % E;
@@ -277,6 +326,13 @@ __global__ __launch_bounds__(BS) void scan_kernel(typename F::T* out, const type
             }
             if (lane < NW) s_agg[lane] = w;
             if (MODE == MODE_SCAN && lane == 0) s_carry = cprev;
+            if (MODE == MODE_COOP && lane == NW - 1) aggs[tile] = w;
+        }
+        if (MODE == MODE_COOP) {    // every tile is in registers somewhere: one barrier, then each CTA for itself
+            __threadfence();
+            cooperative_groups::this_grid().sync();
+            const T c = carry_from_aggs<F, OP, BS>(aggs, tile, s_yt, s_w2, s_x2);
+            if (tid == 0) s_carry = c;
         }
         __syncthreads();
 
@@ -305,7 +361,7 @@ __global__ __launch_bounds__(BS) void scan_kernel(typename F::T* out, const type
 #pragma unroll
             for (int j = 0; j < E; j++) {
                 const T r = stage[sidx + j * SJ];
-                if (j == E - 1 && tid == BS - 1) edge[tile] = r;
+                if (MODE != MODE_COOP && j == E - 1 && tid == BS - 1) edge[tile] = r;   // (COOP: all tiles were read)
                 else *(dst - j * 32) = r;
             }
         } else {
@@ -318,7 +374,7 @@ __global__ __launch_bounds__(BS) void scan_kernel(typename F::T* out, const type
                 if (!REV) out[pos] = r;
                 else if (!rotate) out[len - 1 - pos] = r;
                 else if (pos == len - 1) out[len - 1] = r;             // the remainder goes last
-                else if (e == 32 * E - 1 && warp == NW - 1) edge[tile] = r;
+                else if (MODE != MODE_COOP && e == 32 * E - 1 && warp == NW - 1) edge[tile] = r;
                 else out[len - 2 - pos] = r;
             }
         }

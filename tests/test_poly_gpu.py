@@ -65,12 +65,16 @@ def test_matches_the_reference_recordings(field):
             assert np.array_equal(got, g[f"eval_{n}"]), (field, n, "evaluate")
 
 
-@pytest.mark.parametrize("field", WORD_FIELDS + WIDE_FIELDS)
-def test_matches_oracle(field):
-    """seeded inputs at sizes around every level of the scan hierarchy (thread, warp, tile, the
-    32-tile look-back window) against oracle/poly.py"""
+@pytest.mark.parametrize("field,coop", [(f, True) for f in WORD_FIELDS + WIDE_FIELDS] +
+                         [("gl64", False), ("bb31", False), ("bls12_381_fr", False)])
+def test_matches_oracle(field, coop, monkeypatch):
+    """seeded inputs at sizes around every level of the scan hierarchy (thread, warp, tile, many
+    tiles) against oracle/poly.py; mid sizes run as one cooperative launch by default and as the
+    three-launch scan with SPPARK_B200_POLY_NO_COOP set (what large inputs take) -- both are checked"""
     from oracle import poly as op
     from sppark_b200 import poly
+    if not coop:
+        monkeypatch.setenv("SPPARK_B200_POLY_NO_COOP", "1")
     p, fid = op.FIELDS[field]["p"], _fid(field)
     wide = field in WIDE_FIELDS
     tile = 1024 if wide else 2048
