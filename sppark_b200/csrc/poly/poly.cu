@@ -30,13 +30,14 @@ static uint32_t scan_capacity(const gpu_t& gpu)
 
 template<class F, int OP, int MODE, bool REV>
 static void scan_launch(const gpu_t& gpu, cudaStream_t stream, uint32_t grid_cap, typename F::T* out,
-                        const typename F::T* in, size_t len, typename F::T z, int rotate, uint32_t ntiles,
-                        typename F::T* aggs, typename F::T* edge)
+                        const typename F::T* in, size_t len,
+                        const scan_tab<typename F::T, elems_per_thread<typename F::T>(), scan_threads<typename F::T>()>& z,
+                        int rotate, uint32_t ntiles, typename F::T* aggs, typename F::T* edge)
 {
     constexpr int E = elems_per_thread<typename F::T>(), SBS = scan_threads<typename F::T>();
     const uint32_t grid = std::min<uint32_t>(std::min<uint32_t>(ntiles, grid_cap), scan_capacity<F, OP, MODE, REV>(gpu));
     if (MODE == MODE_COOP) {
-        void* args[] = {&out, &in, &len, &z, &rotate, &ntiles, &aggs, &edge};
+        void* args[] = {&out, &in, &len, (void*)&z, &rotate, &ntiles, &aggs, &edge};
         CUDA_OK(cudaLaunchCooperativeKernel((const void*)scan_kernel<F, OP, E, SBS, MODE, REV>, dim3(grid), dim3(SBS),
                                             args, 0, stream));
     } else {
@@ -61,10 +62,10 @@ static void scan(const gpu_t& gpu, cudaStream_t stream, typename F::T* out, cons
     dev_ptr_t<T> scratch(2 * (size_t)ntiles, st);
     T* aggs = scratch.get();
     T* edge = aggs + ntiles;
-    T zk = arith<F>::zero(), zt = zk;
+    scan_tab<T, E, SBS> zk{}, zt{};                          // powers of z; of z^TILE for the aggregates' scan
     if (OP == OP_DIV) {
-        zk = arith<F>::konst(*z_host);
-        zt = kpow<F>(zk, TILE);
+        scan_tab_fill<F, E, SBS>(zk, arith<F>::konst(*z_host));
+        scan_tab_fill<F, E, SBS>(zt, zk.zt);
     }
     bool parked = rotate != 0;                               // rotate: are boundary coefficients in edge[]?
     if (ntiles <= 2) {
@@ -103,9 +104,17 @@ static void evaluate(const gpu_t& gpu, cudaStream_t stream, typename F::T* d_ret
                   pts == 2 ? evaluate_partial_kernel<F, BS, 2> : evaluate_partial_kernel<F, BS, 1>;
     int per_sm = 0;
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BS, 0));
-    // a resident grid, but at least 8 coefficients per thread before another CTA is worth its reduction
-    const uint32_t nparts = (uint32_t)std::max<size_t>(1, std::min<size_t>((size_t)gpu.sm_count() * std::max(per_sm, 1),
-                                                                          (len + (size_t)BS * 8 - 1) / ((size_t)BS * 8)));
+    // a resident grid, but at least 8 coefficients per thread before another CTA is worth its reduction;
+    // short polynomials stay in ONE CTA, whose "partial" is the answer itself (one launch, no scratch)
+    uint32_t nparts = (uint32_t)std::max<size_t>(1, std::min<size_t>((size_t)gpu.sm_count() * std::max(per_sm, 1),
+                                                                    (len + (size_t)BS * 8 - 1) / ((size_t)BS * 8)));
+    if (len <= ((size_t)1 << 14)) nparts = 1;
+    if (nparts == 1) {
+        kernel<<<1, BS, 0, stream>>>(d_ret, d_x, (uint32_t)n, d_coeffs, len);
+        COUNT_LAUNCH();
+        CUDA_OK(cudaGetLastError());
+        return;
+    }
     const stream_t st(stream);
     dev_ptr_t<T> partial((size_t)n * nparts, st);
     kernel<<<nparts, BS, 0, stream>>>(partial, d_x, (uint32_t)n, d_coeffs, len);
@@ -121,12 +130,28 @@ static void batch_inverse(const gpu_t& gpu, cudaStream_t stream, typename F::T* 
                           size_t len)
 {
     typedef typename F::T T;
-    constexpr int N = sizeof(T) >= 32 ? 4 : 8;
-    constexpr int IBS = sizeof(T) >= 32 ? 512 : 256;
+    constexpr bool wide = sizeof(T) >= 32;
+    constexpr int N = wide ? 4 : 8;
+    constexpr int IBS = wide ? 512 : 256;
     if (len == 0) return;
     const size_t nchunks = (len + (size_t)IBS * N - 1) / ((size_t)IBS * N);
     const uint32_t grid = (uint32_t)std::min<size_t>(nchunks, (size_t)gpu.sm_count() * 8);
-    batch_inverse_kernel<F, N, IBS><<<grid, IBS, 0, stream>>>(d_out, d_inp, len);
+    // one inversion per chunk inside the kernel: always for the word fields (their inversion is ~100 short
+    // multiplications; hoisting it measured slower, BabyBear 2^24: 127 us against 98 us), and for the wide
+    // fields while every chunk has an SM to itself (BLS12-381 fr 2^16: 249 us against 327 us hoisted)
+    if (!wide || nchunks <= 2 * (size_t)gpu.sm_count()) {
+        batch_inverse_kernel<F, N, IBS, INV_SELF><<<grid, IBS, 0, stream>>>(d_out, d_inp, len, nullptr);
+        COUNT_LAUNCH();
+        CUDA_OK(cudaGetLastError());
+        return;
+    }
+    const stream_t st(stream);
+    dev_ptr_t<T> tots(nchunks, st);
+    batch_inverse_kernel<F, N, IBS, INV_PRODUCT><<<grid, IBS, 0, stream>>>(nullptr, d_inp, len, tots);
+    COUNT_LAUNCH();
+    CUDA_OK(cudaGetLastError());
+    batch_inverse<F>(gpu, stream, tots, tots, nchunks);      // chunk products are never zero
+    batch_inverse_kernel<F, N, IBS, INV_GIVEN><<<grid, IBS, 0, stream>>>(d_out, d_inp, len, tots);
     COUNT_LAUNCH();
     CUDA_OK(cudaGetLastError());
 }

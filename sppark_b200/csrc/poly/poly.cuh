@@ -80,6 +80,40 @@ template<class F> HD typename F::T kpow(typename F::T c, uint64_t e)
     return r;
 }
 
+// The powers of z a division needs, computed ONCE on the host (about 130 field multiplications)
+// and handed to the kernels by value: a carry that crosses k elements is weighted by z^k, and every
+// level of the scan hierarchy spans a fixed number of elements.  Unused by Add / Multiply.
+template<class T, int E, int BS> struct scan_tab {
+    static constexpr int NW = BS / 32;
+    T wl[33];          // z^(E k): crossing k threads
+    T ww[NW + 1];      // z^(32 E k): crossing k warps
+    T zp[E + 1];       // z^k
+    T zt;              // z^TILE, TILE = BS E
+    T zw[10];          // z^(2^k): weights of the reduce pass's tree
+    T y;               // z^BS
+    T tw[10];          // zt^(2^k), and
+    T yt;              // zt^BS: folding tile aggregates (MODE_COOP)
+};
+template<class F, int E, int BS>
+inline void scan_tab_fill(scan_tab<typename F::T, E, BS>& t, const typename F::T& z)
+{
+    typedef arith<F> A;
+    constexpr int NW = BS / 32;
+    t.zp[0] = A::kone();
+    for (int k = 1; k <= E; k++) t.zp[k] = A::kmul(t.zp[k - 1], z);
+    t.wl[0] = A::kone();
+    for (int k = 1; k <= 32; k++) t.wl[k] = A::kmul(t.wl[k - 1], t.zp[E]);
+    t.ww[0] = A::kone();
+    for (int k = 1; k <= NW; k++) t.ww[k] = A::kmul(t.ww[k - 1], t.wl[32]);
+    t.zt = t.ww[NW];
+    t.zw[0] = z;
+    for (int k = 1; k < 10; k++) t.zw[k] = A::kmul(t.zw[k - 1], t.zw[k - 1]);
+    t.y = kpow<F>(z, BS);
+    t.tw[0] = t.zt;
+    for (int k = 1; k < 10; k++) t.tw[k] = A::kmul(t.tw[k - 1], t.tw[k - 1]);
+    t.yt = kpow<F>(t.zt, BS);
+}
+
 #if defined(__CUDACC__)
 // ---- whole-element warp shuffles and L2 loads (role of the reference's ff/shfl.cuh) --------------
 DEV uint32_t shfl_up(uint32_t v, uint32_t d) { return __shfl_up_sync(0xffffffffu, v, d); }
@@ -237,7 +271,8 @@ DEV typename F::T carry_from_aggs(const typename F::T* aggs, uint32_t tile, cons
 
 template<class F, int OP, int E, int BS, int MODE, bool REV>
 __global__ __launch_bounds__(BS) void scan_kernel(typename F::T* out, const typename F::T* in, size_t len,
-                                                  typename F::T z, int rotate, uint32_t ntiles,
+                                                  const __grid_constant__ scan_tab<typename F::T, E, BS> tab,
+                                                  int rotate, uint32_t ntiles,
                                                   typename F::T* aggs, typename F::T* edge)
 {
     typedef arith<F> A;
@@ -246,32 +281,22 @@ __global__ __launch_bounds__(BS) void scan_kernel(typename F::T* out, const type
     constexpr uint32_t TILE = BS * E;
     constexpr int ROW = E + 1;       // padded row of the transpose
     static_assert(NW <= 32 && (E & (E - 1)) == 0, "one warp scans the warp aggregates; E is a power of two");
-    __shared__ T s_wl[33];          // z^(E k): a carry crossing k threads
-    __shared__ T s_ww[NW + 1];      // z^(32 E k): crossing k warps
-    __shared__ T s_zp[E + 1];       // z^k
-    __shared__ T s_zt;              // z^TILE
+    __shared__ scan_tab<T, E, BS> s_tab;
     __shared__ T s_agg[NW];
     __shared__ T s_carry;
     __shared__ T s_stage[NW][32 * ROW];
-    __shared__ T s_w2[10], s_x2[NW], s_yt;   // MODE_COOP: weights zt^(2^k), zt^BS
+    __shared__ T s_x2[NW];
+    const T* const s_wl = s_tab.wl;
+    const T* const s_ww = s_tab.ww;
+    const T* const s_zp = s_tab.zp;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const T ident = OP == OP_MUL ? A::one() : A::zero();
 
-    if (OP == OP_DIV) {             // the table of powers of z, one entry per thread
-        for (uint32_t i = tid; i < 33 + (NW + 1) + (E + 1) + 1; i += BS) {
-            if (i < 33) s_wl[i] = kpow<F>(z, (uint64_t)E * i);
-            else if (i < 33 + NW + 1) s_ww[i - 33] = kpow<F>(z, (uint64_t)32 * E * (i - 33));
-            else if (i < 33 + NW + 1 + E + 1) s_zp[i - 33 - NW - 1] = kpow<F>(z, i - 33 - NW - 1);
-            else s_zt = kpow<F>(z, TILE);
-        }
-    }
+    if (OP == OP_DIV)
+        for (uint32_t i = tid; i < sizeof(tab) / sizeof(T); i += BS) ((T*)&s_tab)[i] = ((const T*)&tab)[i];
     if (tid == 0) s_carry = ident;
-    if (MODE == MODE_COOP && OP == OP_DIV) {
-        __syncthreads();
-        if (tid == 32) s_yt = kpow<F>(s_zt, BS);
-        wreduce_setup<F>(s_zt, s_w2);
-    }
+    const T z = OP == OP_DIV ? tab.zp[1] : ident;
 
     // element e = j*32 + lane of the warp's 32 E sits at stage[sidx + j * SJ] (row e / E, column e % E)
     const uint32_t sidx = (lane / E) * ROW + lane % E;
@@ -331,7 +356,7 @@ __global__ __launch_bounds__(BS) void scan_kernel(typename F::T* out, const type
         if (MODE == MODE_COOP) {    // every tile is in registers somewhere: one barrier, then each CTA for itself
             __threadfence();
             cooperative_groups::this_grid().sync();
-            const T c = carry_from_aggs<F, OP, BS>(aggs, tile, s_yt, s_w2, s_x2);
+            const T c = carry_from_aggs<F, OP, BS>(aggs, tile, s_tab.yt, s_tab.tw, s_x2);
             if (tid == 0) s_carry = c;
         }
         __syncthreads();
@@ -387,7 +412,8 @@ __global__ __launch_bounds__(BS) void scan_kernel(typename F::T* out, const type
 // weighted by z^t) and finishes with the weighted tree above: one multiplication per element.
 template<class F, int OP, int E, int BS>
 __global__ __launch_bounds__(BS) void tile_reduce_kernel(typename F::T* aggs, const typename F::T* in, size_t len,
-                                                         typename F::T z, int rev, uint32_t ntiles)
+                                                         const __grid_constant__ scan_tab<typename F::T, E, BS> tab,
+                                                         int rev, uint32_t ntiles)
 {
     typedef arith<F> A;
     typedef typename F::T T;
@@ -395,14 +421,13 @@ __global__ __launch_bounds__(BS) void tile_reduce_kernel(typename F::T* aggs, co
     constexpr uint32_t TILE = BS * E;
     __shared__ T s_w[10];
     __shared__ T s_x[NW];
-    __shared__ T s_y;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const T ident = OP == OP_MUL ? A::one() : A::zero();
     if (OP == OP_DIV) {
-        if (tid == 32) s_y = kpow<F>(z, BS);
-        wreduce_setup<F>(z, s_w);
+        if (tid < 10) s_w[tid] = tab.zw[tid];
+        __syncthreads();
     }
-    const T y = OP == OP_DIV ? s_y : ident;
+    const T y = OP == OP_DIV ? tab.y : ident;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t base = (size_t)tile * TILE + (OP == OP_DIV ? BS - 1 - tid : tid);
         T acc = ident;
@@ -541,9 +566,15 @@ DEV void batch_inversion(typename F::T out[N], const typename F::T inp[N])
     }
 }
 
-// the array form: every CTA shares one inversion among its BS*N elements
-template<class F, int N, int BS>
-__global__ __launch_bounds__(BS) void batch_inverse_kernel(typename F::T* out, const typename F::T* in, size_t len)
+// the array form: every CTA shares one inversion among its BS*N elements (INV_SELF).  The inversion
+// is a serial chain of a few hundred multiplications run by ONE warp, so for long arrays of wide
+// elements it is hoisted out: INV_PRODUCT writes each chunk's product to tots[], the host inverts
+// tots[] with this same routine (recursively, a 2048-fold smaller array), and INV_GIVEN finishes
+// with the chunk inverses read back -- four multiplications per element and nothing serial.
+enum { INV_SELF = 0, INV_PRODUCT = 1, INV_GIVEN = 2 };
+template<class F, int N, int BS, int MODE>
+__global__ __launch_bounds__(BS) void batch_inverse_kernel(typename F::T* out, const typename F::T* in, size_t len,
+                                                           typename F::T* tots)
 {
     typedef arith<F> A;
     typedef typename F::T T;
@@ -588,7 +619,11 @@ __global__ __launch_bounds__(BS) void batch_inverse_kernel(typename F::T* out, c
                 T u = shfl_down(ws, off);
                 if (lane + off < 32) ws = A::dmul(u, ws);
             }
-            const T total_inv = A::inv(shfl_idx(wp, 31));       // the one inversion
+            if (MODE == INV_PRODUCT) {
+                if (lane == 31) tots[chunk] = wp;
+                continue;
+            }
+            const T total_inv = MODE == INV_GIVEN ? ld_cg(tots + chunk) : A::inv(shfl_idx(wp, 31));   // the one inversion
             T wb = shfl_up(wp, 1), wf = shfl_down(ws, 1);
             if (lane == 0) wb = A::one();
             if (lane == 31) wf = A::one();
@@ -597,6 +632,7 @@ __global__ __launch_bounds__(BS) void batch_inverse_kernel(typename F::T* out, c
                 s_suf[lane] = A::dmul(wf, total_inv);
             }
         }
+        if (MODE == INV_PRODUCT) continue;
         __syncthreads();
         T inv = A::dmul(A::dmul(before, after), A::dmul(s_pre[warp], s_suf[warp]));   // 1 / a
 #pragma unroll
