@@ -59,9 +59,10 @@ static void scan(const gpu_t& gpu, cudaStream_t stream, typename F::T* out, cons
     if (len > ((size_t)1 << 40)) throw cuda_error(-(int)cudaErrorInvalidValue, "polynomial: length out of range");
     const uint32_t ntiles = (uint32_t)((len + TILE - 1) / TILE);
     const stream_t st(stream);
-    dev_ptr_t<T> scratch(2 * (size_t)ntiles, st);
+    dev_ptr_t<T> scratch(2 * (size_t)ntiles + (ntiles + TILE - 1) / TILE, st);
     T* aggs = scratch.get();
     T* edge = aggs + ntiles;
+    T* aggs2 = edge + ntiles;                                // aggregates of the aggregates' tiles
     scan_tab<T, E, SBS> zk{}, zt{};                          // powers of z; of z^TILE for the aggregates' scan
     if (OP == OP_DIV) {
         scan_tab_fill<F, E, SBS>(zk, arith<F>::konst(*z_host));
@@ -78,8 +79,13 @@ static void scan(const gpu_t& gpu, cudaStream_t stream, typename F::T* out, cons
         tile_reduce_kernel<F, OP, E, SBS><<<rgrid, SBS, 0, stream>>>(aggs, in, len, zk, REV, ntiles);
         COUNT_LAUNCH();
         CUDA_OK(cudaGetLastError());
+        // the aggregates' own scan: a few tiles; one CTA walking them serially is a chain of ~25 dependent
+        // joins per tile (BLS12-381 fr 2^22: 81 us for 4 tiles), so beyond two tiles they run side by side
         const uint32_t nagg_tiles = (uint32_t)((ntiles + TILE - 1) / TILE);
-        scan_launch<F, OP, MODE_SERIAL, false>(gpu, stream, 1, aggs, aggs, ntiles, zt, 0, nagg_tiles, nullptr, nullptr);
+        if (nagg_tiles > 2 && nagg_tiles <= scan_capacity<F, OP, MODE_COOP, false>(gpu))
+            scan_launch<F, OP, MODE_COOP, false>(gpu, stream, ~0u, aggs, aggs, ntiles, zt, 0, nagg_tiles, aggs2, nullptr);
+        else
+            scan_launch<F, OP, MODE_SERIAL, false>(gpu, stream, 1, aggs, aggs, ntiles, zt, 0, nagg_tiles, nullptr, nullptr);
         scan_launch<F, OP, MODE_SCAN, REV>(gpu, stream, ~0u, out, in, len, zk, rotate, ntiles, aggs, edge);
     }
     if (OP == OP_DIV && parked && ntiles > 1) {
