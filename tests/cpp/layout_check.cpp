@@ -26,4 +26,13 @@ static_assert(sizeof(fr_t) == 8 && alignof(fr_t) == 8, "gl64_t");
 static_assert(sizeof(fr_t) == 4, "bb31_t");
 #endif
 static_assert(sizeof(RustError) == 16 && sizeof(RustError::by_value) == 16, "RustError by value");
+
+// the polynomial/ templates keep the reference's names and argument order
+// (polynomial/prefix_op.cuh:322, div_by_x_minus_z.cuh:445, evaluate.cuh:308): instantiate each once
+RustError (*const poly_add)(fr_t*, const fr_t*, size_t, stream_t&) = &prefix_op<Add<fr_t>>;
+RustError (*const poly_mul)(fr_t*, const fr_t*, size_t, stream_t&) = &prefix_op<Multiply<fr_t>>;
+RustError (*const poly_div)(fr_t*, size_t, const fr_t&, stream_t&) = &div_by_x_minus_z<false, fr_t>;
+RustError (*const poly_rot)(fr_t*, size_t, const fr_t&, stream_t&) = &div_by_x_minus_z<true, fr_t>;
+RustError (*const poly_eval)(fr_t*, const fr_t*, size_t, const fr_t*, size_t, stream_t&) = &evaluate<fr_t>;
+RustError (*const poly_inv)(fr_t*, const fr_t*, size_t, stream_t&) = &batch_inversion<fr_t>;
 int main() { return 0; }

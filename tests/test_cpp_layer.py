@@ -30,6 +30,17 @@ def test_layouts_compile(feature):
                            os.path.join(CPP, "layout_check.cpp")])
 
 
+@pytest.mark.parametrize("feature", ["GOLDILOCKS", "BABY_BEAR", "BLS12_381"])
+def test_polynomial_headers_forward(feature):
+    """<polynomial/prefix_op.cuh>, <polynomial/div_by_x_minus_z.cuh>, <polynomial/evaluate.cuh> and
+    <ff/batch_inversion.hpp> resolve under include/compat to the same-named templates over the C ABI"""
+    src = open(os.path.join(CPP, "poly_compat_check.cpp")).read()
+    if feature != "GOLDILOCKS":
+        src = src.replace("<ff/goldilocks.hpp>", "<ff/baby_bear.hpp>" if feature == "BABY_BEAR" else "<ff/bls12-381.hpp>")
+    subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", f"-DFEATURE_{feature}",
+                    "-I" + os.path.join(ROOT, "include", "compat"), "-"], input=src, text=True, check=True)
+
+
 def test_unbuilt_curves_are_refused_at_compile_time():
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-DFEATURE_MERSENNE31", "-I" + os.path.join(ROOT, "include"),
                         os.path.join(CPP, "layout_check.cpp")], capture_output=True, text=True)
