@@ -115,7 +115,11 @@ enum { SPPARK_FIELD_GL64 = 0, SPPARK_FIELD_BB31 = 1,
 enum { SPPARK_CURVE_BLS12_381_G1 = 0, SPPARK_CURVE_PALLAS = 1, SPPARK_CURVE_VESTA = 2,
        SPPARK_CURVE_BLS12_381_G2 = 3,
        /* the other two G1 groups poc/msm-cuda builds (features bn254, bls12_377; Cargo.toml:12-17) */
-       SPPARK_CURVE_BN254_G1 = 4, SPPARK_CURVE_BLS12_377_G1 = 5 };
+       SPPARK_CURVE_BN254_G1 = 4, SPPARK_CURVE_BLS12_377_G1 = 5,
+       /* and their G2 groups (mult_pippenger_fp2_inf of those builds, pippenger_inf.cu:8-13,36-47):
+        * Fp2 = Fp[u]/(u^2 + 1) for BN254 (ff/alt_bn128-fp2.hpp), Fp[u]/(u^2 + 5) for BLS12-377
+        * (ff/bls12-377-fp2.hpp); coordinates are (c0, c1) pairs of base-field Montgomery limbs */
+       SPPARK_CURVE_BN254_G2 = 6, SPPARK_CURVE_BLS12_377_G2 = 7 };
 
 /* compute_ntt for any single-word field (the reference builds one .so per FEATURE_*) */
 RustError sppark_b200_ntt(int field, size_t device_id, void *inout, uint32_t lg_domain_size,

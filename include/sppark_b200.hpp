@@ -77,11 +77,11 @@ typedef fr_t bb31_t;
 #elif defined(FEATURE_BN254)
 typedef sppark_b200::felem_t<9, 8, -1, SPPARK_CURVE_BN254_G1> fp_t;                // ff/alt_bn128.hpp
 typedef sppark_b200::felem_t<10, 8, SPPARK_FIELD_BN254_FR, -1> fr_t;
-typedef sppark_b200::felem_t<13, 16, -1, -1> fp2_t;         // layout only: G2 is not instantiated
+typedef sppark_b200::felem_t<13, 16, -1, SPPARK_CURVE_BN254_G2> fp2_t;             // ff/alt_bn128-fp2.hpp, (c0, c1)
 #elif defined(FEATURE_BLS12_377)
 typedef sppark_b200::felem_t<11, 12, -1, SPPARK_CURVE_BLS12_377_G1> fp_t;          // ff/bls12-377.hpp
 typedef sppark_b200::felem_t<12, 8, SPPARK_FIELD_BLS12_377_FR, -1> fr_t;
-typedef sppark_b200::felem_t<14, 24, -1, -1> fp2_t;         // layout only: G2 is not instantiated
+typedef sppark_b200::felem_t<14, 24, -1, SPPARK_CURVE_BLS12_377_G2> fp2_t;         // ff/bls12-377-fp2.hpp, (c0, c1)
 #elif defined(FEATURE_MERSENNE31)
 # error "sppark_b200: Mersenne31 is not instantiated in this library (DESIGN.md section 1)"
 #endif
@@ -184,7 +184,7 @@ public:
         static_assert(sizeof(scalar_t) == 32, "scalars are 256-bit");
         static_assert(sizeof(point_t) == 3 * sizeof(field_t) && sizeof(bucket_t) == 4 * sizeof(field_t), "layout");
         (void)device_id;                                   // the MSM runs on the caller's current device
-        if constexpr (field_t::msm_curve < 0) {            // e.g. G2 of BN254 / BLS12-377
+        if constexpr (field_t::msm_curve < 0) {            // a field no curve of this library is defined over
             out.inf();
             return RustError{-1, strdup("sppark_b200: no MSM is instantiated over this field")};
         } else {

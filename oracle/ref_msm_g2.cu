@@ -14,7 +14,13 @@
  * The packed affine_t has no such field, so this instantiation is consistent and pins G2.
  */
 #include <cuda.h>
-#include <ff/bls12-381-fp2.hpp>
+#if defined(FEATURE_BN254)               /* the msm crate's other two features: same harness, their Fp2 */
+# include <ff/alt_bn128-fp2.hpp>
+#elif defined(FEATURE_BLS12_377)
+# include <ff/bls12-377-fp2.hpp>
+#else
+# include <ff/bls12-381-fp2.hpp>
+#endif
 #include <ec/jacobian_t.hpp>
 #include <ec/xyzz_t.hpp>
 

@@ -320,6 +320,89 @@ static inline void rshift_mod_384(vec384 r, const vec384 a, size_t n, const vec3
     }
     memcpy(r, t, sizeof(t));
 }
+// ---- the 256-bit members of the same family (ff/alt_bn128-fp2.hpp's host fp2_t calls them directly) ----
+namespace shim_detail {
+template<size_t N> static inline void mul_mont_n(limb_t* r, const limb_t* a, const limb_t* b, const limb_t* p, limb_t n0)
+{
+    limb_t t[N + 2] = {0};
+    for (size_t i = 0; i < N; i++) {
+        limb_t c = 0;
+        for (size_t j = 0; j < N; j++) {
+            u128 x = (u128)a[j] * b[i] + t[j] + c;
+            t[j] = (limb_t)x; c = (limb_t)(x >> 64);
+        }
+        u128 s = (u128)t[N] + c;
+        t[N] = (limb_t)s; t[N + 1] = (limb_t)(s >> 64);
+        limb_t m = t[0] * n0;
+        u128 x = (u128)m * p[0] + t[0];
+        c = (limb_t)(x >> 64);
+        for (size_t j = 1; j < N; j++) {
+            x = (u128)m * p[j] + t[j] + c;
+            t[j - 1] = (limb_t)x; c = (limb_t)(x >> 64);
+        }
+        s = (u128)t[N] + c;
+        t[N - 1] = (limb_t)s; t[N] = t[N + 1] + (limb_t)(s >> 64);
+    }
+    if (t[N] || geq<N>(t, p)) sub_n<N>(t, p);
+    memcpy(r, t, N * sizeof(limb_t));
+}
+}  // namespace shim_detail
+static inline void mul_mont_sparse_256(vec256 r, const vec256 a, const vec256 b, const vec256 p, limb_t n0)
+{   shim_detail::mul_mont_n<4>(r, a, b, p, n0);   }
+static inline void sqr_mont_sparse_256(vec256 r, const vec256 a, const vec256 p, limb_t n0)
+{   shim_detail::mul_mont_n<4>(r, a, a, p, n0);   }
+static inline void from_mont_256(vec256 r, const vec256 a, const vec256 p, limb_t n0)
+{
+    const vec256 one = {1};
+    shim_detail::mul_mont_n<4>(r, a, one, p, n0);
+}
+static inline void add_mod_256(vec256 r, const vec256 a, const vec256 b, const vec256 p)
+{
+    typedef shim_detail::u128 u128;
+    limb_t t[4], c = 0;
+    for (size_t i = 0; i < 4; i++) { u128 x = (u128)a[i] + b[i] + c; t[i] = (limb_t)x; c = (limb_t)(x >> 64); }
+    if (c || shim_detail::geq<4>(t, p)) shim_detail::sub_n<4>(t, p);
+    memcpy(r, t, sizeof(vec256));
+}
+static inline void sub_mod_256(vec256 r, const vec256 a, const vec256 b, const vec256 p)
+{
+    typedef shim_detail::u128 u128;
+    limb_t t[4], br = 0;
+    for (size_t i = 0; i < 4; i++) { u128 x = (u128)a[i] - b[i] - br; t[i] = (limb_t)x; br = (limb_t)(x >> 64) & 1; }
+    if (br) shim_detail::add_n<4>(t, p);
+    memcpy(r, t, sizeof(vec256));
+}
+static inline void cneg_mod_256(vec256 r, const vec256 a, bool flag, const vec256 p)
+{
+    if (flag && !vec_is_zero(a, sizeof(vec256))) {
+        const vec256 zero = {0};
+        sub_mod_256(r, zero, a, p);
+    } else {
+        memmove(r, a, sizeof(vec256));
+    }
+}
+static inline void lshift_mod_256(vec256 r, const vec256 a, size_t n, const vec256 p)
+{
+    vec256 t;
+    memcpy(t, a, sizeof(t));
+    while (n--) add_mod_256(t, t, t, p);
+    memcpy(r, t, sizeof(t));
+}
+static inline void rshift_mod_256(vec256 r, const vec256 a, size_t n, const vec256 p)
+{
+    typedef shim_detail::u128 u128;
+    limb_t t[4];
+    memcpy(t, a, sizeof(t));
+    while (n--) {
+        limb_t c = 0;
+        if (t[0] & 1)
+            for (size_t i = 0; i < 4; i++) { u128 x = (u128)t[i] + p[i] + c; t[i] = (limb_t)x; c = (limb_t)(x >> 64); }
+        for (size_t i = 0; i < 3; i++) t[i] = (t[i] >> 1) | (t[i + 1] << 63);
+        t[3] = (t[3] >> 1) | (c << 63);
+    }
+    memcpy(r, t, sizeof(t));
+}
+
 static inline void add_mod_384x(vec384x r, const vec384x a, const vec384x b, const vec384 p)
 {   add_mod_384(r[0], a[0], b[0], p); add_mod_384(r[1], a[1], b[1], p);   }
 static inline void sub_mod_384x(vec384x r, const vec384x a, const vec384x b, const vec384 p)

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("SPPARK_B200_LIB") or os.path.join(HERE, "libsppark_b200.so")   # override: experiments only
 
 SOURCES = ["api.cu", "util/gpu.cu", "ntt/ntt.cu", "ntt/ntt_warp.cu", "poly/poly.cu", "msm/msm.cu", "msm/msm_bls12_381.cu", "msm/msm_bls12_381_g2.cu",
-           "msm/msm_pasta.cu", "msm/msm_bn254_bls12_377.cu"]
+           "msm/msm_pasta.cu", "msm/msm_bn254_bls12_377.cu", "msm/msm_bn254_g2.cu", "msm/msm_bls12_377_g2.cu"]
 # the wide-product variants of the hot-loop multiplications (dedicated squaring, single-reduction
 # a*b - c*d, Karatsuba; ff/mont.cuh) measured SLOWER than the fused ladder on B200 (round 1:
 # accumulate 2^24: fused 111 ms, +msub 115, +sqr 126, +both 130), so they are compiled out

@@ -3,90 +3,67 @@
 #include <thread>
 #include <vector>
 
-RustError msm_host_bls12_381(void*, const void*, size_t, const void*, size_t, bool, bool);
-RustError msm_dev_bls12_381(void*, const void*, size_t, const void*, void*);
-RustError msm_host_pallas(void*, const void*, size_t, const void*, size_t, bool, bool);
-RustError msm_dev_pallas(void*, const void*, size_t, const void*, void*);
-RustError msm_host_vesta(void*, const void*, size_t, const void*, size_t, bool, bool);
-RustError msm_dev_vesta(void*, const void*, size_t, const void*, void*);
+// one row per curve id (SPPARK_CURVE_*): the six entry points its translation unit defines
+// (msm_bls12_381.cu, msm_pasta.cu, msm_bn254_bls12_377.cu, msm_*_g2.cu) and its packed layouts
+#define CURVE_DECLS(name)                                                                          \
+    RustError msm_host_##name(void*, const void*, size_t, const void*, size_t, bool, bool);        \
+    RustError msm_dev_##name(void*, const void*, size_t, const void*, void*);                      \
+    RustError gen_points_##name(void*, size_t, void*);                                             \
+    RustError combine_##name(void*, const void*, size_t);                                          \
+    RustError msm_preload_##name(const void*, size_t, size_t, bool, void**);                       \
+    RustError msm_resident_##name(void*, const void*, size_t, const void*, bool);
+CURVE_DECLS(bls12_381) CURVE_DECLS(pallas) CURVE_DECLS(vesta) CURVE_DECLS(bls12_381_g2)
+CURVE_DECLS(bn254) CURVE_DECLS(bls12_377) CURVE_DECLS(bn254_g2) CURVE_DECLS(bls12_377_g2)
 
-RustError msm_host_bls12_381_g2(void*, const void*, size_t, const void*, size_t, bool, bool);
-RustError msm_dev_bls12_381_g2(void*, const void*, size_t, const void*, void*);
-RustError gen_points_bls12_381_g2(void*, size_t, void*);
-RustError combine_bls12_381_g2(void*, const void*, size_t);
-RustError msm_host_bn254(void*, const void*, size_t, const void*, size_t, bool, bool);
-RustError msm_dev_bn254(void*, const void*, size_t, const void*, void*);
-RustError gen_points_bn254(void*, size_t, void*);
-RustError combine_bn254(void*, const void*, size_t);
-RustError msm_host_bls12_377(void*, const void*, size_t, const void*, size_t, bool, bool);
-RustError msm_dev_bls12_377(void*, const void*, size_t, const void*, void*);
-RustError gen_points_bls12_377(void*, size_t, void*);
-RustError combine_bls12_377(void*, const void*, size_t);
-RustError msm_preload_bls12_381(const void*, size_t, size_t, bool, void**);
-RustError msm_resident_bls12_381(void*, const void*, size_t, const void*, bool);
-RustError msm_preload_bls12_381_g2(const void*, size_t, size_t, bool, void**);
-RustError msm_resident_bls12_381_g2(void*, const void*, size_t, const void*, bool);
-RustError msm_preload_pallas(const void*, size_t, size_t, bool, void**);
-RustError msm_resident_pallas(void*, const void*, size_t, const void*, bool);
-RustError msm_preload_vesta(const void*, size_t, size_t, bool, void**);
-RustError msm_resident_vesta(void*, const void*, size_t, const void*, bool);
-RustError msm_preload_bn254(const void*, size_t, size_t, bool, void**);
-RustError msm_resident_bn254(void*, const void*, size_t, const void*, bool);
-RustError msm_preload_bls12_377(const void*, size_t, size_t, bool, void**);
-RustError msm_resident_bls12_377(void*, const void*, size_t, const void*, bool);
-RustError gen_points_bls12_381(void*, size_t, void*);
-RustError gen_points_pallas(void*, size_t, void*);
-RustError gen_points_vesta(void*, size_t, void*);
-RustError combine_bls12_381(void*, const void*, size_t);
-RustError combine_pallas(void*, const void*, size_t);
-RustError combine_vesta(void*, const void*, size_t);
+struct curve_ops {
+    RustError (*host)(void*, const void*, size_t, const void*, size_t, bool, bool);
+    RustError (*dev)(void*, const void*, size_t, const void*, void*);
+    RustError (*gen)(void*, size_t, void*);
+    RustError (*combine)(void*, const void*, size_t);
+    RustError (*preload)(const void*, size_t, size_t, bool, void**);
+    RustError (*resident)(void*, const void*, size_t, const void*, bool);
+    size_t affine_bytes, jacobian_bytes;        // packed {X, Y} and {X, Y, Z}
+};
+#define CURVE_ROW(name, affine, jac)                                                               \
+    {msm_host_##name, msm_dev_##name, gen_points_##name, combine_##name, msm_preload_##name,       \
+     msm_resident_##name, affine, jac}
+static const curve_ops CURVES[] = {
+    CURVE_ROW(bls12_381, 96, 144),        // SPPARK_CURVE_BLS12_381_G1
+    CURVE_ROW(pallas, 64, 96),            // SPPARK_CURVE_PALLAS
+    CURVE_ROW(vesta, 64, 96),             // SPPARK_CURVE_VESTA
+    CURVE_ROW(bls12_381_g2, 192, 288),    // SPPARK_CURVE_BLS12_381_G2
+    CURVE_ROW(bn254, 64, 96),             // SPPARK_CURVE_BN254_G1
+    CURVE_ROW(bls12_377, 96, 144),        // SPPARK_CURVE_BLS12_377_G1
+    CURVE_ROW(bn254_g2, 128, 192),        // SPPARK_CURVE_BN254_G2
+    CURVE_ROW(bls12_377_g2, 192, 288),    // SPPARK_CURVE_BLS12_377_G2
+};
+static_assert(sizeof(CURVES) / sizeof(CURVES[0]) == SPPARK_CURVE_BLS12_377_G2 + 1, "one row per curve id");
+static const curve_ops* curve_of(int curve)
+{   return curve < 0 || curve > SPPARK_CURVE_BLS12_377_G2 ? nullptr : &CURVES[curve];   }
 
 extern "C" RustError sppark_b200_generate_points_dev(int curve, void* d_out, size_t n, void* stream)
 {
     if (n >= (1ull << 31)) return rust_err(-(int)cudaErrorInvalidValue, "generate_points: n too large");
-    switch (curve) {
-    case SPPARK_CURVE_BLS12_381_G1: return gen_points_bls12_381(d_out, n, stream);
-    case SPPARK_CURVE_PALLAS: return gen_points_pallas(d_out, n, stream);
-    case SPPARK_CURVE_VESTA: return gen_points_vesta(d_out, n, stream);
-    case SPPARK_CURVE_BLS12_381_G2: return gen_points_bls12_381_g2(d_out, n, stream);
-    case SPPARK_CURVE_BN254_G1: return gen_points_bn254(d_out, n, stream);
-    case SPPARK_CURVE_BLS12_377_G1: return gen_points_bls12_377(d_out, n, stream);
-    default: return rust_err(-(int)cudaErrorInvalidValue, "generate_points: unknown curve");
-    }
+    const curve_ops* c = curve_of(curve);
+    if (c == nullptr) return rust_err(-(int)cudaErrorInvalidValue, "generate_points: unknown curve");
+    return c->gen(d_out, n, stream);
 }
 
 extern "C" RustError sppark_b200_msm_combine(int curve, void* out, const void* partials, size_t count)
 {
-    switch (curve) {
-    case SPPARK_CURVE_BLS12_381_G1: return combine_bls12_381(out, partials, count);
-    case SPPARK_CURVE_PALLAS: return combine_pallas(out, partials, count);
-    case SPPARK_CURVE_VESTA: return combine_vesta(out, partials, count);
-    case SPPARK_CURVE_BLS12_381_G2: return combine_bls12_381_g2(out, partials, count);
-    case SPPARK_CURVE_BN254_G1: return combine_bn254(out, partials, count);
-    case SPPARK_CURVE_BLS12_377_G1: return combine_bls12_377(out, partials, count);
-    default: return rust_err(-(int)cudaErrorInvalidValue, "msm_combine: unknown curve");
-    }
+    const curve_ops* c = curve_of(curve);
+    if (c == nullptr) return rust_err(-(int)cudaErrorInvalidValue, "msm_combine: unknown curve");
+    return c->combine(out, partials, count);
 }
 
+// ffi_affine_sz: 0 = packed {X, Y}; larger than that = arkworks rows with an infinity flag after Y
 static RustError msm_any(int curve, void* out, const void* points, size_t npoints, const void* scalars,
                          size_t ffi_affine_sz, bool mont)
 {
-    switch (curve) {
-    case SPPARK_CURVE_BLS12_381_G1:
-        return msm_host_bls12_381(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 96, ffi_affine_sz > 96, mont);
-    case SPPARK_CURVE_PALLAS:
-        return msm_host_pallas(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 64, ffi_affine_sz > 64, mont);
-    case SPPARK_CURVE_VESTA:
-        return msm_host_vesta(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 64, ffi_affine_sz > 64, mont);
-    case SPPARK_CURVE_BLS12_381_G2:
-        return msm_host_bls12_381_g2(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 192, ffi_affine_sz > 192, mont);
-    case SPPARK_CURVE_BN254_G1:
-        return msm_host_bn254(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 64, ffi_affine_sz > 64, mont);
-    case SPPARK_CURVE_BLS12_377_G1:
-        return msm_host_bls12_377(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : 96, ffi_affine_sz > 96, mont);
-    default:
-        return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_msm: unknown curve");
-    }
+    const curve_ops* c = curve_of(curve);
+    if (c == nullptr) return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_msm: unknown curve");
+    return c->host(out, points, npoints, scalars, ffi_affine_sz ? ffi_affine_sz : c->affine_bytes,
+                   ffi_affine_sz > c->affine_bytes, mont);
 }
 
 extern "C" RustError sppark_b200_msm(int curve, void* out, const void* points, size_t npoints,
@@ -100,15 +77,9 @@ extern "C" RustError sppark_b200_msm_ex(int curve, void* out, const void* points
 extern "C" RustError sppark_b200_msm_dev(int curve, void* out, const void* d_points, size_t npoints,
                                          const void* d_scalars, void* stream)
 {
-    switch (curve) {
-    case SPPARK_CURVE_BLS12_381_G1: return msm_dev_bls12_381(out, d_points, npoints, d_scalars, stream);
-    case SPPARK_CURVE_PALLAS: return msm_dev_pallas(out, d_points, npoints, d_scalars, stream);
-    case SPPARK_CURVE_VESTA: return msm_dev_vesta(out, d_points, npoints, d_scalars, stream);
-    case SPPARK_CURVE_BLS12_381_G2: return msm_dev_bls12_381_g2(out, d_points, npoints, d_scalars, stream);
-    case SPPARK_CURVE_BN254_G1: return msm_dev_bn254(out, d_points, npoints, d_scalars, stream);
-    case SPPARK_CURVE_BLS12_377_G1: return msm_dev_bls12_377(out, d_points, npoints, d_scalars, stream);
-    default: return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_msm_dev: unknown curve");
-    }
+    const curve_ops* c = curve_of(curve);
+    if (c == nullptr) return rust_err(-(int)cudaErrorInvalidValue, "sppark_b200_msm_dev: unknown curve");
+    return c->dev(out, d_points, npoints, d_scalars, stream);
 }
 
 // ---- one MSM sharded by point-chunk over several GPUs of this process --------
@@ -117,32 +88,15 @@ extern "C" RustError sppark_b200_msm_dev(int curve, void* out, const void* d_poi
 // own PCIe link), the partial results -- one Jacobian point each -- are added on the first device.
 // No collective library is needed inside one process: the "all-gather" of the multi-process
 // route (sppark_b200/parallel.py over NCCL) is a host array here.
-static size_t jacobian_bytes(int curve)
-{
-    switch (curve) {
-    case SPPARK_CURVE_BLS12_381_G1: case SPPARK_CURVE_BLS12_377_G1: return 144;
-    case SPPARK_CURVE_BLS12_381_G2: return 288;
-    default: return 96;
-    }
-}
-static size_t packed_affine_bytes(int curve)
-{
-    switch (curve) {
-    case SPPARK_CURVE_BLS12_381_G1: case SPPARK_CURVE_BLS12_377_G1: return 96;
-    case SPPARK_CURVE_BLS12_381_G2: return 192;
-    default: return 64;
-    }
-}
-
 extern "C" RustError sppark_b200_msm_sharded(int curve, void* out, const void* points, size_t npoints,
                                              const void* scalars, size_t ffi_affine_sz, int scalars_mont,
                                              const int* device_ids, size_t ndev)
 {
-    if (curve < 0 || curve > SPPARK_CURVE_BLS12_377_G1)
-        return rust_err(-(int)cudaErrorInvalidValue, "msm_sharded: unknown curve");
+    const curve_ops* c = curve_of(curve);
+    if (c == nullptr) return rust_err(-(int)cudaErrorInvalidValue, "msm_sharded: unknown curve");
     if (out == nullptr || ndev == 0 || ndev > 64 || device_ids == nullptr)
         return rust_err(-(int)cudaErrorInvalidValue, "msm_sharded: need 1..64 device ids");
-    const size_t jb = jacobian_bytes(curve), stride = ffi_affine_sz ? ffi_affine_sz : packed_affine_bytes(curve);
+    const size_t jb = c->jacobian_bytes, stride = ffi_affine_sz ? ffi_affine_sz : c->affine_bytes;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess) return rust_err(-(int)cudaErrorNoDevice, "msm_sharded: no CUDA device");
     for (size_t i = 0; i < ndev; i++)
@@ -203,16 +157,10 @@ extern "C" RustError sppark_b200_msm_ctx_create(int curve, const void* points, s
     if (out == nullptr) return rust_err(-(int)cudaErrorInvalidValue, "msm_ctx_create: null output");
     *out = nullptr;
     void* d = nullptr;
-    RustError e;
-    switch (curve) {
-    case SPPARK_CURVE_BLS12_381_G1: e = msm_preload_bls12_381(points, npoints, ffi_affine_sz ? ffi_affine_sz : 96, ffi_affine_sz > 96, &d); break;
-    case SPPARK_CURVE_PALLAS: e = msm_preload_pallas(points, npoints, ffi_affine_sz ? ffi_affine_sz : 64, ffi_affine_sz > 64, &d); break;
-    case SPPARK_CURVE_VESTA: e = msm_preload_vesta(points, npoints, ffi_affine_sz ? ffi_affine_sz : 64, ffi_affine_sz > 64, &d); break;
-    case SPPARK_CURVE_BLS12_381_G2: e = msm_preload_bls12_381_g2(points, npoints, ffi_affine_sz ? ffi_affine_sz : 192, ffi_affine_sz > 192, &d); break;
-    case SPPARK_CURVE_BN254_G1: e = msm_preload_bn254(points, npoints, ffi_affine_sz ? ffi_affine_sz : 64, ffi_affine_sz > 64, &d); break;
-    case SPPARK_CURVE_BLS12_377_G1: e = msm_preload_bls12_377(points, npoints, ffi_affine_sz ? ffi_affine_sz : 96, ffi_affine_sz > 96, &d); break;
-    default: return rust_err(-(int)cudaErrorInvalidValue, "msm_ctx_create: unknown curve");
-    }
+    const curve_ops* c = curve_of(curve);
+    if (c == nullptr) return rust_err(-(int)cudaErrorInvalidValue, "msm_ctx_create: unknown curve");
+    RustError e = c->preload(points, npoints, ffi_affine_sz ? ffi_affine_sz : c->affine_bytes,
+                             ffi_affine_sz > c->affine_bytes, &d);
     if (e.code != 0) return e;
     int dev = 0;
     (void)cudaGetDevice(&dev);
@@ -228,15 +176,7 @@ extern "C" RustError sppark_b200_msm_ctx_invoke(sppark_b200_msm_ctx* ctx, void* 
     int cur = 0;
     (void)cudaGetDevice(&cur);
     if (cur != ctx->device) return rust_err(-(int)cudaErrorInvalidDevice, "msm_ctx_invoke: the points live on another device");
-    const bool mont = scalars_mont != 0;
-    switch (ctx->curve) {
-    case SPPARK_CURVE_BLS12_381_G1: return msm_resident_bls12_381(out, ctx->d_points, npoints, scalars, mont);
-    case SPPARK_CURVE_PALLAS: return msm_resident_pallas(out, ctx->d_points, npoints, scalars, mont);
-    case SPPARK_CURVE_VESTA: return msm_resident_vesta(out, ctx->d_points, npoints, scalars, mont);
-    case SPPARK_CURVE_BLS12_381_G2: return msm_resident_bls12_381_g2(out, ctx->d_points, npoints, scalars, mont);
-    case SPPARK_CURVE_BN254_G1: return msm_resident_bn254(out, ctx->d_points, npoints, scalars, mont);
-    default: return msm_resident_bls12_377(out, ctx->d_points, npoints, scalars, mont);
-    }
+    return curve_of(ctx->curve)->resident(out, ctx->d_points, npoints, scalars, scalars_mont != 0);
 }
 
 extern "C" void sppark_b200_msm_ctx_free(sppark_b200_msm_ctx* ctx)

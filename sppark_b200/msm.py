@@ -9,8 +9,8 @@ import numpy as np
 
 from . import _lib
 
-BLS12_381_G1, PALLAS, VESTA, BLS12_381_G2, BN254_G1, BLS12_377_G1 = 0, 1, 2, 3, 4, 5
-_LIMBS = {BLS12_381_G1: 6, PALLAS: 4, VESTA: 4, BLS12_381_G2: 12, BN254_G1: 4, BLS12_377_G1: 6}    # 64-bit limbs per coordinate
+BLS12_381_G1, PALLAS, VESTA, BLS12_381_G2, BN254_G1, BLS12_377_G1, BN254_G2, BLS12_377_G2 = 0, 1, 2, 3, 4, 5, 6, 7
+_LIMBS = {BLS12_381_G1: 6, PALLAS: 4, VESTA: 4, BLS12_381_G2: 12, BN254_G1: 4, BLS12_377_G1: 6, BN254_G2: 8, BLS12_377_G2: 12}    # 64-bit limbs per coordinate
 
 
 def _check(points, scalars):

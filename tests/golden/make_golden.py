@@ -9,6 +9,8 @@
                     (G1, arkworks layout with infinity flags): `... make_golden.py g2` on a GPU.
   msm_curves2_ref_gpu.npz  the reference's CUDA MSM for BN254 and BLS12-377 G1: `... make_golden.py curves2`.
   msm_pasta_ref_gpu.npz    the reference's CUDA MSM templates for Pallas and Vesta: `... make_golden.py pasta`.
+  msm_g2_<curve>_ref_gpu.npz  the reference's CUDA MSM over Fp2 for BN254 and BLS12-377 (G2):
+                    `... make_golden.py g2_bn254|g2_bls12_377`.
   poly_<field>_ref_gpu.npz  the reference's polynomial/ templates (prefix_op, div_by_x_minus_z,
                     evaluate) through oracle/ref_poly.cu: `... make_golden.py poly_gl64|poly_bb31|poly_bls12_381_fr`.
   msm_ref_cpu.npz   the reference's CPU msm/pippenger.hpp (oracle/_ref/libref_msm_cpu.so);
@@ -373,6 +375,39 @@ def gen_poly(outdir, field):
     print(f"wrote poly_{field}_ref_gpu.npz")
 
 
+def gen_g2_curve(outdir, name):
+    """msm_g2_<curve>_ref_gpu.npz: the reference's CUDA MSM templates over Fp2 for the msm crate's
+    bn254 / bls12_377 features (oracle/ref_msm_g2.cu built with FEATURE_BN254 / FEATURE_BLS12_377:
+    packed affine rows, see that file for why not mult_pippenger_fp2_inf itself).  Points are
+    multiples of an order-r point (oracle/g2py.py), so every scalar below r is legitimate."""
+    import random
+    from oracle import g2py
+    c = g2py.curve(name + "_g2")
+    ref = C.CDLL(o.ref_path(f"libref_msm_g2_packed_{name}_gpu.so"))
+    ref.ref_mult_pippenger_fp2.restype = RE
+    ref.ref_mult_pippenger_fp2.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    rnd = random.Random(c.nl)
+    base = g2py.multiples(c, 64)
+    out, k = {}, 0
+    for n in (1, 2, 33, 200, 1000):
+        pts = [base[rnd.randrange(64)] for _ in range(n)]
+        sc = [rnd.randrange(c.r) for _ in range(n)]
+        if n > 10:
+            pts[3] = None                                   # infinity row (all zero)
+            sc[5], sc[6], sc[7] = 0, 1, c.r - 1
+            pts[9], sc[9] = pts[8], sc[8]                   # the same term twice
+            pts[11] = c.neg(pts[10])                        # P and -P in one bucket
+            sc[11] = sc[10]
+        rows, srows = c.encode_affine(pts), g2py.scalars_to_rows(sc)
+        jac = np.zeros(6 * c.nl, dtype=np.uint64)
+        ok(ref.ref_mult_pippenger_fp2(jac.ctypes.data, rows.ctypes.data, n, srows.ctypes.data), f"{name} g2 n={n}")
+        out[f"points{k}"], out[f"scalars{k}"], out[f"out{k}"] = rows, srows, jac
+        k += 1
+    out["ncases"] = np.int64(k)
+    np.savez_compressed(os.path.join(outdir, f"msm_g2_{name}_ref_gpu.npz"), **out)
+    print(f"wrote msm_g2_{name}_ref_gpu.npz")
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "cpu"
     if mode == "cpu":
@@ -394,6 +429,8 @@ if __name__ == "__main__":
             gen_ntt256(outdir)
         elif mode == "msm":
             gen_msm(outdir)
+        elif mode in ("g2_bn254", "g2_bls12_377"):
+            gen_g2_curve(outdir, mode[3:])
         elif mode.startswith("poly_"):
             gen_poly(outdir, mode[5:])
         else:

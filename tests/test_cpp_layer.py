@@ -176,6 +176,21 @@ def test_reference_poc_glue_runs_on_this_library(oracle):
         assert glue.mult_pippenger_inf(o2.ctypes.data, ark.ctypes.data, 500, sc2.ctypes.data, ark.strides[0]).code == 0
         w2 = oracle.msm(curve, np.ascontiguousarray(ark[:, :2 * nl]), sc2, "pippenger", ncpus=8)
         assert np.array_equal(oracle.jac_to_affine(curve, o2), oracle.jac_to_affine(curve, w2)), curve
+        # the same glue's G2 entry (pippenger_inf.cu:36-47 over that feature's fp2_t), arkworks G2Affine rows
+        from oracle import g2py
+        c = g2py.curve(curve + "_g2")
+        glue.mult_pippenger_fp2_inf.restype = RE
+        glue.mult_pippenger_fp2_inf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        base = g2py.multiples(c, 16)
+        idx = [rnd.randrange(16) for _ in range(60)]
+        g2rows = np.zeros((60, 4 * c.nl + 1), dtype=np.uint64)
+        g2rows[:, :4 * c.nl] = c.encode_affine([base[i] for i in idx])
+        g2rows[7, 4 * c.nl] = 1                              # flagged infinity
+        o3 = np.zeros(6 * c.nl, dtype=np.uint64)
+        assert glue.mult_pippenger_fp2_inf(o3.ctypes.data, g2rows.ctypes.data, 60, sc2.ctypes.data, g2rows.strides[0]).code == 0
+        ks = [int(sum(int(v) << (64 * j) for j, v in enumerate(row))) for row in sc2[:60]]
+        pts = [None if i == 7 else base[idx[i]] for i in range(60)]
+        assert c.jacobian_to_affine(o3) == c.msm(pts, ks), curve + " G2 through the reference's glue"
     rng = np.random.default_rng(5)
     for lib, dt, p, ofn in (("libdropin_ntt_gl64.so", np.uint64, GL_P, oracle.ntt_gl64),
                             ("libdropin_ntt_bb31.so", np.uint32, 0x78000001, oracle.ntt_bb31)):

@@ -29,10 +29,15 @@ def best(fn, reps=4):
 def main():
     ref_dir = os.path.join(ROOT, "oracle", "_ref")
     cases = [("bls12_381_g2", msm.BLS12_381_G2, 12, "libref_msm_g2_packed_gpu.so", "ref_mult_pippenger_fp2", False),
+             ("bn254_g2", msm.BN254_G2, 8, "libref_msm_g2_packed_bn254_gpu.so", "ref_mult_pippenger_fp2", False),
+             ("bls12_377_g2", msm.BLS12_377_G2, 12, "libref_msm_g2_packed_bls12_377_gpu.so", "ref_mult_pippenger_fp2", False),
              ("bn254", msm.BN254_G1, 4, "libref_msm_bn254_gpu.so", "mult_pippenger_inf", True),
              ("bls12_377", msm.BLS12_377_G1, 6, "libref_msm_bls12_377_gpu.so", "mult_pippenger_inf", True),
              ("bls12_381_g1", msm.BLS12_381_G1, 6, "libref_msm_gpu.so", "mult_pippenger", False)]
+    only = sys.argv[1:]
     for name, cid, nl, lib, sym, inf in cases:
+        if only and name not in only:
+            continue
         for lg in (16, 20, 22):
             n = 1 << lg
             base = msm.generate_points_dev(cid, 1 << 12)
