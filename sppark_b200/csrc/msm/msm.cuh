@@ -400,14 +400,18 @@ template<class F> struct Par4 {
 // combine level (see combine_body) with four lanes per item: the chains of a level are G x 3 full
 // additions long and there are only a few thousand items, so latency, not throughput, sets its
 // time; the additions run as four rounds of lane-parallel products
+// four-lane groups per CTA: 20 field elements of shared memory each (30 KB for 48-byte Fp at 32
+// groups; Fp2 elements are twice as wide, so half as many groups)
+template<class F> struct par_groups { static constexpr uint32_t value = F::N <= 12 ? 32 : 16; };
+
 template<class F>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(4 * par_groups<F>::value)
 combine_par_kernel(const uint32_t* inR, const uint32_t* inS, uint32_t G, uint32_t lg_span,
                    uint32_t nitems, uint32_t* outR, uint32_t* outS)
 {
-    __shared__ F sm[32][20];                                // per group: acc, weighted, rsum, 8 scratch
+    __shared__ F sm[par_groups<F>::value][20];                   // per group: acc, weighted, rsum, 8 scratch
     const uint32_t grp = threadIdx.x >> 2, lane = threadIdx.x & 3;
-    const uint32_t item = blockIdx.x * 32 + grp;
+    const uint32_t item = blockIdx.x * par_groups<F>::value + grp;
     if (item >= nitems) return;                             // whole groups leave together
     const unsigned mask = 0xFu << ((threadIdx.x & 31) & ~3u);
     F* base = sm[grp];
@@ -653,20 +657,16 @@ public:
                 uint32_t lg_g = 31 - __builtin_clz(per_win);
                 if (lg_g > 4) lg_g = 4;                         // radix 16 keeps the serial chains short
                 uint32_t G = 1u << lg_g, nitems = cfg.nwins * (per_win >> lg_g);
-                if constexpr (F::N <= 12)
-                    combine_par_kernel<F><<<(nitems + 31) / 32, 128, 0, stream>>>(j.R[cur], j.S[cur], G, lg_span, nitems,
-                                                                                  j.R[cur ^ 1], j.S[cur ^ 1]);
-                else
-                    combine_kernel<F><<<(nitems + 127) / 128, 128, 0, stream>>>(j.R[cur], j.S[cur], G, lg_span, nitems,
-                                                                               j.R[cur ^ 1], j.S[cur ^ 1]);
+                constexpr uint32_t PG = par_groups<F>::value;
+                combine_par_kernel<F><<<(nitems + PG - 1) / PG, 4 * PG, 0, stream>>>(j.R[cur], j.S[cur], G, lg_span, nitems,
+                                                                                     j.R[cur ^ 1], j.S[cur ^ 1]);
                 COUNT_LAUNCH();
                 per_win >>= lg_g;
                 lg_span += lg_g;
                 cur ^= 1;
             }
             g_profile.mark("finish", stream);
-            if constexpr (F::N <= 12) finish_par_kernel<F><<<1, 32, 0, stream>>>(cfg, j.R[cur], d_out);
-            else finish_kernel<F><<<1, 32, 0, stream>>>(cfg, j.R[cur], d_out);        // Fp2 (G2): one lane
+            finish_par_kernel<F><<<1, 32, 0, stream>>>(cfg, j.R[cur], d_out);
             COUNT_LAUNCH();
             g_profile.mark("end", stream);
             CUDA_OK(cudaGetLastError());
