@@ -47,6 +47,21 @@ static void scan_launch(const gpu_t& gpu, cudaStream_t stream, uint32_t grid_cap
     COUNT_LAUNCH();
 }
 
+// a cooperative launch can be refused where an ordinary one is not (a device or a partition without
+// cooperative-launch support, a grid the driver will not co-schedule): the plain launches still work
+template<class Launch> static bool try_coop(Launch&& launch)
+{
+    try {
+        launch();
+        return true;
+    } catch (const cuda_error& e) {
+        if (e.code() == -(int)cudaErrorCooperativeLaunchTooLarge || e.code() == -(int)cudaErrorNotSupported ||
+            e.code() == -(int)cudaErrorLaunchOutOfResources)
+            return false;
+        throw;
+    }
+}
+
 template<class F, int OP>
 static void scan(const gpu_t& gpu, cudaStream_t stream, typename F::T* out, const typename F::T* in, size_t len,
                  const typename F::T* z_host, int rotate)
@@ -71,8 +86,8 @@ static void scan(const gpu_t& gpu, cudaStream_t stream, typename F::T* out, cons
     bool parked = rotate != 0;                               // rotate: are boundary coefficients in edge[]?
     if (ntiles <= 2) {
         scan_launch<F, OP, MODE_SERIAL, REV>(gpu, stream, 1, out, in, len, zk, rotate, ntiles, aggs, edge);
-    } else if (ntiles <= scan_capacity<F, OP, MODE_COOP, REV>(gpu) && !getenv("SPPARK_B200_POLY_NO_COOP")) {
-        scan_launch<F, OP, MODE_COOP, REV>(gpu, stream, ~0u, out, in, len, zk, rotate, ntiles, aggs, edge);
+    } else if (ntiles <= scan_capacity<F, OP, MODE_COOP, REV>(gpu) && !getenv("SPPARK_B200_POLY_NO_COOP") &&
+               try_coop([&] { scan_launch<F, OP, MODE_COOP, REV>(gpu, stream, ~0u, out, in, len, zk, rotate, ntiles, aggs, edge); })) {
         parked = false;
     } else {
         const uint32_t rgrid = std::min<uint32_t>(ntiles, (uint32_t)gpu.sm_count() * 8);
@@ -82,9 +97,8 @@ static void scan(const gpu_t& gpu, cudaStream_t stream, typename F::T* out, cons
         // the aggregates' own scan: a few tiles; one CTA walking them serially is a chain of ~25 dependent
         // joins per tile (BLS12-381 fr 2^22: 81 us for 4 tiles), so beyond two tiles they run side by side
         const uint32_t nagg_tiles = (uint32_t)((ntiles + TILE - 1) / TILE);
-        if (nagg_tiles > 2 && nagg_tiles <= scan_capacity<F, OP, MODE_COOP, false>(gpu))
-            scan_launch<F, OP, MODE_COOP, false>(gpu, stream, ~0u, aggs, aggs, ntiles, zt, 0, nagg_tiles, aggs2, nullptr);
-        else
+        if (!(nagg_tiles > 2 && nagg_tiles <= scan_capacity<F, OP, MODE_COOP, false>(gpu) &&
+              try_coop([&] { scan_launch<F, OP, MODE_COOP, false>(gpu, stream, ~0u, aggs, aggs, ntiles, zt, 0, nagg_tiles, aggs2, nullptr); })))
             scan_launch<F, OP, MODE_SERIAL, false>(gpu, stream, 1, aggs, aggs, ntiles, zt, 0, nagg_tiles, nullptr, nullptr);
         scan_launch<F, OP, MODE_SCAN, REV>(gpu, stream, ~0u, out, in, len, zk, rotate, ntiles, aggs, edge);
     }
