@@ -642,7 +642,70 @@ def bench_reference_gpu(args, torch, msm, ntt, _lib, pts_host, sc_host, ours_res
         out["ntt"] = res
     except Exception as e:
         out["ntt"] = {"error": f"{type(e).__name__}: {e}"}
+    try:
+        out["polynomial"] = bench_polynomial(args, torch, _lib, refdir)
+    except Exception as e:
+        out["polynomial"] = {"error": f"{type(e).__name__}: {e}"}
     return out
+
+
+def bench_polynomial(args, torch, _lib, refdir):
+    """SURVEY.md section 8 row f4 next to the reference's own polynomial/ kernels (oracle/ref_poly.cu
+    built for sm_100a): Goldilocks, 2^lg_ntt elements resident in HBM (128 MiB at 2^24, larger
+    than L2), CUDA events on the stream each side launches on, mean of 10 calls back to back."""
+    path = os.path.join(refdir, "libref_poly_gl64_gpu.so")
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    ref = C.CDLL(path)
+    ref.ref_poly_stream.restype = C.c_void_p
+    ref.ref_prefix_op_dev.argtypes = [C.c_int, C.c_void_p, C.c_size_t]
+    ref.ref_div_by_x_minus_z_dev.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+    ref.ref_evaluate_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    l = _lib.lib()
+    n = 1 << args.lg_ntt
+    host = np.random.default_rng(11).integers(0, GL_P, size=n, dtype=np.uint64)
+    d = torch.from_numpy(host.view(np.int64)).cuda()
+    z = np.array([123456789], dtype=np.uint64)
+    xs = torch.tensor([3], dtype=torch.int64, device="cuda")
+    r1, r2 = torch.zeros_like(xs), torch.zeros_like(xs)
+    cur, rs = torch.cuda.current_stream(), torch.cuda.ExternalStream(ref.ref_poly_stream())
+    s = cur.cuda_stream
+
+    def timed(fn, stream, iters=10):
+        for _ in range(3):
+            fn()
+        stream.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e3
+
+    rows = {}
+    for name, mine, theirs in (
+            ("prefix_add", lambda: l.sppark_b200_prefix_op_dev(0, 0, d.data_ptr(), d.data_ptr(), n, s),
+             lambda: ref.ref_prefix_op_dev(0, d.data_ptr(), n)),
+            ("prefix_multiply", lambda: l.sppark_b200_prefix_op_dev(0, 1, d.data_ptr(), d.data_ptr(), n, s),
+             lambda: ref.ref_prefix_op_dev(1, d.data_ptr(), n)),
+            ("div_by_x_minus_z", lambda: l.sppark_b200_div_by_x_minus_z_dev(0, d.data_ptr(), n, z.ctypes.data, 0, s),
+             lambda: ref.ref_div_by_x_minus_z_dev(d.data_ptr(), n, z.ctypes.data, 0)),
+            ("evaluate_1_point", lambda: l.sppark_b200_evaluate_dev(0, r1.data_ptr(), xs.data_ptr(), 1, d.data_ptr(), n, s),
+             lambda: ref.ref_evaluate_dev(r2.data_ptr(), xs.data_ptr(), 1, d.data_ptr(), n))):
+        ours_us, ref_us = timed(mine, cur), timed(theirs, rs)
+        rows[name] = {"ours_us": ours_us, "reference_us": ref_us, "speedup": ref_us / ours_us}
+    torch.cuda.synchronize()
+    rows["evaluate_1_point"]["same_value"] = bool(torch.equal(r1, r2))
+    # the two sides' division of the same polynomial, bit for bit
+    a = torch.from_numpy(host.view(np.int64)).cuda()
+    b = a.clone()
+    _lib.check(l.sppark_b200_div_by_x_minus_z_dev(0, a.data_ptr(), n, z.ctypes.data, 0, s))
+    if ref.ref_div_by_x_minus_z_dev(b.data_ptr(), n, z.ctypes.data, 0) != 0:
+        raise RuntimeError("reference div_by_x_minus_z failed")
+    torch.cuda.synchronize()
+    rows["div_by_x_minus_z"]["bit_identical"] = bool(torch.equal(a, b))
+    return {"workload": f"Goldilocks, 2^{args.lg_ntt} elements, device resident", **rows}
 
 
 def bench_ntt(args, torch, ntt, _lib, peak, peak_src, barrier, max_over_ranks, world):
