@@ -290,6 +290,13 @@ inline uint32_t choose_wbits(size_t npoints)
     for (uint32_t c = 4; c <= 22; c++) {
         uint32_t nwins = (256 + c - 1) / c;
         double cost = (double)nwins * (1.11 * (double)npoints + 5.5 * (double)(1u << (c - 1)));
+        // a top window of only a few bits puts npoints / 2^e entries into each of its 2^e buckets: the
+        // count / scatter atomics collide on them and they go through the heavy-bucket path.  Measured
+        // at 2^23 points (the per-GPU share of the 8-GPU run): c = 18 (e = 4) 65.4 ms, c = 19 (e = 9)
+        // 64.6 ms against c = 16 (no thin window) 62.6 ms, where this model without the term ranks
+        // 18 first.  Left alone below 2^22 points, where the table was tuned without it.
+        const uint32_t e = 256 - (nwins - 1) * c;                 // bits of the top window
+        if (npoints >= ((size_t)1 << 22) && e <= 10 && (npoints >> e) > 2048) cost += 1.25 * (double)npoints;
         if (cost < best_cost) { best_cost = cost; best = c; }
     }
     if (const char* env = getenv("SPPARK_B200_MSM_WBITS")) {
