@@ -4,9 +4,10 @@
 //
 // The reference writes each of these as ONE cooperative kernel with grid-wide barriers between a
 // local phase, a cross-block carry phase and an apply phase.  Here:
-//  * prefix_op and div_by_x_minus_z are the same tiled scan in three ordinary launches (tile
-//    aggregates, a one-CTA scan of the aggregates, rescan with carries): no grid barrier, no
-//    cooperative launch, no ordering between CTAs.  Division by (x - z) is the scan of
+//  * prefix_op and div_by_x_minus_z are the same tiled scan.  Long inputs: three ordinary launches
+//    (tile aggregates, a scan of the aggregates, rescan with carries), no ordering between CTAs;
+//    inputs whose tiles are all resident: ONE cooperative launch with a single grid barrier, the
+//    tile kept in registers across it; up to two tiles: one plain launch.  Division by (x - z) is the scan of
 //    b[i] = c[i] + z * b[i+1]  from the top coefficient down: the carry that crosses k elements
 //    is weighted by z^k, and since every level of the hierarchy (thread, lane, warp, tile) spans
 //    a fixed number of elements the weights are a handful of constants held in shared memory;
@@ -15,7 +16,8 @@
 //    coefficient and point, contiguous reads) followed by  sum_t s_t * x^t  over the CTA by
 //    shuffles, one partial per CTA and a one-CTA finish per point.
 //  * batch inversion shares ONE field inversion per CTA: prefix and suffix products over the CTA
-//    give every thread the inverse of its own chunk product.
+//    give every thread the inverse of its own chunk product; for long arrays of wide elements the
+//    inversions themselves are batched the same way, one level up.
 // All arithmetic is on the field's memory format (arith<F> below), the same the NTT entry points
 // use, so buffers pass between NTT and these helpers unchanged.
 #pragma once
@@ -406,7 +408,7 @@ __global__ __launch_bounds__(BS) void scan_kernel(typename F::T* out, const type
     }
 }
 
-// MODE_REDUCE without the scan: a tile's aggregate needs no per-element prefix, so thread t takes
+// The first of the three launches: a tile's aggregate needs no per-element prefix, so thread t takes
 // the tile's positions t, t+BS, ... (contiguous per warp, no transpose).  Add / Multiply fold them
 // in any order; division runs Horner in z^BS over its positions (mirrored, so that thread t ends up
 // weighted by z^t) and finishes with the weighted tree above: one multiplication per element.
